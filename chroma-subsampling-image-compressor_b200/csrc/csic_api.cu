@@ -1,0 +1,372 @@
+// Device half of the C ABI: contexts, plan construction, the device / band / host entry points.
+// No CPU compute path exists here: every process call ends in a kernel launch or an error code.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "csic_internal.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int cuda_fail(cudaError_t e, const char* what) {
+  g_last_error = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+  return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInitializationError)
+             ? CSIC_ENODEVICE
+             : (e == cudaErrorMemoryAllocation ? CSIC_ENOMEM : CSIC_ECUDA);
+}
+
+#define CSIC_CUDA(call)                                   \
+  do {                                                    \
+    cudaError_t e__ = (call);                             \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+constexpr int kPipe = 3;   // chunks in flight in csic_process_host
+
+}  // namespace
+
+struct csic_ctx {
+  int device = 0;
+  int sm_count = 0;
+  size_t max_smem_optin = 0;
+  cudaStream_t stream = nullptr;             // default compute stream
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  void* d_in[kPipe] = {nullptr, nullptr, nullptr};
+  void* d_out[kPipe] = {nullptr, nullptr, nullptr};
+  size_t d_in_cap = 0, d_out_cap = 0;
+  cudaEvent_t ev_h2d[kPipe], ev_k[kPipe], ev_d2h[kPipe];
+  int last_family = 0;
+  int64_t launches = 0;
+  int opt_family = 0;
+  size_t opt_chunk_bytes = 64u << 20;
+  int opt_ctas_per_sm = 0;
+  int opt_stages = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int build_plan(const csic_params& p, const void* d_rgb, void* d_out, size_t n_frames, int32_t row0,
+               int32_t rows, csic::KPlan& k) {
+  const csic::Geometry g = csic::geometry(p);
+  std::memset(&k, 0, sizeof(k));
+  k.in = static_cast<const uint8_t*>(d_rgb);
+  k.out = static_cast<uint8_t*>(d_out);
+  k.in_frame_bytes = g.in_frame_bytes;
+  k.out_frame_bytes = g.out_frame_bytes;
+  if (g.in_row_bytes > 0xFFFFFFFFull || g.out_row_bytes > 0xFFFFFFFFull) return CSIC_EINVAL_DIMS;
+  if ((uint64_t)g.out_w * (uint64_t)g.out_h >= (1ull << 31) || (uint64_t)p.width * p.height >= (1ull << 31))
+    return CSIC_EINVAL_DIMS;   // the reference's counters are far narrower; 2^31 pixels per frame is our limit
+  k.in_row_bytes = (uint32_t)g.in_row_bytes;
+  k.out_row_bytes = (uint32_t)g.out_row_bytes;
+  k.W = p.width;
+  k.H = p.height;
+  k.Wo = g.out_w;
+  k.Ho = g.out_h;
+  k.f = p.factor;
+  k.hf = g.hf;
+  k.vf = g.vf;
+  k.last_sample_col = ((p.width - 1) / g.hf) * g.hf;
+  k.case_b = (!g.chroma_first && p.factor > 1) ? 1 : 0;
+  k.quant_first = g.quant_first ? 1 : 0;
+  k.trunc = p.round_mode == CSIC_ROUND_TRUNC;
+  k.average = (p.pool_mode == CSIC_POOL_AVERAGE && p.factor > 1) ? 1 : 0;
+  if (p.out_format == CSIC_OUT_YCC888) k.kformat = csic::KF_YCC888;
+  else if (p.out_format == CSIC_OUT_RGB888) k.kformat = csic::KF_RGB888;
+  else k.kformat = g.out_px_bytes == 1 ? csic::KF_SLOT8 : (g.out_px_bytes == 2 ? csic::KF_SLOT16 : csic::KF_SLOT32);
+  k.slot_bytes = g.out_px_bytes;
+  k.slots_per_row = k.kformat <= csic::KF_RGB888 ? g.out_w : (int32_t)(g.out_row_bytes / (size_t)g.out_px_bytes);
+  k.sy = 8 - p.y_bits;
+  k.scb = 8 - p.cb_bits;
+  k.scr = 8 - p.cr_bits;
+  k.cb_bits = p.cb_bits;
+  k.cr_bits = p.cr_bits;
+  k.qmask = ((0xFFu << k.sy) & 0xFFu) | (((0xFFu << k.scb) & 0xFFu) << 8) | (((0xFFu << k.scr) & 0xFFu) << 16);
+  k.row0 = row0;
+  k.band_rows = rows;
+  if (n_frames > 0xFFFFFFFFull) return CSIC_EINVAL_ARG;
+  k.n_frames = (uint32_t)n_frames;
+  return CSIC_OK;
+}
+
+int run(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t n_frames, void* d_out, int32_t row0,
+        int32_t rows, void* cuda_stream) {
+  if (!ctx || !p) return CSIC_EINVAL_ARG;
+  int rc = csic_validate(p, nullptr, 0);
+  if (rc != CSIC_OK) return rc;
+  if (n_frames == 0 || rows == 0) return CSIC_OK;
+  if (!d_rgb || !d_out) return CSIC_EINVAL_ARG;
+  csic::KPlan k;
+  rc = build_plan(*p, d_rgb, d_out, n_frames, row0, rows, k);
+  if (rc != CSIC_OK) return rc;
+  if (row0 < 0 || rows < 0 || row0 + rows > k.Ho) return CSIC_EINVAL_ARG;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+  int err;
+  if (ctx->opt_family != 1 && csic::plan_rows_kernel(k, ctx->sm_count, ctx->max_smem_optin, ctx->opt_stages)) {
+    err = csic::launch_rows(k, ctx->sm_count, ctx->opt_ctas_per_sm, st);
+    ctx->last_family = 2;
+  } else {
+    err = csic::launch_generic(k, st);
+    ctx->last_family = 1;
+  }
+  ctx->launches += 1;
+  if (err != (int)cudaSuccess) return cuda_fail((cudaError_t)err, "kernel launch");
+  return CSIC_OK;
+}
+
+int ensure_staging(csic_ctx* ctx, size_t in_bytes, size_t out_bytes) {
+  if (in_bytes > ctx->d_in_cap) {
+    for (int i = 0; i < kPipe; ++i) {
+      if (ctx->d_in[i]) cudaFree(ctx->d_in[i]);
+      ctx->d_in[i] = nullptr;
+    }
+    ctx->d_in_cap = 0;
+    for (int i = 0; i < kPipe; ++i) CSIC_CUDA(cudaMalloc(&ctx->d_in[i], in_bytes));
+    ctx->d_in_cap = in_bytes;
+  }
+  if (out_bytes > ctx->d_out_cap) {
+    for (int i = 0; i < kPipe; ++i) {
+      if (ctx->d_out[i]) cudaFree(ctx->d_out[i]);
+      ctx->d_out[i] = nullptr;
+    }
+    ctx->d_out_cap = 0;
+    for (int i = 0; i < kPipe; ++i) CSIC_CUDA(cudaMalloc(&ctx->d_out[i], out_bytes));
+    ctx->d_out_cap = out_bytes;
+  }
+  return CSIC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* csic_last_error(void) { return g_last_error.c_str(); }
+
+int csic_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cuda_fail(e, "cudaGetDeviceCount");
+    return CSIC_ENODEVICE;
+  }
+  return n;
+}
+
+int csic_create(int device, csic_ctx** out) {
+  if (!out) return CSIC_EINVAL_ARG;
+  *out = nullptr;
+  int n = csic_device_count();
+  if (n <= 0) return CSIC_ENODEVICE;
+  if (device < 0 || device >= n) return CSIC_EINVAL_ARG;
+  csic_ctx* c = new (std::nothrow) csic_ctx();
+  if (!c) return CSIC_ENOMEM;
+  c->device = device;
+  DeviceGuard guard(device);
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaGetDeviceProperties"); }
+  if (prop.major < 10) {   // the row kernel is written for sm_100a only; there is no other build
+    delete c;
+    g_last_error = "device is not sm_100 (Blackwell B200); this library is built for sm_100a only";
+    return CSIC_ENODEVICE;
+  }
+  c->sm_count = prop.multiProcessorCount;
+  c->max_smem_optin = prop.sharedMemPerBlockOptin;
+  bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; ok && i < kPipe; ++i)
+    ok = cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming) == cudaSuccess;
+  if (ok) ok = csic::rows_kernel_set_attributes(c->max_smem_optin) == (int)cudaSuccess;
+  if (!ok) {
+    int rc = cuda_fail(cudaGetLastError(), "csic_create");
+    delete c;
+    return rc == CSIC_OK ? CSIC_ECUDA : rc;
+  }
+  *out = c;
+  return CSIC_OK;
+}
+
+int csic_destroy(csic_ctx* ctx) {
+  if (!ctx) return CSIC_OK;
+  DeviceGuard guard(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->s_h2d);
+  cudaStreamSynchronize(ctx->s_d2h);
+  for (int i = 0; i < kPipe; ++i) {
+    if (ctx->d_in[i]) cudaFree(ctx->d_in[i]);
+    if (ctx->d_out[i]) cudaFree(ctx->d_out[i]);
+    cudaEventDestroy(ctx->ev_h2d[i]);
+    cudaEventDestroy(ctx->ev_k[i]);
+    cudaEventDestroy(ctx->ev_d2h[i]);
+  }
+  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->s_h2d);
+  cudaStreamDestroy(ctx->s_d2h);
+  delete ctx;
+  return CSIC_OK;
+}
+
+int csic_set_option(csic_ctx* ctx, int option, int64_t value) {
+  if (!ctx) return CSIC_EINVAL_ARG;
+  switch (option) {
+    case CSIC_OPT_KERNEL_FAMILY:
+      if (value != 0 && value != 1) return CSIC_EINVAL_ARG;
+      ctx->opt_family = (int)value;
+      return CSIC_OK;
+    case CSIC_OPT_HOST_CHUNK_BYTES:
+      if (value < 0) return CSIC_EINVAL_ARG;
+      ctx->opt_chunk_bytes = value == 0 ? (64u << 20) : (size_t)value;
+      return CSIC_OK;
+    case CSIC_OPT_GRID_CTAS_PER_SM:
+      if (value < 0 || value > 32) return CSIC_EINVAL_ARG;
+      ctx->opt_ctas_per_sm = (int)value;
+      return CSIC_OK;
+    case CSIC_OPT_STAGES:
+      if (value < 0 || value > 16 || value == 1) return CSIC_EINVAL_ARG;
+      ctx->opt_stages = (int)value;
+      return CSIC_OK;
+    default:
+      return CSIC_EINVAL_ARG;
+  }
+}
+
+int csic_process_device(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t n_frames, void* d_out,
+                        void* cuda_stream) {
+  if (!p) return CSIC_EINVAL_ARG;
+  int rc = csic_validate(p, nullptr, 0);
+  if (rc != CSIC_OK) return rc;
+  const csic::Geometry g = csic::geometry(*p);
+  return run(ctx, p, d_rgb, n_frames, d_out, 0, g.out_h, cuda_stream);
+}
+
+int csic_process_band(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t n_frames, void* d_out,
+                      int32_t out_row0, int32_t out_rows, void* cuda_stream) {
+  return run(ctx, p, d_rgb, n_frames, d_out, out_row0, out_rows, cuda_stream);
+}
+
+// Input rows a band of output rows reads: the rows it decimates / pools from, plus -- when the band
+// starts on a line whose chroma is held from the line above -- the row holding that sample.
+int csic_band_input_rows(const csic_params* p, int32_t out_row0, int32_t out_rows, int32_t* in_row0,
+                         int32_t* in_rows) {
+  int rc = csic_validate(p, nullptr, 0);
+  if (rc != CSIC_OK) return rc;
+  const csic::Geometry g = csic::geometry(*p);
+  if (out_row0 < 0 || out_rows <= 0 || out_row0 + out_rows > g.out_h) return CSIC_EINVAL_ARG;
+  const int f = p->factor;
+  const bool avg = p->pool_mode == CSIC_POOL_AVERAGE && f > 1;
+  int64_t lo = (int64_t)out_row0 * f;
+  int64_t hi = (int64_t)(out_row0 + out_rows - 1) * f + (avg ? f - 1 : 0);   // inclusive
+  const bool case_b = !g.chroma_first && f > 1;
+  if (!case_b) {
+    if (g.vf == 2 && (lo & 1)) lo -= 1;   // only possible for f == 1
+  } else {
+    // chroma runs on the decimated stream with full-size counters: walk the band's first and last
+    // stream elements back to their sources (ImageCompressorTop.scala:52-58).
+    const int64_t W = p->width, Wo = g.out_w;
+    const int64_t last = ((W - 1) / g.hf) * g.hf;
+    auto src_row = [&](int64_t m) {
+      const int64_t col = m % W, line = (m / W) % p->height;
+      const int64_t s = (g.vf == 2 && (line & 1)) ? (line - 1) * W + last : m - col % g.hf;
+      return (s / Wo) * f;
+    };
+    lo = std::min(lo, src_row((int64_t)out_row0 * Wo));
+    lo = std::min(lo, src_row((int64_t)out_row0 * Wo + Wo - 1));
+  }
+  hi = std::min<int64_t>(hi, p->height - 1);
+  if (in_row0) *in_row0 = (int32_t)lo;
+  if (in_rows) *in_rows = (int32_t)(hi - lo + 1);
+  return CSIC_OK;
+}
+
+int csic_process_host(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, size_t n_frames, uint8_t* out) {
+  if (!ctx || !p) return CSIC_EINVAL_ARG;
+  int rc = csic_validate(p, nullptr, 0);
+  if (rc != CSIC_OK) return rc;
+  if (n_frames == 0) return CSIC_OK;
+  if (!rgb || !out) return CSIC_EINVAL_ARG;
+  const csic::Geometry g = csic::geometry(*p);
+  DeviceGuard guard(ctx->device);
+
+  // Frames per chunk: ~opt_chunk_bytes of input, at least one frame, at most what is there.
+  size_t per = std::max<size_t>(1, ctx->opt_chunk_bytes / std::max<size_t>(1, g.in_frame_bytes));
+  per = std::min(per, n_frames);
+  rc = ensure_staging(ctx, per * g.in_frame_bytes, per * g.out_frame_bytes);
+  if (rc != CSIC_OK) return rc;
+
+  const size_t n_chunks = (n_frames + per - 1) / per;
+  for (size_t c = 0; c < n_chunks; ++c) {
+    const int b = (int)(c % kPipe);
+    const size_t f0 = c * per, nf = std::min(per, n_frames - f0);
+    if (c >= (size_t)kPipe) {
+      // buffer reuse: the kernel that read d_in[b] and the copy that drained d_out[b] must be done
+      CSIC_CUDA(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_k[b], 0));
+      CSIC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));
+    }
+    CSIC_CUDA(cudaMemcpyAsync(ctx->d_in[b], rgb + f0 * g.in_frame_bytes, nf * g.in_frame_bytes,
+                              cudaMemcpyHostToDevice, ctx->s_h2d));
+    CSIC_CUDA(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
+    CSIC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
+    rc = run(ctx, p, ctx->d_in[b], nf, ctx->d_out[b], 0, g.out_h, ctx->stream);
+    if (rc != CSIC_OK) return rc;
+    CSIC_CUDA(cudaEventRecord(ctx->ev_k[b], ctx->stream));
+    CSIC_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_k[b], 0));
+    CSIC_CUDA(cudaMemcpyAsync(out + f0 * g.out_frame_bytes, ctx->d_out[b], nf * g.out_frame_bytes,
+                              cudaMemcpyDeviceToHost, ctx->s_d2h));
+    CSIC_CUDA(cudaEventRecord(ctx->ev_d2h[b], ctx->s_d2h));
+  }
+  CSIC_CUDA(cudaStreamSynchronize(ctx->s_d2h));
+  CSIC_CUDA(cudaStreamSynchronize(ctx->stream));
+  CSIC_CUDA(cudaStreamSynchronize(ctx->s_h2d));
+  return CSIC_OK;
+}
+
+int csic_host_alloc(size_t bytes, void** out) {
+  if (!out) return CSIC_EINVAL_ARG;
+  *out = nullptr;
+  if (csic_device_count() <= 0) return CSIC_ENODEVICE;
+  CSIC_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+  return CSIC_OK;
+}
+
+int csic_host_free(void* p) {
+  if (!p) return CSIC_OK;
+  CSIC_CUDA(cudaFreeHost(p));
+  return CSIC_OK;
+}
+
+int csic_synchronize(csic_ctx* ctx) {
+  if (!ctx) return CSIC_EINVAL_ARG;
+  DeviceGuard guard(ctx->device);
+  CSIC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CSIC_OK;
+}
+
+int csic_last_kernel(const csic_ctx* ctx, int32_t* family, int64_t* launches_total) {
+  if (!ctx) return CSIC_EINVAL_ARG;
+  if (family) *family = ctx->last_family;
+  if (launches_total) *launches_total = ctx->launches;
+  return CSIC_OK;
+}
+
+}  // extern "C"

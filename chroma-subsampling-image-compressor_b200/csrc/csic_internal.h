@@ -1,0 +1,70 @@
+// Internal declarations shared by the host half (csic_params.cpp, csic_api.cu) and the kernels.
+#ifndef CSIC_INTERNAL_H_
+#define CSIC_INTERNAL_H_
+
+#include <cstddef>
+#include <cstdint>
+
+#include "../../include/csic.h"
+
+namespace csic {
+
+struct Geometry {
+  int32_t out_w, out_h;
+  size_t in_row_bytes, in_frame_bytes;
+  size_t out_row_bytes, out_frame_bytes;
+  int32_t out_px_bytes;      // 3 for YCC888/RGB888, slot bytes (1/2/4) for bundles
+  bool chroma_first;         // ChromaSubsampling precedes SpatialSampling in op1..op3
+  bool quant_first;          // ColorQuantization precedes SpatialSampling (only matters for AVERAGE)
+  int32_t hf, vf;            // ChromaSubsampler.scala:26-27
+};
+
+int slot_bits(const csic_params& p);
+Geometry geometry(const csic_params& p);
+
+// Kernel-side output format after resolving the bundle slot width.
+enum KFormat : int32_t { KF_YCC888 = 0, KF_RGB888 = 1, KF_SLOT8 = 2, KF_SLOT16 = 3, KF_SLOT32 = 4 };
+
+// Everything a kernel needs, passed by value (lives in the constant bank).
+struct KPlan {
+  const uint8_t* in;
+  uint8_t* out;
+  uint64_t in_frame_bytes, out_frame_bytes;
+  uint32_t in_row_bytes, out_row_bytes;
+  int32_t W, H, Wo, Ho;
+  int32_t f;
+  int32_t hf, vf, last_sample_col;       // ((W-1)/hf)*hf : last chroma sample column of a line
+  int32_t case_b;                        // spatial before chroma with f > 1 (misaligned counters)
+  int32_t quant_first, trunc, average;
+  int32_t kformat, slot_bytes, slots_per_row;
+  int32_t sy, scb, scr;                  // 8 - target bits
+  int32_t cb_bits, cr_bits;
+  int32_t row0, band_rows;               // output rows [row0, row0 + band_rows) of every frame
+  uint32_t n_frames;
+  // ---- TMA row kernel only ----
+  int32_t hfe;                           // chroma hold width in *output* pixels inside a 4-pixel granule
+  int32_t nsplit, tile_px;               // tiles per output row, output pixels per tile
+  uint32_t tile_in_bytes, tile_out_bytes;
+  uint32_t n_tiles;
+  int32_t stages;
+  uint32_t stage_stride, out_buf_off, out_buf_stride, meta_off, bar_off, smem_bytes;
+  uint32_t qmask;                        // my | mcb<<8 | mcr<<16 (per-channel keep masks)
+};
+
+struct LaunchInfo {
+  int family;      // 1 generic gather kernel, 2 TMA-staged row kernel
+  int launches;
+};
+
+// Fills the TMA-row-kernel fields of `k`; returns false when the configuration is not eligible
+// (then the generic kernel runs).  `sm_count`/`max_smem` come from the device.
+bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_stages);
+
+// Both return a cudaError_t as int.
+int launch_generic(const KPlan& k, void* stream);
+int launch_rows(const KPlan& k, int sm_count, int force_ctas_per_sm, void* stream);
+int rows_kernel_set_attributes(size_t max_smem_optin);
+
+}  // namespace csic
+
+#endif  // CSIC_INTERNAL_H_

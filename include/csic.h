@@ -28,6 +28,12 @@ extern "C" {
 
 #define CSIC_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define CSIC_API __attribute__((visibility("default")))
+#else
+#define CSIC_API
+#endif
+
 /* ProcessingStep ids -- src/main/scala/jpeg/ImageCompressorTop.scala:7-9 (ChiselEnum declaration order). */
 enum csic_step {
   CSIC_STEP_NOOP = 0,              /* exists in the enum, rejected by the top (:27-31) */
@@ -99,46 +105,46 @@ typedef struct csic_ctx csic_ctx;   /* one per (host thread, GPU); not thread-sa
 
 /* Defaults of `ImageCompressionApp` (ImageCompressorTopApp.scala:164-173): a=b=4, 8/8/8 bits, sf=8,
  * spatial -> color -> chroma; FLOOR, DECIMATE, YCC888. */
-int csic_params_default(int32_t width, int32_t height, csic_params* out);
+CSIC_API int csic_params_default(int32_t width, int32_t height, csic_params* out);
 
 /* `ImageProcessorParams(width,height,factor,chromaParamA,chromaParamB)` + `class ImageProcessor`
  * (ImageProcessor.scala:15-63): fixed order toYC -> chroma -> spatial, no quantiser (8/8/8), and the
  * extra divisibility requirement (:25). */
-int csic_params_from_image_processor(int32_t width, int32_t height, int32_t factor, int32_t chroma_a,
+CSIC_API int csic_params_from_image_processor(int32_t width, int32_t height, int32_t factor, int32_t chroma_a,
                                      int32_t chroma_b, csic_params* out);
 
 /* Legacy surface `ImageCompressorTop(w,h,ChromaSubsamplingMode,QuantizationMode,factor)`:
  * CHROMA_444/422/420 -> (4,4)/(2,2)/(2,0); Q_24BIT/Q_16BIT/Q_8BIT -> (8,8,8)/(6,5,5)/(3,3,2);
  * order chroma -> color -> spatial. */
-int csic_params_from_legacy(int32_t width, int32_t height, int32_t chroma_mode, int32_t quant_mode,
+CSIC_API int csic_params_from_legacy(int32_t width, int32_t height, int32_t chroma_mode, int32_t quant_mode,
                             int32_t factor, csic_params* out);
 
 /* All `require(...)` predicates of ChromaSubsampler.scala:13-18, ColorQuantizer.scala:12-15,
  * SpatialDownsampler.scala:7-8, ImageCompressorTop.scala:27-31.  On failure writes the reference's
  * message text (NUL terminated, truncated to n) into msg when msg != NULL. */
-int csic_validate(const csic_params* p, char* msg, size_t n);
+CSIC_API int csic_validate(const csic_params* p, char* msg, size_t n);
 
 /* Output geometry.  out_w x out_h = ceil(W/f) x ceil(H/f): what the DUT emits
  * (SpatialDownsamplerSpec.scala:120-123); bytes_per_frame includes BUNDLE row padding. */
-int csic_out_shape(const csic_params* p, int32_t* out_w, int32_t* out_h, size_t* out_row_bytes,
+CSIC_API int csic_out_shape(const csic_params* p, int32_t* out_w, int32_t* out_h, size_t* out_row_bytes,
                    size_t* out_bytes_per_frame);
 
 /* `ImageCompressionApp.parseProcessingStep` (ImageCompressorTopApp.scala:154-161): case-insensitive
  * "spatial"|"spatialsampling" -> 1, "color"|"colorquantization" -> 2, "chroma"|"chromasubsampling" -> 3,
  * anything else -> CSIC_EINVAL_OPS. */
-int csic_parse_step(const char* name);
+CSIC_API int csic_parse_step(const char* name);
 
-const char* csic_strerror(int status);
-const char* csic_last_error(void);  /* thread-local text of the last CSIC_ECUDA */
-int csic_abi_version(void);
+CSIC_API const char* csic_strerror(int status);
+CSIC_API const char* csic_last_error(void);  /* thread-local text of the last CSIC_ECUDA */
+CSIC_API int csic_abi_version(void);
 
 /* ---- device side ------------------------------------------------------------------------------ */
 
-int csic_device_count(void);        /* >= 0, or CSIC_ENODEVICE */
+CSIC_API int csic_device_count(void);        /* >= 0, or CSIC_ENODEVICE */
 
 /* Binds a context to one GPU; owns a stream, events and the staging buffers of csic_process_host. */
-int csic_create(int device, csic_ctx** out);
-int csic_destroy(csic_ctx* ctx);
+CSIC_API int csic_create(int device, csic_ctx** out);
+CSIC_API int csic_destroy(csic_ctx* ctx);
 
 /* The hot path.  Replaces the body `chiseltest.RawTester.test(new ImageCompressorTop(...)){...}` of
  * ImageCompressionApp.processImage (ImageCompressorTopApp.scala:53-131) for n_frames independent frames
@@ -146,33 +152,41 @@ int csic_destroy(csic_ctx* ctx);
  * raster order (pixel.red/green/blue, :86-89).  d_out: n_frames x bytes_per_frame.  Both device
  * pointers on ctx's GPU.  Asynchronous on `cuda_stream` (a cudaStream_t; NULL = the context's own
  * stream); no hidden synchronisation. */
-int csic_process_device(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t n_frames,
+CSIC_API int csic_process_device(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t n_frames,
                         void* d_out, void* cuda_stream);
 
 /* Row-band shard of ONE frame layout: processes output rows [out_row0, out_row0+out_rows) of every
  * frame, reading d_rgb / writing d_out at their whole-frame offsets (so bands of one frame may be
  * issued on different streams, or -- with per-GPU copies of the rows a band needs -- on different
  * GPUs).  csic_band_input_rows() tells which input rows a band reads. */
-int csic_process_band(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t n_frames,
+CSIC_API int csic_process_band(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t n_frames,
                       void* d_out, int32_t out_row0, int32_t out_rows, void* cuda_stream);
-int csic_band_input_rows(const csic_params* p, int32_t out_row0, int32_t out_rows, int32_t* in_row0,
+CSIC_API int csic_band_input_rows(const csic_params* p, int32_t out_row0, int32_t out_rows, int32_t* in_row0,
                          int32_t* in_rows);
 
 /* Host buffers in, host buffers out: H2D + kernel + D2H, chunked and double-buffered on the
  * context's streams, synchronous on return.  This is the call a Scala `processImage` replacement
  * makes (ImageCompressorTopApp.scala:23-145 minus PNG I/O).  rgb/out may be pageable or pinned. */
-int csic_process_host(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, size_t n_frames,
+CSIC_API int csic_process_host(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, size_t n_frames,
                       uint8_t* out);
 
 /* Pinned host memory helpers for callers that want the fast H2D/D2H path. */
-int csic_host_alloc(size_t bytes, void** out);
-int csic_host_free(void* p);
+CSIC_API int csic_host_alloc(size_t bytes, void** out);
+CSIC_API int csic_host_free(void* p);
 
-int csic_synchronize(csic_ctx* ctx);
+CSIC_API int csic_synchronize(csic_ctx* ctx);
+
+/* Tuning / test knobs (never change results).  KERNEL_FAMILY: 0 = automatic (TMA row kernel whenever
+ * the shape satisfies its 16-byte alignment rules, else the generic gather kernel), 1 = always the
+ * generic gather kernel.  HOST_CHUNK_BYTES: input bytes per pipelined chunk of csic_process_host.
+ * GRID_CTAS_PER_SM / STAGES: overrides for the row kernel's persistent grid and ring depth (0 = auto). */
+enum csic_option { CSIC_OPT_KERNEL_FAMILY = 0, CSIC_OPT_HOST_CHUNK_BYTES = 1, CSIC_OPT_GRID_CTAS_PER_SM = 2,
+                   CSIC_OPT_STAGES = 3 };
+CSIC_API int csic_set_option(csic_ctx* ctx, int option, int64_t value);
 
 /* Diagnostics: which kernel family the last process call on this ctx used (0 none, 1 generic gather
  * kernel, 2 TMA-staged row kernel) and how many kernels it launched. */
-int csic_last_kernel(const csic_ctx* ctx, int32_t* family, int64_t* launches_total);
+CSIC_API int csic_last_kernel(const csic_ctx* ctx, int32_t* family, int64_t* launches_total);
 
 #ifdef __cplusplus
 }
