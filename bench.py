@@ -1,0 +1,353 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the pixel-pipeline hot path on B200, one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4|cfg3|cfg2|cfg5]
+
+Workload (default): BASELINE.json configs[3], the 4K batch `metric` is quoted on -- 1024 frames of
+3840x2160 RGB24 per GPU, 4:2:0 (a=2,b=0) -> spatial f=2 -> 8/8/8 bits, BUNDLE128 output, one fused
+kernel launch per step.  A "step" = one pass of the hot path over that batch.
+
+  value          input megapixels / s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e            same metric through csic_process_host (the reference-facing C-ABI call) with pinned HOST
+                 buffers: H2D + kernel + D2H all inside the timed region
+  roofline       algorithmic bytes (DECIMATE needs only every f-th input row) / kernel time,
+                 against the measured HBM copy peak of this pool (MEASURED_PEAKS.json)
+  cpu_baseline   the oracle (CPU restatement of the reference, all host cores) on a bounded sample
+  --impl reference   the reference's CPU path.  The Scala/Chisel reference cannot run here (no JVM), so this
+                 arm times the oracle port with all host threads on bounded samples of the same workload.
+
+Under torchrun (N > 1) every rank owns one GPU and its own shard of frames; nothing is exchanged on
+the data path (torch.distributed is used for the barrier and the max-over-ranks of the time only).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# name: (W, H, frames_per_gpu, a, b, (y,cb,cr) bits, factor, order, out_format, description)
+WORKLOADS = {
+    "cfg4": (3840, 2160, 1024, 2, 0, (8, 8, 8), 2, "CSQ", 3,
+             "BASELINE configs[3]: 3840x2160 x1024 frames, 4:2:0 + f=2 decimate + BUNDLE128"),
+    "cfg4s": (3840, 2160, 1024, 2, 0, (8, 8, 8), 2, "SQC", 3,
+              "BASELINE configs[3], spatial before chroma (misaligned chroma counters)"),
+    "cfg3": (1920, 1080, 256, 2, 0, (4, 4, 4), 1, "CSQ", 0,
+             "BASELINE configs[2]: 1920x1080 x256 frames, 4:2:0 + Y4Cb4Cr4, YCC888"),
+    "cfg2": (512, 512, 4096, 2, 2, (8, 8, 8), 2, "CSQ", 0,
+             "BASELINE configs[1] batched: 512x512 x4096 frames, 4:2:2 + f=2, YCC888"),
+    "cfg5": (7680, 4320, 64, 2, 0, (6, 5, 5), 4, "CSQ", 1,
+             "BASELINE configs[4]: 7680x4320 x64 frames, 4:2:0 + f=4 + Q_16BIT + RGB888 reconstruct"),
+}
+ORD = {"S": 1, "Q": 2, "C": 3}
+
+
+def algorithmic_bytes_per_frame(W, H, f, out_frame_bytes, average=False):
+    """in_required + out_bytes; DECIMATE with f>1 needs only every f-th row."""
+    rows = H if (f == 1 or average) else -(-H // f)
+    return 3 * W * rows + out_frame_bytes
+
+
+def load_peak():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md "clocks" line).
+    NVML in a thread every 5 ms (the timed region is a fraction of a second); nvidia-smi -lms as fallback."""
+    NAMES = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+             "hw_power_brake_slowdown": 0x80}
+
+    def __init__(self, gpu_index):
+        self.idx, self.sm, self.mask, self.max = gpu_index, [], 0, None
+        self._stop = threading.Event()
+        self.t = None
+        self.how = None
+
+    def _uuid_index(self):
+        # CUDA_VISIBLE_DEVICES may renumber devices; NVML does not honour it
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            tok = vis.split(",")[self.idx].strip()
+            return tok
+        return self.idx
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            ident = self._uuid_index()
+            if isinstance(ident, str) and not ident.isdigit():
+                h = pynvml.nvmlDeviceGetHandleByUUID(ident.encode() if hasattr(ident, "encode") else ident)
+            else:
+                h = pynvml.nvmlDeviceGetHandleByIndex(int(ident))
+            self.max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+            self.how = "nvml"
+            self.t = threading.Thread(target=loop, daemon=True)
+            self.t.start()
+        except Exception:
+            self.how = None
+
+    def stop(self):
+        if self.how != "nvml":
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        self._stop.set()
+        self.t.join(timeout=1)
+        reasons = sorted(n for n, bit in self.NAMES.items() if self.mask & bit)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_min_mhz": min(self.sm) if self.sm else None,
+                "sm_max_mhz": self.max, "samples": len(self.sm), "reasons": reasons, "how": "NVML, 5 ms period"}
+
+
+def oracle_throughput(wl, frames, threads, steps, warmup):
+    """MP/s of the CPU oracle on `frames` synthetic frames per step (same geometry and parameters)."""
+    import numpy as np
+    import oracle
+    W, H, _, a, b, q, f, order, fmt, _ = wl
+    rng = np.random.default_rng(7)
+    base = rng.integers(0, 256, size=(min(frames, 4), H, W, 3), dtype=np.uint8)
+    rgb = np.concatenate([base] * (-(-frames // len(base))))[:frames]       # CPU speed is not data dependent
+    po = oracle.make_params(W, H, a, b, q, f, order, out_format=fmt)
+    for _ in range(warmup):
+        oracle.process(po, rgb, threads=threads)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        oracle.process(po, rgb, threads=threads)
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return frames * W * H * steps / 1e6 / total, total / steps * 1e3
+
+
+def run_reference(args, wl, name):
+    """The reference arm: the reference's own implementation is Scala + Chisel RTL simulation and cannot
+    run in this image (no JVM/sbt); its CPU restatement (oracle/, pinned to the reference's golden PNGs)
+    is timed instead, on all host threads, on a bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    W, H, _, a, b, q, f, order, fmt, desc = wl
+    cores = os.cpu_count() or 1
+    frames = max(cores, min(4 * cores, int(2.0e9 / (W * H * 3 * 4)) or 1))   # bounded sample, ~<= 2 GB of staging
+    mps, ms = oracle_throughput(wl, frames, cores, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "input megapixels/s", "value": round(mps, 2), "unit": "MP/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": config_dict(name, wl, frames, note="reference arm: CPU oracle port, bounded sample per step"),
+        "cpu_baseline": {"value": round(mps, 2), "unit": "MP/s", "cores": cores, "kind": "port",
+                         "sample": f"{frames} frames of {W}x{H} per step, {cores} host threads"},
+        "e2e": {"value": round(mps, 2), "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(name, wl, frames_per_gpu, note=None):
+    W, H, _, a, b, q, f, order, fmt, desc = wl
+    c = {"workload": f"{name}: {desc}", "width": W, "height": H, "frames_per_gpu": frames_per_gpu,
+         "chroma": f"4:{a}:{b}", "quant_bits": list(q), "factor": f, "order": order,
+         "out_format": ["YCC888", "RGB888", "BUNDLE64", "BUNDLE128"][fmt], "round_mode": "FLOOR",
+         "pool_mode": "DECIMATE", "sharding": "frames split across ranks, no collective",
+         "l2": "inputs (>=1 GB per step) far larger than the 126 MB L2; no flush needed"}
+    if note:
+        c["note"] = note
+    return c
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg4", choices=list(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default: the workload's)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--stages", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl, args.workload)
+        return
+
+    import numpy as np
+    import torch
+    import csic_b200 as csic
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        sys.exit("bench.py needs a CUDA device: there is no CPU fallback for the pixel path")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    W, H, frames, a, b, q, f, order, fmt, desc = wl
+    frames = args.frames or frames
+    ops = tuple(ORD[c] for c in order)
+    p = csic.make_params(W, H, a, b, q[0], q[1], q[2], f, ops, out_format=fmt)
+    _, out_h, _, out_fb = csic.out_shape(p)
+    ctx = csic.Context(local)
+    if args.ctas_per_sm:
+        ctx.set_option(2, args.ctas_per_sm)
+    if args.stages:
+        ctx.set_option(3, args.stages)
+
+    # ---- synthetic input, resident in HBM --------------------------------------------------------
+    gen = torch.Generator(device="cuda").manual_seed(0x5EED + rank)
+    rgb = torch.empty((frames, H, W, 3), dtype=torch.uint8, device="cuda")
+    for i in range(0, frames, 64):      # chunked: randint materialises int64 temporaries for some dtypes
+        rgb[i:i + 64] = torch.randint(0, 256, rgb[i:i + 64].shape, dtype=torch.uint8, device="cuda", generator=gen)
+    out = torch.empty((frames, out_fb), dtype=torch.uint8, device="cuda")
+
+    # parity spot check (outside the timed region): one frame against the oracle
+    parity = None
+    if rank == 0:
+        import oracle
+        ctx.process_torch(p, rgb[:2], out=out[:2])
+        torch.cuda.synchronize()
+        want = oracle.process(oracle.make_params(W, H, a, b, q, f, order, out_format=fmt), rgb[1].cpu().numpy())
+        parity = bool(np.array_equal(out[1].cpu().numpy(), want[0]))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing --------------------------------------------------------------------
+    for _ in range(args.warmup):
+        ctx.process_torch(p, rgb, out=out)
+    barrier()
+    fam0, launches0 = ctx.last_kernel()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        ctx.process_torch(p, rgb, out=out)      # one kernel launch on torch's current stream
+        ev[i + 1].record()
+    barrier()
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[-1])
+    clocks = sampler.stop() if rank == 0 else None
+    fam, launches1 = ctx.last_kernel()
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    mp_per_step_all = frames * W * H * world / 1e6
+    value = mp_per_step_all * args.steps / (total_ms_max / 1e3)
+
+    alg_bytes = algorithmic_bytes_per_frame(W, H, f, out_fb) * frames          # per launch (one rank)
+    kernel_ms = statistics.mean(step_ms)                                      # one launch per step
+    peak, peak_src = load_peak()
+    achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp)).get(args.workload)
+            if tj:      # bytes per frame measured by ncu --set full, scaled to this launch
+                traffic = tj["dram_bytes_per_frame"] * frames
+        except Exception:
+            pass
+
+    # ---- end to end through the C ABI with host buffers --------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        hb = min(frames, max(1, int(3.2e9 // (W * H * 3))))         # frames per pinned host batch (~3.2 GB)
+        calls = -(-frames // hb)
+        pin_in = csic.PinnedBuffer(hb * H * W * 3)
+        pin_out = csic.PinnedBuffer(hb * out_fb)
+        hin = torch.from_numpy(pin_in.array)
+        hin.copy_(rgb[:hb].reshape(-1))                               # real pixel data in the pinned buffer
+        torch.cuda.synchronize()
+        hin_np = pin_in.array.reshape(hb, H, W, 3)
+        hout_np = pin_out.array.reshape(hb, out_fb)
+        e2e_steps = max(1, min(args.steps, 3))
+
+        def e2e_step():
+            done = 0
+            for _ in range(calls):
+                n = min(hb, frames - done)
+                ctx.process_host(p, hin_np[:n], out=hout_np[:n])   # H2D + kernel + D2H, synchronous
+                done += n
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ok = bool(np.array_equal(hout_np[1], out[1].cpu().numpy())) if hb > 1 else None
+        e2e = {"value": round(mp_per_step_all * e2e_steps / float(tt.item()), 1), "unit": "MP/s",
+               "h2d_bytes_per_step": frames * H * W * 3, "d2h_bytes_per_step": frames * out_fb,
+               "steps": e2e_steps, "calls_per_step": calls, "host_batch_frames": hb,
+               "api": "csic_process_host (pinned host buffers; chunked H2D/kernel/D2H pipeline)",
+               "matches_device_path": e2e_ok}
+        pin_in.free(); pin_out.free()
+
+    # ---- CPU baseline (rank 0, N=1 only; bounded sample) -------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        fr = max(cores, min(2 * cores, 64))
+        mps, _ = oracle_throughput(wl, fr, cores, steps=2, warmup=1)
+        cpu = {"value": round(mps, 2), "unit": "MP/s", "cores": cores, "kind": "port",
+               "sample": f"{fr} frames of {W}x{H}, 2 timed passes, {cores} host threads (oracle/csic_oracle.c)"}
+
+    if rank == 0:
+        line = {
+            "metric": "input megapixels/s", "value": round(value, 1), "unit": "MP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms_max / args.steps, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic (uniform random bytes, torch.randint, seed 0x5EED+rank, generated in HBM)",
+            "config": config_dict(args.workload, wl, frames),
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": traffic,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(kernel_ms, 4),
+                         "kernel": "csic_rows_kernel" if fam == 2 else "csic_generic_kernel", "peak_source": peak_src},
+            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": int(launches1 - launches0) * world,
+            "parity_spot_check": parity, "step_ms_min": round(min(step_ms), 4), "step_ms_max": round(max(step_ms), 4),
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -220,7 +220,9 @@ class Context:
         fb = out_shape(p)[3]
         if out is None:
             out = torch.empty((n, fb), dtype=torch.uint8, device=rgb.device)
-        stream = torch.cuda.current_stream(rgb.device).cuda_stream
+        # torch's default stream has handle 0, which the C ABI reads as "the context's own stream":
+        # name it explicitly as cudaStreamLegacy (0x1) so the launch is ordered with torch's work.
+        stream = torch.cuda.current_stream(rgb.device).cuda_stream or 1
         if out_row0 is None:
             self.process_device(p, rgb.data_ptr(), n, out.data_ptr(), stream)
         else:

@@ -151,6 +151,7 @@ CSIC_API int csic_destroy(csic_ctx* ctx);
  * (the reference builds a fresh DUT per image, :53).  d_rgb: n_frames x H x W x 3 bytes, packed RGB24,
  * raster order (pixel.red/green/blue, :86-89).  d_out: n_frames x bytes_per_frame.  Both device
  * pointers on ctx's GPU.  Asynchronous on `cuda_stream` (a cudaStream_t; NULL = the context's own
+ * non-blocking stream -- pass cudaStreamLegacy (0x1) / cudaStreamPerThread (0x2) to name a default
  * stream); no hidden synchronisation. */
 CSIC_API int csic_process_device(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t n_frames,
                         void* d_out, void* cuda_stream);
