@@ -43,8 +43,10 @@ struct KPlan {
   uint32_t n_frames;
   // ---- TMA row kernel only ----
   int32_t hfe;                           // chroma hold width in *output* pixels inside a 4-pixel granule
-  int32_t nsplit, tile_px;               // tiles per output row, output pixels per tile
-  uint32_t tile_in_bytes, tile_out_bytes;
+  int32_t nsplit, tile_px;               // segments per output row, output pixels per row segment
+  int32_t tile_rows;                     // output rows per tile (1 when nsplit > 1)
+  uint32_t tiles_per_band;
+  uint32_t tile_in_bytes, tile_out_bytes; // bytes of ONE row segment (input / output)
   uint32_t n_tiles;
   int32_t stages;
   uint32_t stage_stride, out_buf_off, out_buf_stride, meta_off, bar_off, smem_bytes;

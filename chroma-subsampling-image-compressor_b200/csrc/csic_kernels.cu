@@ -260,6 +260,11 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
   return v;
 }
+__device__ __forceinline__ uint32_t lds8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
 __device__ __forceinline__ uint2 lds64(uint32_t a) {
   uint2 v;
   asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
@@ -268,103 +273,217 @@ __device__ __forceinline__ uint2 lds64(uint32_t a) {
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
-__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
-  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
-}
-__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-}
 
 // The four sampled pixels of a granule, each as a word whose low three bytes are R,G,B.
-// A granule is 4 consecutive output pixels = 4 input pixels at a stride of F pixels (3F bytes).
+// A granule is 4 consecutive output pixels = 4 input pixels at a stride of F pixels (3F bytes);
+// `a` is the shared-memory address of its first byte.
 template <int F>
-__device__ __forceinline__ void load_granule(uint32_t base, uint32_t g, uint32_t (&p)[4]) {
-  if (F == 1) {
-    const uint32_t a = base + g * 12u;          // word stride 3 across lanes: conflict free
+__device__ __forceinline__ void load_granule(uint32_t a, uint32_t (&p)[4]) {
+  if (F == 1) {                                  // 12 bytes; word stride 3 across lanes: conflict free
     const uint32_t w0 = lds32(a), w1 = lds32(a + 4), w2 = lds32(a + 8);
     p[0] = w0;
     p[1] = __funnelshift_r(w0, w1, 24);
     p[2] = __funnelshift_r(w1, w2, 16);
     p[3] = w2 >> 8;
-  } else if (F == 2) {
-    const uint32_t a = base + g * 24u;          // 8-byte aligned, conflict free per half warp
+  } else if (F == 2) {                           // 24 bytes, 8-byte aligned; conflict free per half warp
     const uint2 u0 = lds64(a), u1 = lds64(a + 8), u2 = lds64(a + 16);
     p[0] = u0.x;                                 // bytes 0..2
     p[1] = __funnelshift_r(u0.y, u1.x, 16);      // bytes 6..8
     p[2] = u1.y;                                 // bytes 12..14
     p[3] = __funnelshift_r(u2.x, u2.y, 16);      // bytes 18..20
-  } else {
-    const uint32_t a = base + g * (12u * F);
+  } else {                                       // pixels sit on word boundaries
 #pragma unroll
     for (int j = 0; j < 4; ++j) p[j] = lds32(a + j * 3u * F);
   }
 }
 
-struct TileMeta {       // written by the producer thread, read by everyone after the stage's mbarrier flips
-  uint32_t held;        // 1: the whole tile replays one held chroma pair (odd 4:2:0 / 4:1:0 line)
-  uint32_t aux_off;     // byte offset of that pixel inside the stage's 32-byte aux window
-  uint32_t pad[2];
+// Per-stage tile descriptor: written by the producer thread before it arms the stage's mbarrier
+// (release), read by every thread after the barrier's phase flips (acquire).
+constexpr int kMaxTileRows = 16;
+struct TileMeta {
+  uint64_t out_base;                 // global address of the tile's first output byte
+  uint32_t n_granules;               // rows * granules per row segment
+  uint32_t any_held;                 // some row of the tile replays a held chroma pair
+  uint32_t held_addr[kMaxTileRows];  // per row: 0, or shared address of the RGB pixel whose chroma the row replays
 };
 
-template <int F, int FMT, bool TRUNC>
+// Runtime constants of the inner loop, hoisted into registers once per kernel.
+struct LoopConst {
+  uint32_t qm0, qm1, qm2;            // YCC888: quantiser keep-masks over the three packed words
+  uint32_t my, mcb, mcr;             // RGB888
+  int shy, shb, shr, ly, lb;         // bundles
+  uint32_t gran_per_row;
+  uint32_t row0_of_thread, rem0_of_thread;   // threadIdx.x / gran_per_row, threadIdx.x % gran_per_row
+  uint32_t drow, drem;                       // blockDim.x / gran_per_row, blockDim.x % gran_per_row
+  bool trunc;
+};
+
+__device__ __forceinline__ uint32_t fwd_nc16_rt(uint32_t p, uint32_t coef, bool trunc) {
+  int32_t x = max(dp4a_us(p, coef, 32639), 0);
+  if (trunc) x -= (x >> 15) * 255;
+  return (uint32_t)x;
+}
+
+// One tile: a flat loop over its granules.  Rows are packed back to back in the stage (and, for the
+// staged formats, in the output buffer), so granule q lives at  base + q * granule_bytes  and the row
+// index is only needed to look up a held chroma pair (HELD tiles).
+//   HFE   chroma hold width inside a granule, in output pixels (1, 2 or 4)
+//   HELD  the tile may contain rows that replay a held pair (odd 4:2:0 / 4:1:0 lines)
+//   Q8    8/8/8 bits in a 32-bit slot: pure byte permutes
+template <int F, int FMT, int HFE, bool HELD, bool Q8>
+__device__ __forceinline__ void tile_loop(uint32_t in_s, uint32_t out_s, uint8_t* __restrict__ out_g,
+                                          const TileMeta* __restrict__ meta, const LoopConst& C) {
+  const uint32_t n = meta->n_granules;
+  uint32_t row = C.row0_of_thread, rem = C.rem0_of_thread;   // row of granule q, tracked without a division
+  for (uint32_t q = threadIdx.x; q < n; q += blockDim.x) {
+    uint32_t p[4];
+    load_granule<F>(in_s + q * (12u * F), p);
+    uint32_t dy[4], xb[4], xr[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dy[j] = fwd_y16(p[j]);
+    uint32_t haddr = 0;
+    if (HELD) {
+      haddr = meta->held_addr[row];
+      row += C.drow;
+      rem += C.drem;
+      if (rem >= C.gran_per_row) { rem -= C.gran_per_row; ++row; }
+    }
+    if (HELD && haddr != 0) {
+      const uint32_t hp = lds8(haddr) | (lds8(haddr + 1) << 8) | (lds8(haddr + 2) << 16);
+      const uint32_t hb = fwd_nc16_rt(hp, kCoefNCb, C.trunc), hr = fwd_nc16_rt(hp, kCoefNCr, C.trunc);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { xb[j] = hb; xr[j] = hr; }
+    } else {
+      // sample where j % HFE == 0, hold in between (ChromaSubsampler.scala:57-65)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j % HFE == 0) {
+          xb[j] = fwd_nc16_rt(p[j], kCoefNCb, C.trunc);
+          xr[j] = fwd_nc16_rt(p[j], kCoefNCr, C.trunc);
+        } else {
+          xb[j] = xb[j - 1];
+          xr[j] = xr[j - 1];
+        }
+      }
+    }
+
+    if (FMT == KF_YCC888) {
+      // byte 1 of dy is Y, byte 1 of xb/xr is ~Cb/~Cr: gather with PRMT, flip and quantise per word.
+      uint32_t t, u;
+      t = __byte_perm(dy[0], xb[0], 0x0051); u = __byte_perm(xr[0], dy[1], 0x0051);
+      const uint32_t w0 = (__byte_perm(t, u, 0x5410) ^ 0x00FFFF00u) & C.qm0;
+      t = __byte_perm(xb[1], xr[1], 0x0051); u = __byte_perm(dy[2], xb[2], 0x0051);
+      const uint32_t w1 = (__byte_perm(t, u, 0x5410) ^ 0xFF00FFFFu) & C.qm1;
+      t = __byte_perm(xr[2], dy[3], 0x0051); u = __byte_perm(xb[3], xr[3], 0x0051);
+      const uint32_t w2 = (__byte_perm(t, u, 0x5410) ^ 0xFFFF00FFu) & C.qm2;
+      const uint32_t a = out_s + q * 12u;
+      sts32(a, w0); sts32(a + 4, w1); sts32(a + 8, w2);
+    } else if (FMT == KF_RGB888) {
+      uint32_t v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int y = (int)((dy[j] >> 8) & C.my);
+        const int cb = (int)((255u - (xb[j] >> 8)) & C.mcb);
+        const int cr = (int)((255u - (xr[j] >> 8)) & C.mcr);
+        v[j] = inverse_rgb(y, cb, cr);
+      }
+      const uint32_t a = out_s + q * 12u;
+      sts32(a, v[0] | (v[1] << 24));
+      sts32(a + 4, (v[1] >> 8) | (v[2] << 16));
+      sts32(a + 8, (v[2] >> 16) | (v[3] << 8));
+    } else {
+      // bundle slots go straight to global memory: one coalesced 4/8/16-byte store per granule
+      uint32_t v[4];
+      if (Q8) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)   // (Cr, Cb, Y, 0): dy < 65536 so its byte 3 is the zero pad
+          v[j] = __byte_perm(__byte_perm(xr[j], xb[j], 0x0051), dy[j], 0x7510) ^ 0x0000FFFFu;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          v[j] = ((dy[j] >> C.shy) << C.ly) | (((xb[j] ^ 0xFFFFu) >> C.shb) << C.lb) | ((xr[j] ^ 0xFFFFu) >> C.shr);
+      }
+      if (FMT == KF_SLOT32) __stcs(reinterpret_cast<uint4*>(out_g) + q, make_uint4(v[0], v[1], v[2], v[3]));
+      else if (FMT == KF_SLOT16) __stcs(reinterpret_cast<uint2*>(out_g) + q, make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16)));
+      else __stcs(reinterpret_cast<uint32_t*>(out_g) + q, v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
+    }
+  }
+}
+
+template <int F, int FMT, bool Q8>
 __global__ void __launch_bounds__(256) csic_rows_kernel(const __grid_constant__ KPlan P) {
   extern __shared__ __align__(128) uint8_t smem[];
+  constexpr bool kStaged = (FMT == KF_YCC888 || FMT == KF_RGB888);   // output leaves through smem + TMA store
   const uint32_t tid = threadIdx.x;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t S = (uint32_t)P.stages;
   const uint32_t n_my = (P.n_tiles > blockIdx.x) ? (P.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  TileMeta* meta = reinterpret_cast<TileMeta*>(smem + P.meta_off);
   const uint64_t pol = policy_evict_first();   // every byte is touched exactly once: do not keep it in L2
 
   // -- producer (thread 0): tile i of this CTA -> stage i % S ------------------------------------
-  auto tile_coords = [&](uint32_t i, uint32_t& k, uint32_t& ro, uint32_t& seg) {
-    const uint32_t tile = blockIdx.x + i * gridDim.x;
-    const uint32_t rowid = tile / (uint32_t)P.nsplit;
-    seg = tile - rowid * (uint32_t)P.nsplit;
-    k = rowid / (uint32_t)P.band_rows;
-    ro = (uint32_t)P.row0 + (rowid - k * (uint32_t)P.band_rows);
-  };
   auto issue_load = [&](uint32_t i) {
-    uint32_t k, ro, seg;
-    tile_coords(i, k, ro, seg);
+    const uint32_t tile = blockIdx.x + i * gridDim.x;
+    const uint32_t t2 = tile / (uint32_t)P.nsplit;
+    const uint32_t seg = tile - t2 * (uint32_t)P.nsplit;
+    const uint32_t k = t2 / P.tiles_per_band;
+    const uint32_t tb = t2 - k * P.tiles_per_band;
+    const uint32_t ro0 = (uint32_t)P.row0 + tb * (uint32_t)P.tile_rows;
+    const uint32_t nrows = min((uint32_t)P.tile_rows, (uint32_t)(P.row0 + P.band_rows) - ro0);
     const uint32_t s = i % S;
     const uint8_t* frame = P.in + (uint64_t)k * P.in_frame_bytes;
-    const uint8_t* src = frame + (uint64_t)(ro * F) * P.in_row_bytes + (uint64_t)seg * P.tile_in_bytes;
-    // Which chroma does this output row replay?  (KPlan::hfe handles the in-row hold.)
-    bool held = false;
-    const uint8_t* hp = nullptr;
-    if (P.vf == 2) {
-      if (!P.case_b) {
-        if (F == 1 && (ro & 1)) {            // odd line at full resolution: last sample point of the line above
-          held = true;
-          hp = frame + (uint64_t)(ro - 1) * P.in_row_bytes + (uint32_t)P.last_sample_col * 3u;
-        }
-      } else {
-        const uint32_t line = ro / F;         // W == F * Wo: one counter line spans F output rows
-        if (line & 1) {
-          held = true;
-          const uint32_t srow = (line - 1) * F + (uint32_t)P.last_sample_col / (uint32_t)P.Wo;
-          const uint32_t scol = (uint32_t)P.last_sample_col % (uint32_t)P.Wo;
-          hp = frame + (uint64_t)(srow * F) * P.in_row_bytes + (uint64_t)scol * (3u * F);
-        }
-      }
-    }
     const uint32_t bar = sbase + P.bar_off + s * 8u;
     const uint32_t dst = sbase + s * P.stage_stride;
-    TileMeta m;
-    m.held = held ? 1u : 0u;
-    m.aux_off = 0;
-    if (held) {
-      const uint64_t a = reinterpret_cast<uint64_t>(hp);
-      m.aux_off = (uint32_t)(a & 15u);
-      meta[s] = m;
-      mbar_expect_tx(bar, P.tile_in_bytes + 32u);
-      tma_load_1d(dst, src, P.tile_in_bytes, bar, pol);
-      tma_load_1d(dst + P.tile_in_bytes, reinterpret_cast<const void*>(a & ~(uint64_t)15), 32u, bar, pol);
+    const uint32_t aux = dst + (uint32_t)P.tile_rows * P.tile_in_bytes;    // 32-byte window per row
+    TileMeta* m = reinterpret_cast<TileMeta*>(smem + P.meta_off) + s;
+
+    // Which rows replay a held chroma pair, and from where?  (KPlan::hfe covers the in-row hold.)
+    uint32_t n_aux = 0, any = 0;
+    const uint8_t* aux_src[kMaxTileRows];
+    if (P.vf == 2) {
+      for (uint32_t j = 0; j < nrows; ++j) {
+        const uint32_t ro = ro0 + j;
+        uint32_t h = 0;
+        const uint8_t* hp = nullptr;
+        if (!P.case_b) {
+          if (F == 1 && (ro & 1)) {          // odd line at full resolution: last sample point of the line above
+            if (j > 0 && P.nsplit == 1) h = dst + (j - 1) * P.tile_in_bytes + (uint32_t)P.last_sample_col * 3u;   // in this tile
+            else hp = frame + (uint64_t)(ro - 1) * P.in_row_bytes + (uint32_t)P.last_sample_col * 3u;
+          }
+        } else {
+          const uint32_t line = ro / F;      // W == F * Wo: one counter line spans F output rows
+          if (line & 1) {
+            const uint32_t srow = (line - 1) * F + (uint32_t)P.last_sample_col / (uint32_t)P.Wo;
+            const uint32_t scol = (uint32_t)P.last_sample_col % (uint32_t)P.Wo;
+            hp = frame + (uint64_t)(srow * F) * P.in_row_bytes + (uint64_t)scol * (3u * F);
+          }
+        }
+        if (hp) {
+          const uint64_t a = reinterpret_cast<uint64_t>(hp);
+          h = aux + j * 32u + (uint32_t)(a & 15u);
+          aux_src[j] = reinterpret_cast<const uint8_t*>(a & ~(uint64_t)15);
+          ++n_aux;
+        } else {
+          aux_src[j] = nullptr;
+        }
+        m->held_addr[j] = h;
+        any |= h;
+      }
+    }
+    m->any_held = any;
+    m->n_granules = nrows * ((uint32_t)P.tile_px >> 2);
+    m->out_base = reinterpret_cast<uint64_t>(P.out) + (uint64_t)k * P.out_frame_bytes + (uint64_t)ro0 * P.out_row_bytes +
+                  (uint64_t)seg * P.tile_out_bytes;
+    mbar_expect_tx(bar, nrows * P.tile_in_bytes + n_aux * 32u);
+    const uint8_t* src = frame + (uint64_t)(ro0 * F) * P.in_row_bytes + (uint64_t)seg * P.tile_in_bytes;
+    if (F == 1 && P.nsplit == 1) {           // consecutive rows are contiguous in memory: one bulk copy
+      tma_load_1d(dst, src, nrows * P.tile_in_bytes, bar, pol);
     } else {
-      meta[s] = m;
-      mbar_expect_tx(bar, P.tile_in_bytes);
-      tma_load_1d(dst, src, P.tile_in_bytes, bar, pol);
+      for (uint32_t j = 0; j < nrows; ++j)
+        tma_load_1d(dst + j * P.tile_in_bytes, src + (uint64_t)j * F * P.in_row_bytes, P.tile_in_bytes, bar, pol);
+    }
+    if (n_aux) {
+      for (uint32_t j = 0; j < nrows; ++j)
+        if (aux_src[j]) tma_load_1d(aux + j * 32u, aux_src[j], 32u, bar, pol);
     }
   };
 
@@ -374,16 +493,25 @@ __global__ void __launch_bounds__(256) csic_rows_kernel(const __grid_constant__ 
   }
   __syncthreads();
   if (tid == 0) {
-    // meta[] is written before the arrive (release) and read after try_wait (acquire).
     for (uint32_t i = 0; i + 1 < S && i < n_my; ++i) issue_load(i);
   }
 
-  const uint32_t granules = (uint32_t)P.tile_px >> 2;
-  const uint32_t my = P.qmask & 0xFFu, mcb = (P.qmask >> 8) & 0xFFu, mcr = (P.qmask >> 16) & 0xFFu;
-  // quantiser keep-masks laid over the three words of four packed Y,Cb,Cr pixels
-  const uint32_t qm0 = my | (mcb << 8) | (mcr << 16) | (my << 24);
-  const uint32_t qm1 = mcb | (mcr << 8) | (my << 16) | (mcb << 24);
-  const uint32_t qm2 = mcr | (my << 8) | (mcb << 16) | (mcr << 24);
+  LoopConst C;
+  {
+    const uint32_t my = P.qmask & 0xFFu, mcb = (P.qmask >> 8) & 0xFFu, mcr = (P.qmask >> 16) & 0xFFu;
+    C.qm0 = my | (mcb << 8) | (mcr << 16) | (my << 24);
+    C.qm1 = mcb | (mcr << 8) | (my << 16) | (mcb << 24);
+    C.qm2 = mcr | (my << 8) | (mcb << 16) | (mcr << 24);
+    C.my = my; C.mcb = mcb; C.mcr = mcr;
+    C.shy = 8 + P.sy; C.shb = 8 + P.scb; C.shr = 8 + P.scr;
+    C.ly = P.cb_bits + P.cr_bits; C.lb = P.cr_bits;
+    C.gran_per_row = (uint32_t)P.tile_px >> 2;
+    C.row0_of_thread = tid / C.gran_per_row;
+    C.rem0_of_thread = tid % C.gran_per_row;
+    C.drow = blockDim.x / C.gran_per_row;
+    C.drem = blockDim.x % C.gran_per_row;
+    C.trunc = P.trunc != 0;
+  }
   const int hfe = P.hfe;
 
   for (uint32_t i = 0; i < n_my; ++i) {
@@ -394,98 +522,37 @@ __global__ void __launch_bounds__(256) csic_rows_kernel(const __grid_constant__ 
 
     const uint32_t in_s = sbase + s * P.stage_stride;
     const uint32_t out_s = sbase + P.out_buf_off + (i & 1u) * P.out_buf_stride;
-    const TileMeta m = meta[s];
-    uint32_t hcb = 0, hcr = 0;
-    if (m.held) {
-      const uint8_t* hq = smem + s * P.stage_stride + P.tile_in_bytes + m.aux_off;
-      const uint32_t hp = (uint32_t)hq[0] | ((uint32_t)hq[1] << 8) | ((uint32_t)hq[2] << 16);
-      hcb = fwd_nc16<TRUNC>(hp, kCoefNCb);
-      hcr = fwd_nc16<TRUNC>(hp, kCoefNCr);
+    const TileMeta* m = reinterpret_cast<const TileMeta*>(smem + P.meta_off) + s;
+    uint8_t* out_g = reinterpret_cast<uint8_t*>(m->out_base);
+    if (m->any_held) {
+      if (hfe == 1) tile_loop<F, FMT, 1, true, Q8>(in_s, out_s, out_g, m, C);
+      else if (hfe == 2) tile_loop<F, FMT, 2, true, Q8>(in_s, out_s, out_g, m, C);
+      else tile_loop<F, FMT, 4, true, Q8>(in_s, out_s, out_g, m, C);
+    } else {
+      if (hfe == 1) tile_loop<F, FMT, 1, false, Q8>(in_s, out_s, out_g, m, C);
+      else if (hfe == 2) tile_loop<F, FMT, 2, false, Q8>(in_s, out_s, out_g, m, C);
+      else tile_loop<F, FMT, 4, false, Q8>(in_s, out_s, out_g, m, C);
     }
 
-    for (uint32_t g = tid; g < granules; g += blockDim.x) {
-      uint32_t p[4];
-      load_granule<F>(in_s, g, p);
-      uint32_t dy[4], xb[4], xr[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dy[j] = fwd_y16(p[j]);
-      if (m.held) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { xb[j] = hcb; xr[j] = hcr; }
-      } else {
-        // sample at j % hfe == 0, hold in between (ChromaSubsampler.scala:57-65)
-        xb[0] = fwd_nc16<TRUNC>(p[0], kCoefNCb);
-        xr[0] = fwd_nc16<TRUNC>(p[0], kCoefNCr);
-        if (hfe == 1) {
-#pragma unroll
-          for (int j = 1; j < 4; ++j) { xb[j] = fwd_nc16<TRUNC>(p[j], kCoefNCb); xr[j] = fwd_nc16<TRUNC>(p[j], kCoefNCr); }
-        } else if (hfe == 2) {
-          xb[1] = xb[0]; xr[1] = xr[0];
-          xb[2] = fwd_nc16<TRUNC>(p[2], kCoefNCb);
-          xr[2] = fwd_nc16<TRUNC>(p[2], kCoefNCr);
-          xb[3] = xb[2]; xr[3] = xr[2];
-        } else {
-#pragma unroll
-          for (int j = 1; j < 4; ++j) { xb[j] = xb[0]; xr[j] = xr[0]; }
-        }
+    if (kStaged) {
+      // Hand the tile to the TMA engine.  Generic-proxy writes must be fenced before the async proxy
+      // reads them; the staging buffer used two tiles ago must have been read out before it is reused.
+      const uint32_t bytes = m->n_granules * 12u;
+      fence_proxy_async_smem();
+      if (tid == 0) tma_store_wait_read0();
+      __syncthreads();
+      if (tid == 0) {
+        tma_store_1d(out_g, out_s, bytes, pol);
+        tma_store_commit();
       }
-
-      if (FMT == KF_YCC888) {
-        // byte 1 of dy is Y, byte 1 of xb/xr is ~Cb/~Cr: gather with PRMT, flip and quantise per word.
-        uint32_t t, u;
-        t = __byte_perm(dy[0], xb[0], 0x0051); u = __byte_perm(xr[0], dy[1], 0x0051);
-        const uint32_t w0 = (__byte_perm(t, u, 0x5410) ^ 0x00FFFF00u) & qm0;
-        t = __byte_perm(xb[1], xr[1], 0x0051); u = __byte_perm(dy[2], xb[2], 0x0051);
-        const uint32_t w1 = (__byte_perm(t, u, 0x5410) ^ 0xFF00FFFFu) & qm1;
-        t = __byte_perm(xr[2], dy[3], 0x0051); u = __byte_perm(xb[3], xr[3], 0x0051);
-        const uint32_t w2 = (__byte_perm(t, u, 0x5410) ^ 0xFFFF00FFu) & qm2;
-        const uint32_t a = out_s + g * 12u;
-        sts32(a, w0); sts32(a + 4, w1); sts32(a + 8, w2);
-      } else if (FMT == KF_RGB888) {
-        uint32_t v[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int y = (int)((dy[j] >> 8) & my);
-          const int cb = (int)((255u - (xb[j] >> 8)) & mcb);
-          const int cr = (int)((255u - (xr[j] >> 8)) & mcr);
-          v[j] = inverse_rgb(y, cb, cr);
-        }
-        const uint32_t a = out_s + g * 12u;
-        sts32(a, v[0] | (v[1] << 24));
-        sts32(a + 4, (v[1] >> 8) | (v[2] << 16));
-        sts32(a + 8, (v[2] >> 16) | (v[3] << 8));
-      } else {
-        uint32_t v[4];
-        const int shy = 8 + P.sy, shb = 8 + P.scb, shr = 8 + P.scr;
-        const int ly = P.cb_bits + P.cr_bits, lb = P.cr_bits;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          v[j] = ((dy[j] >> shy) << ly) | (((xb[j] ^ 0xFFFFu) >> shb) << lb) | ((xr[j] ^ 0xFFFFu) >> shr);
-        if (FMT == KF_SLOT32) sts128(out_s + g * 16u, v[0], v[1], v[2], v[3]);
-        else if (FMT == KF_SLOT16) sts64(out_s + g * 8u, v[0] | (v[1] << 16), v[2] | (v[3] << 16));
-        else sts32(out_s + g * 4u, v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
-      }
-    }
-
-    // Hand the tile to the TMA engine.  Generic-proxy writes must be fenced before the async proxy
-    // reads them; the staging buffer used two tiles ago must have been read out before it is reused.
-    fence_proxy_async_smem();
-    if (tid == 0) tma_store_wait_read0();
-    __syncthreads();
-    if (tid == 0) {
-      uint32_t k, ro, seg;
-      tile_coords(i, k, ro, seg);
-      uint8_t* dst = P.out + (uint64_t)k * P.out_frame_bytes + (uint64_t)ro * P.out_row_bytes +
-                     (uint64_t)seg * P.tile_out_bytes;
-      tma_store_1d(dst, out_s, P.tile_out_bytes, pol);
-      tma_store_commit();
+    } else {
+      __syncthreads();    // everyone is done reading stage s (and its meta) before it is refilled
     }
   }
-  if (tid == 0) tma_store_wait_all();
+  if (kStaged && tid == 0) tma_store_wait_all();
 }
 
 bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_stages) {
-  (void)sm_count;
   if (k.average && k.f > 1) return false;                       // AVERAGE extension: generic kernel
   if (k.W % k.f != 0) return false;                             // a counter line must be whole output rows
   if (k.Wo % 16 != 0) return false;                             // 16-byte TMA granularity on the output rows
@@ -500,46 +567,57 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
   if (!k.case_b) k.hfe = std::max(1, k.hf / k.f);
   else k.hfe = k.hf;
 
-  // Split rows so that a tile's input is at most ~16 KB (several tiles in flight per CTA).
+  const bool staged = k.kformat <= KF_RGB888;
+  const uint32_t opx = staged ? 3u : (uint32_t)k.slot_bytes;
+  // Tile budget: input bytes of one tile.  Staged formats also hold two output buffers per CTA.
+  const uint32_t tile_budget = staged ? 12u * 1024u : 24u * 1024u;
   const uint32_t row_in = (uint32_t)k.Wo * 3u * (uint32_t)k.f;  // == in_row_bytes
   int nsplit = 0;
-  for (int n = (int)((row_in + 16383u) / 16384u); n <= 64; ++n) {
+  for (int n = (int)((row_in + tile_budget - 1) / tile_budget); n <= 64; ++n) {
     if (k.Wo % (16 * n) == 0) { nsplit = n; break; }
   }
   if (nsplit == 0) return false;
   k.nsplit = nsplit;
   k.tile_px = k.Wo / nsplit;
-  k.tile_in_bytes = (uint32_t)k.tile_px * 3u * (uint32_t)k.f;
-  const uint32_t opx = k.kformat <= KF_RGB888 ? 3u : (uint32_t)k.slot_bytes;
+  k.tile_in_bytes = (uint32_t)k.tile_px * 3u * (uint32_t)k.f;    // one row segment
   k.tile_out_bytes = (uint32_t)k.tile_px * opx;
-  const uint64_t n_tiles = (uint64_t)k.n_frames * (uint64_t)k.band_rows * (uint64_t)nsplit;
+  // Rows per tile: whole rows only (so the tile's output is contiguous), as many as fit the budget,
+  // but keep at least ~4 tiles per SM so small batches still spread over the chip.
+  int rows = 1;
+  if (nsplit == 1) {
+    rows = (int)std::min<uint32_t>((uint32_t)kMaxTileRows, std::max<uint32_t>(1u, tile_budget / k.tile_in_bytes));
+    rows = std::min(rows, k.band_rows);
+    auto tiles_for = [&](int r) { return (uint64_t)k.n_frames * (uint64_t)((k.band_rows + r - 1) / r); };
+    while (rows > 1 && tiles_for(rows) < (uint64_t)sm_count * 4u) rows = (rows + 1) / 2;
+  }
+  k.tile_rows = rows;
+  k.tiles_per_band = (uint32_t)((k.band_rows + rows - 1) / rows);
+  const uint64_t n_tiles = (uint64_t)k.n_frames * (uint64_t)k.tiles_per_band * (uint64_t)nsplit;
   if (n_tiles >= (1ull << 31)) return false;
   k.n_tiles = (uint32_t)n_tiles;
 
   auto up128 = [](uint32_t v) { return (v + 127u) & ~127u; };
-  k.stage_stride = up128(k.tile_in_bytes + 32u);
-  k.out_buf_stride = up128(k.tile_out_bytes);
-  // Aim for >= 3 CTAs per SM and 4 stages per CTA, within the opt-in shared memory limit.
-  const uint32_t budget = (uint32_t)std::min<size_t>(max_smem_optin, 72 * 1024);
-  int stages = force_stages >= 2 ? force_stages : 4;
-  auto need = [&](int s) { return (uint32_t)s * k.stage_stride + 2u * k.out_buf_stride + (uint32_t)s * 16u + (uint32_t)s * 8u + 128u; };
-  while (force_stages < 2 && stages > 2 && need(stages) > budget) --stages;
+  k.stage_stride = up128((uint32_t)rows * (k.tile_in_bytes + 32u));
+  k.out_buf_stride = staged ? up128((uint32_t)rows * k.tile_out_bytes) : 0u;
+  int stages = force_stages >= 2 ? force_stages : 3;
+  auto need = [&](int s) {
+    return (uint32_t)s * k.stage_stride + 2u * k.out_buf_stride + (uint32_t)s * (uint32_t)sizeof(TileMeta) + (uint32_t)s * 8u + 256u;
+  };
+  while (force_stages < 2 && stages > 2 && need(stages) > 76u * 1024u) --stages;
   if (need(stages) > max_smem_optin) return false;
   k.stages = stages;
   k.out_buf_off = (uint32_t)stages * k.stage_stride;
-  k.meta_off = k.out_buf_off + 2u * k.out_buf_stride;
-  k.bar_off = (k.meta_off + (uint32_t)stages * 16u + 63u) & ~63u;
+  k.meta_off = up128(k.out_buf_off + 2u * k.out_buf_stride);
+  k.bar_off = up128(k.meta_off + (uint32_t)stages * (uint32_t)sizeof(TileMeta));
   k.smem_bytes = k.bar_off + (uint32_t)stages * 8u;
   return true;
 }
 
 template <int F, int FMT>
 static int launch_rows_t(const KPlan& k, unsigned grid, cudaStream_t st) {
-  if (k.trunc) {
-    csic_rows_kernel<F, FMT, true><<<grid, 256, k.smem_bytes, st>>>(k);
-  } else {
-    csic_rows_kernel<F, FMT, false><<<grid, 256, k.smem_bytes, st>>>(k);
-  }
+  const bool q8 = FMT == KF_SLOT32 && k.sy == 0 && k.scb == 0 && k.scr == 0;
+  if (FMT == KF_SLOT32 && q8) csic_rows_kernel<F, FMT, (FMT == KF_SLOT32)><<<grid, 256, k.smem_bytes, st>>>(k);
+  else csic_rows_kernel<F, FMT, false><<<grid, 256, k.smem_bytes, st>>>(k);
   return (int)cudaGetLastError();
 }
 
@@ -554,18 +632,19 @@ static int launch_rows_f(const KPlan& k, unsigned grid, cudaStream_t st) {
   }
 }
 
-template <int F, int FMT, bool TR>
+template <int F, int FMT, bool Q8>
 static cudaError_t set_attr_one(size_t bytes) {
-  return cudaFuncSetAttribute(csic_rows_kernel<F, FMT, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return cudaFuncSetAttribute(csic_rows_kernel<F, FMT, Q8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 template <int F>
 static cudaError_t set_attr_f(size_t b) {
   cudaError_t e;
-#define CSIC_SET(FMT)                                             \
-  if ((e = set_attr_one<F, FMT, false>(b)) != cudaSuccess) return e; \
-  if ((e = set_attr_one<F, FMT, true>(b)) != cudaSuccess) return e;
-  CSIC_SET(KF_YCC888) CSIC_SET(KF_RGB888) CSIC_SET(KF_SLOT8) CSIC_SET(KF_SLOT16) CSIC_SET(KF_SLOT32)
-#undef CSIC_SET
+  if ((e = set_attr_one<F, KF_YCC888, false>(b)) != cudaSuccess) return e;
+  if ((e = set_attr_one<F, KF_RGB888, false>(b)) != cudaSuccess) return e;
+  if ((e = set_attr_one<F, KF_SLOT8, false>(b)) != cudaSuccess) return e;
+  if ((e = set_attr_one<F, KF_SLOT16, false>(b)) != cudaSuccess) return e;
+  if ((e = set_attr_one<F, KF_SLOT32, false>(b)) != cudaSuccess) return e;
+  if ((e = set_attr_one<F, KF_SLOT32, true>(b)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -581,7 +660,7 @@ int rows_kernel_set_attributes(size_t max_smem_optin) {
 int launch_rows(const KPlan& k, int sm_count, int force_ctas_per_sm, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   // Persistent grid: a whole number of CTAs per SM, as many as the shared-memory footprint allows.
-  uint32_t per_sm = std::max<uint32_t>(1u, std::min<uint32_t>(8u, (uint32_t)(220u * 1024u / (k.smem_bytes + 1024u))));
+  uint32_t per_sm = std::max<uint32_t>(1u, std::min<uint32_t>(8u, (uint32_t)(224u * 1024u / (k.smem_bytes + 1024u))));
   if (force_ctas_per_sm > 0) per_sm = std::min<uint32_t>(per_sm, (uint32_t)force_ctas_per_sm);
   const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)k.n_tiles, (uint64_t)sm_count * per_sm);
   switch (k.f) {
