@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
+    ap.add_argument("--tile-bytes", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = WORKLOADS[args.workload]
@@ -217,6 +218,8 @@ def main():
         ctx.set_option(2, args.ctas_per_sm)
     if args.stages:
         ctx.set_option(3, args.stages)
+    if args.tile_bytes:
+        ctx.set_option(4, args.tile_bytes)
 
     # ---- synthetic input, resident in HBM --------------------------------------------------------
     gen = torch.Generator(device="cuda").manual_seed(0x5EED + rank)

@@ -47,6 +47,7 @@ struct csic_ctx {
   size_t opt_chunk_bytes = 64u << 20;
   int opt_ctas_per_sm = 0;
   int opt_stages = 0;
+  uint32_t opt_tile_bytes = 0;
 };
 
 namespace {
@@ -120,7 +121,7 @@ int run(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t n_frames,
   DeviceGuard guard(ctx->device);
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
   int err;
-  if (ctx->opt_family != 1 && csic::plan_rows_kernel(k, ctx->sm_count, ctx->max_smem_optin, ctx->opt_stages)) {
+  if (ctx->opt_family != 1 && csic::plan_rows_kernel(k, ctx->sm_count, ctx->max_smem_optin, ctx->opt_stages, ctx->opt_tile_bytes)) {
     err = csic::launch_rows(k, ctx->sm_count, ctx->opt_ctas_per_sm, st);
     ctx->last_family = 2;
   } else {
@@ -245,6 +246,10 @@ int csic_set_option(csic_ctx* ctx, int option, int64_t value) {
     case CSIC_OPT_STAGES:
       if (value < 0 || value > 16 || value == 1) return CSIC_EINVAL_ARG;
       ctx->opt_stages = (int)value;
+      return CSIC_OK;
+    case CSIC_OPT_TILE_BYTES:
+      if (value < 0 || value > (200 << 10)) return CSIC_EINVAL_ARG;
+      ctx->opt_tile_bytes = (uint32_t)value;
       return CSIC_OK;
     default:
       return CSIC_EINVAL_ARG;

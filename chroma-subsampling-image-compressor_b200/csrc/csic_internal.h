@@ -60,7 +60,7 @@ struct LaunchInfo {
 
 // Fills the TMA-row-kernel fields of `k`; returns false when the configuration is not eligible
 // (then the generic kernel runs).  `sm_count`/`max_smem` come from the device.
-bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_stages);
+bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_stages, uint32_t force_tile_bytes);
 
 // Both return a cudaError_t as int.
 int launch_generic(const KPlan& k, void* stream);

@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(256) csic_rows_kernel(const __grid_constant__ 
   if (kStaged && tid == 0) tma_store_wait_all();
 }
 
-bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_stages) {
+bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_stages, uint32_t force_tile_bytes) {
   if (k.average && k.f > 1) return false;                       // AVERAGE extension: generic kernel
   if (k.W % k.f != 0) return false;                             // a counter line must be whole output rows
   if (k.Wo % 16 != 0) return false;                             // 16-byte TMA granularity on the output rows
@@ -570,7 +570,7 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
   const bool staged = k.kformat <= KF_RGB888;
   const uint32_t opx = staged ? 3u : (uint32_t)k.slot_bytes;
   // Tile budget: input bytes of one tile.  Staged formats also hold two output buffers per CTA.
-  const uint32_t tile_budget = staged ? 12u * 1024u : 24u * 1024u;
+  const uint32_t tile_budget = force_tile_bytes ? force_tile_bytes : (staged ? 12u * 1024u : 24u * 1024u);
   const uint32_t row_in = (uint32_t)k.Wo * 3u * (uint32_t)k.f;  // == in_row_bytes
   int nsplit = 0;
   for (int n = (int)((row_in + tile_budget - 1) / tile_budget); n <= 64; ++n) {
@@ -603,7 +603,7 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
   auto need = [&](int s) {
     return (uint32_t)s * k.stage_stride + 2u * k.out_buf_stride + (uint32_t)s * (uint32_t)sizeof(TileMeta) + (uint32_t)s * 8u + 256u;
   };
-  while (force_stages < 2 && stages > 2 && need(stages) > 76u * 1024u) --stages;
+  while (force_stages < 2 && !force_tile_bytes && stages > 2 && need(stages) > 76u * 1024u) --stages;
   if (need(stages) > max_smem_optin) return false;
   k.stages = stages;
   k.out_buf_off = (uint32_t)stages * k.stage_stride;

@@ -180,9 +180,10 @@ CSIC_API int csic_synchronize(csic_ctx* ctx);
 /* Tuning / test knobs (never change results).  KERNEL_FAMILY: 0 = automatic (TMA row kernel whenever
  * the shape satisfies its 16-byte alignment rules, else the generic gather kernel), 1 = always the
  * generic gather kernel.  HOST_CHUNK_BYTES: input bytes per pipelined chunk of csic_process_host.
- * GRID_CTAS_PER_SM / STAGES: overrides for the row kernel's persistent grid and ring depth (0 = auto). */
+ * GRID_CTAS_PER_SM / STAGES / TILE_BYTES: overrides for the row kernel's persistent grid, ring depth and
+ * input bytes per tile (0 = auto). */
 enum csic_option { CSIC_OPT_KERNEL_FAMILY = 0, CSIC_OPT_HOST_CHUNK_BYTES = 1, CSIC_OPT_GRID_CTAS_PER_SM = 2,
-                   CSIC_OPT_STAGES = 3 };
+                   CSIC_OPT_STAGES = 3, CSIC_OPT_TILE_BYTES = 4 };
 CSIC_API int csic_set_option(csic_ctx* ctx, int option, int64_t value);
 
 /* Diagnostics: which kernel family the last process call on this ctx used (0 none, 1 generic gather
