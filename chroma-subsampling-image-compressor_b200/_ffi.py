@@ -46,6 +46,7 @@ PROTOTYPES = {
     "csic_host_free": (_int, [_vp]),
     "csic_synchronize": (_int, [_vp]),
     "csic_set_option": (_int, [_vp, _int, _i64]),
+    "csic_host_bytes": (_int, [_vp, ctypes.POINTER(ctypes.c_uint64)]),
     "csic_last_kernel": (_int, [_vp, ctypes.POINTER(_i32), ctypes.POINTER(_i64)]),
 }
 

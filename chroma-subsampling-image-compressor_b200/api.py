@@ -184,6 +184,11 @@ class Context:
     def synchronize(self):
         check(_ffi.lib().csic_synchronize(self._h))
 
+    def host_bytes(self):
+        n = ctypes.c_uint64()
+        check(_ffi.lib().csic_host_bytes(self._h, ctypes.byref(n)))
+        return n.value
+
     def last_kernel(self):
         fam, n = ctypes.c_int32(), ctypes.c_int64()
         check(_ffi.lib().csic_last_kernel(self._h, ctypes.byref(fam), ctypes.byref(n)))

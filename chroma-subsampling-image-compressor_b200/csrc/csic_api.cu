@@ -48,6 +48,9 @@ struct csic_ctx {
   int opt_ctas_per_sm = 0;
   int opt_stages = 0;
   uint32_t opt_tile_bytes = 0;
+  int opt_block_threads = 0;
+  int opt_no_compact = 0;
+  uint64_t h2d_bytes = 0;    // bytes csic_process_host has shipped host -> device so far
 };
 
 namespace {
@@ -64,13 +67,21 @@ struct DeviceGuard {
   }
 };
 
+// True when a DECIMATE pipeline reads only every f-th input row and those rows sit at a uniform pitch
+// across the frames of a batch: then csic_process_host ships just those rows over PCIe.
+bool can_compact(const csic_params& p) {
+  return p.pool_mode == CSIC_POOL_DECIMATE && p.factor > 1 && p.height % p.factor == 0;
+}
+
 int build_plan(const csic_params& p, const void* d_rgb, void* d_out, size_t n_frames, int32_t row0,
-               int32_t rows, csic::KPlan& k) {
+               int32_t rows, bool compact, csic::KPlan& k) {
   const csic::Geometry g = csic::geometry(p);
   std::memset(&k, 0, sizeof(k));
   k.in = static_cast<const uint8_t*>(d_rgb);
   k.out = static_cast<uint8_t*>(d_out);
-  k.in_frame_bytes = g.in_frame_bytes;
+  k.compact = compact ? 1 : 0;
+  k.row_step = compact ? 1 : p.factor;
+  k.in_frame_bytes = compact ? g.in_row_bytes * (size_t)g.out_h : g.in_frame_bytes;
   k.out_frame_bytes = g.out_frame_bytes;
   if (g.in_row_bytes > 0xFFFFFFFFull || g.out_row_bytes > 0xFFFFFFFFull) return CSIC_EINVAL_DIMS;
   if ((uint64_t)g.out_w * (uint64_t)g.out_h >= (1ull << 31) || (uint64_t)p.width * p.height >= (1ull << 31))
@@ -108,18 +119,19 @@ int build_plan(const csic_params& p, const void* d_rgb, void* d_out, size_t n_fr
 }
 
 int run(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t n_frames, void* d_out, int32_t row0,
-        int32_t rows, void* cuda_stream) {
+        int32_t rows, void* cuda_stream, bool compact = false) {
   if (!ctx || !p) return CSIC_EINVAL_ARG;
   int rc = csic_validate(p, nullptr, 0);
   if (rc != CSIC_OK) return rc;
   if (n_frames == 0 || rows == 0) return CSIC_OK;
   if (!d_rgb || !d_out) return CSIC_EINVAL_ARG;
   csic::KPlan k;
-  rc = build_plan(*p, d_rgb, d_out, n_frames, row0, rows, k);
+  rc = build_plan(*p, d_rgb, d_out, n_frames, row0, rows, compact, k);
   if (rc != CSIC_OK) return rc;
   if (row0 < 0 || rows < 0 || row0 + rows > k.Ho) return CSIC_EINVAL_ARG;
   DeviceGuard guard(ctx->device);
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+  k.block_threads = ctx->opt_block_threads;
   int err;
   if (ctx->opt_family != 1 && csic::plan_rows_kernel(k, ctx->sm_count, ctx->max_smem_optin, ctx->opt_stages, ctx->opt_tile_bytes)) {
     err = csic::launch_rows(k, ctx->sm_count, ctx->opt_ctas_per_sm, st);
@@ -247,6 +259,13 @@ int csic_set_option(csic_ctx* ctx, int option, int64_t value) {
       if (value < 0 || value > 16 || value == 1) return CSIC_EINVAL_ARG;
       ctx->opt_stages = (int)value;
       return CSIC_OK;
+    case CSIC_OPT_BLOCK_THREADS:
+      if (value < 0 || value > 512 || (value % 32) != 0) return CSIC_EINVAL_ARG;
+      ctx->opt_block_threads = (int)value;
+      return CSIC_OK;
+    case CSIC_OPT_HOST_FULL_FRAMES:
+      ctx->opt_no_compact = value != 0;
+      return CSIC_OK;
     case CSIC_OPT_TILE_BYTES:
       if (value < 0 || value > (200 << 10)) return CSIC_EINVAL_ARG;
       ctx->opt_tile_bytes = (uint32_t)value;
@@ -313,10 +332,13 @@ int csic_process_host(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, s
   const csic::Geometry g = csic::geometry(*p);
   DeviceGuard guard(ctx->device);
 
+  // DECIMATE with f > 1 reads only every f-th row: ship only those (a strided 2-D copy), 1/f of the H2D bytes.
+  const bool compact = can_compact(*p) && !ctx->opt_no_compact;
+  const size_t dev_frame_bytes = compact ? g.in_row_bytes * (size_t)g.out_h : g.in_frame_bytes;
   // Frames per chunk: ~opt_chunk_bytes of input, at least one frame, at most what is there.
-  size_t per = std::max<size_t>(1, ctx->opt_chunk_bytes / std::max<size_t>(1, g.in_frame_bytes));
+  size_t per = std::max<size_t>(1, ctx->opt_chunk_bytes / std::max<size_t>(1, dev_frame_bytes));
   per = std::min(per, n_frames);
-  rc = ensure_staging(ctx, per * g.in_frame_bytes, per * g.out_frame_bytes);
+  rc = ensure_staging(ctx, per * dev_frame_bytes, per * g.out_frame_bytes);
   if (rc != CSIC_OK) return rc;
 
   const size_t n_chunks = (n_frames + per - 1) / per;
@@ -328,11 +350,18 @@ int csic_process_host(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, s
       CSIC_CUDA(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_k[b], 0));
       CSIC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));
     }
-    CSIC_CUDA(cudaMemcpyAsync(ctx->d_in[b], rgb + f0 * g.in_frame_bytes, nf * g.in_frame_bytes,
-                              cudaMemcpyHostToDevice, ctx->s_h2d));
+    if (compact) {
+      CSIC_CUDA(cudaMemcpy2DAsync(ctx->d_in[b], g.in_row_bytes, rgb + f0 * g.in_frame_bytes,
+                                  g.in_row_bytes * (size_t)p->factor, g.in_row_bytes, nf * (size_t)g.out_h,
+                                  cudaMemcpyHostToDevice, ctx->s_h2d));
+    } else {
+      CSIC_CUDA(cudaMemcpyAsync(ctx->d_in[b], rgb + f0 * g.in_frame_bytes, nf * g.in_frame_bytes,
+                                cudaMemcpyHostToDevice, ctx->s_h2d));
+    }
+    ctx->h2d_bytes += compact ? nf * dev_frame_bytes : nf * g.in_frame_bytes;
     CSIC_CUDA(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
     CSIC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
-    rc = run(ctx, p, ctx->d_in[b], nf, ctx->d_out[b], 0, g.out_h, ctx->stream);
+    rc = run(ctx, p, ctx->d_in[b], nf, ctx->d_out[b], 0, g.out_h, ctx->stream, compact);
     if (rc != CSIC_OK) return rc;
     CSIC_CUDA(cudaEventRecord(ctx->ev_k[b], ctx->stream));
     CSIC_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_k[b], 0));
@@ -364,6 +393,12 @@ int csic_synchronize(csic_ctx* ctx) {
   if (!ctx) return CSIC_EINVAL_ARG;
   DeviceGuard guard(ctx->device);
   CSIC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CSIC_OK;
+}
+
+int csic_host_bytes(const csic_ctx* ctx, uint64_t* h2d_total) {
+  if (!ctx) return CSIC_EINVAL_ARG;
+  if (h2d_total) *h2d_total = ctx->h2d_bytes;
   return CSIC_OK;
 }
 

@@ -1,0 +1,60 @@
+// Device-side integer arithmetic shared by both kernels (sm_100a).
+#ifndef CSIC_DEVICE_MATH_CUH_
+#define CSIC_DEVICE_MATH_CUH_
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "csic_internal.h"
+
+namespace csic {
+
+// ------------------------------------------------------------------------------------------------
+// Forward transform on one packed pixel word p = R | G<<8 | B<<16 | (don't care)<<24.
+//
+//   Y  = (77R + 150G + 29B + 128) >> 8                      never clamps (max 255)
+//   Cb = clamp(((-43R - 85G + 128B + 128) >> 8) + 128)      only 256 -> 255 ever clamps
+// The chroma rows are evaluated *negated* so that every coefficient fits a signed byte for dp4a:
+//   x  = max(43R + 85G - 128B + 32639, 0)   ==  65535 - (cbi + 128 + 32768)   (clamped)
+//   Cb = 255 - (x >> 8)                     ==  ~byte1(x)
+// which equals the reference for all 2^24 colours (tests/test_device_math.py replays this identity
+// exhaustively; the kernel itself is checked against the oracle on the full colour cube).
+// TRUNC (Scala `/ 256`, toward zero) differs from floor only for negative numerators, i.e. x >= 32768:
+//   x -= 255 there.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t dp4a_uu(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int32_t dp4a_us(uint32_t a, uint32_t b_s8x4, int32_t c) {
+  int32_t d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b_s8x4), "r"(c));
+  return d;
+}
+
+constexpr uint32_t kCoefY = 0x001D964Du;     //  77, 150,  29, 0   (u8)
+constexpr uint32_t kCoefNCb = 0x0080552Bu;   //  43,  85,-128, 0   (s8)  == -cb row
+constexpr uint32_t kCoefNCr = 0x00156B80u;   //-128, 107,  21, 0   (s8)  == -cr row
+
+// byte 1 of the result is Y
+__device__ __forceinline__ uint32_t fwd_y16(uint32_t p) { return dp4a_uu(p, kCoefY, 128u); }
+// byte 1 of the result is ~Cb / ~Cr; result < 65536
+template <bool TRUNC>
+__device__ __forceinline__ uint32_t fwd_nc16(uint32_t p, uint32_t coef) {
+  int32_t x = max(dp4a_us(p, coef, 32639), 0);
+  if (TRUNC) x -= (x >> 15) * 255;
+  return (uint32_t)x;
+}
+
+__device__ __forceinline__ int clamp255(int v) { return min(max(v, 0), 255); }
+
+// YCbCrUtils.ycbcr2rgb with the -128 offsets folded into the constants.  Returns R | G<<8 | B<<16.
+__device__ __forceinline__ uint32_t inverse_rgb(int y, int cb, int cr) {
+  const int c = 298 * y;
+  const int r = clamp255((c + 409 * cr - 52224) >> 8);
+  const int g = clamp255((c - 100 * cb - 208 * cr + 39552) >> 8);
+  const int b = clamp255((c + 516 * cb - 65920) >> 8);
+  return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
+}
+
+}  // namespace csic
+#endif  // CSIC_DEVICE_MATH_CUH_

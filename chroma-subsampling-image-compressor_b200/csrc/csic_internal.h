@@ -40,6 +40,8 @@ struct KPlan {
   int32_t sy, scb, scr;                  // 8 - target bits
   int32_t cb_bits, cr_bits;
   int32_t row0, band_rows;               // output rows [row0, row0 + band_rows) of every frame
+  int32_t compact;                       // input holds only the rows a DECIMATE pipeline reads (every f-th), densely
+  int32_t row_step;                      // input rows between consecutive output rows: f, or 1 when compact
   uint32_t n_frames;
   // ---- TMA row kernel only ----
   int32_t hfe;                           // chroma hold width in *output* pixels inside a 4-pixel granule
@@ -49,6 +51,8 @@ struct KPlan {
   uint32_t tile_in_bytes, tile_out_bytes; // bytes of ONE row segment (input / output)
   uint32_t n_tiles;
   int32_t stages;
+  int32_t block_threads;
+  int32_t ctas_per_sm;
   uint32_t stage_stride, out_buf_off, out_buf_stride, meta_off, bar_off, smem_bytes;
   uint32_t qmask;                        // my | mcb<<8 | mcr<<16 (per-channel keep masks)
 };
@@ -65,7 +69,14 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
 // Both return a cudaError_t as int.
 int launch_generic(const KPlan& k, void* stream);
 int launch_rows(const KPlan& k, int sm_count, int force_ctas_per_sm, void* stream);
+constexpr int kDefaultBlockThreads = 256;
 int rows_kernel_set_attributes(size_t max_smem_optin);
+
+// Implemented once per spatial factor in csic_rows_kernel.cu (explicit specialisations for F = 1, 2, 4, 8).
+template <int F> int launch_rows_factor(const KPlan& k, unsigned grid, void* stream);
+template <int F> int rows_set_attributes_factor(size_t max_smem_optin);
+constexpr int kMaxTileRows = 16;        // rows per tile of the row kernel
+constexpr uint32_t kTileMetaBytes = 16 + 4 * kMaxTileRows;   // sizeof(TileMeta) in csic_rows_kernel.cu
 
 }  // namespace csic
 

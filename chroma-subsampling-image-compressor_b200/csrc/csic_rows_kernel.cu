@@ -1,0 +1,397 @@
+// The TMA-staged row kernel and its launchers for ONE spatial factor F = CSIC_ROWS_F.
+// build.sh compiles this file four times (F = 1, 2, 4, 8) in parallel.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+
+#include "csic_internal.h"
+#include "csic_device_math.cuh"
+
+#ifndef CSIC_ROWS_F
+#error "compile with -DCSIC_ROWS_F=1|2|4|8"
+#endif
+
+namespace csic {
+
+// ================================================================================================
+// TMA-staged row kernel
+// ================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// global -> shared bulk copy performed by the TMA engine; completion counted in bytes on `bar`.
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+      : "memory");
+}
+// shared -> global bulk copy (bulk async-group completion).
+__device__ __forceinline__ void tma_store_1d(void* dst, uint32_t src, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src),
+               "r"(bytes), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+// The four sampled pixels of a granule, each as a word whose low three bytes are R,G,B.
+// A granule is 4 consecutive output pixels = 4 input pixels at a stride of F pixels (3F bytes);
+// `a` is the shared-memory address of its first byte.
+template <int F>
+__device__ __forceinline__ void load_granule(uint32_t a, uint32_t (&p)[4]) {
+  if (F == 1) {                                  // 12 bytes; word stride 3 across lanes: conflict free
+    const uint32_t w0 = lds32(a), w1 = lds32(a + 4), w2 = lds32(a + 8);
+    p[0] = w0;
+    p[1] = __funnelshift_r(w0, w1, 24);
+    p[2] = __funnelshift_r(w1, w2, 16);
+    p[3] = w2 >> 8;
+  } else if (F == 2) {                           // 24 bytes, 8-byte aligned; conflict free per half warp
+    const uint2 u0 = lds64(a), u1 = lds64(a + 8), u2 = lds64(a + 16);
+    p[0] = u0.x;                                 // bytes 0..2
+    p[1] = __funnelshift_r(u0.y, u1.x, 16);      // bytes 6..8
+    p[2] = u1.y;                                 // bytes 12..14
+    p[3] = __funnelshift_r(u2.x, u2.y, 16);      // bytes 18..20
+  } else {                                       // pixels sit on word boundaries
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[j] = lds32(a + j * 3u * F);
+  }
+}
+
+// Per-stage tile descriptor: written by the producer thread before it arms the stage's mbarrier
+// (release), read by every thread after the barrier's phase flips (acquire).
+struct TileMeta {
+  uint64_t out_base;                 // global address of the tile's first output byte
+  uint32_t n_granules;               // rows * granules per row segment
+  uint32_t any_held;                 // some row of the tile replays a held chroma pair
+  uint32_t held_addr[kMaxTileRows];  // per row: 0, or shared address of the RGB pixel whose chroma the row replays
+};
+static_assert(sizeof(TileMeta) == kTileMetaBytes, "kTileMetaBytes out of sync");
+
+// Runtime constants of the inner loop, hoisted into registers once per kernel.
+struct LoopConst {
+  uint32_t qm0, qm1, qm2;            // YCC888: quantiser keep-masks over the three packed words
+  uint32_t my, mcb, mcr;             // RGB888
+  int shy, shb, shr, ly, lb;         // bundles
+  uint32_t gran_per_row;
+  uint32_t row0_of_thread, rem0_of_thread;   // threadIdx.x / gran_per_row, threadIdx.x % gran_per_row
+  uint32_t drow, drem;                       // blockDim.x / gran_per_row, blockDim.x % gran_per_row
+};
+
+// One tile: a flat loop over its granules.  Rows are packed back to back in the stage (and, for the
+// staged formats, in the output buffer), so granule q lives at  base + q * granule_bytes  and the row
+// index is only needed to look up a held chroma pair (HELD tiles).
+//   HFE   chroma hold width inside a granule, in output pixels (1, 2 or 4)
+//   HELD  the tile may contain rows that replay a held pair (odd 4:2:0 / 4:1:0 lines)
+//   Q8    8/8/8 bits in a 32-bit slot: pure byte permutes
+template <int F, int FMT, int HFE, bool HELD, bool Q8, bool TRUNC>
+__device__ __forceinline__ void tile_loop(uint32_t in_s, uint32_t out_s, uint8_t* __restrict__ out_g,
+                                          const TileMeta* __restrict__ meta, const LoopConst& C) {
+  const uint32_t n = meta->n_granules;
+  uint32_t row = C.row0_of_thread, rem = C.rem0_of_thread;   // row of granule q, tracked without a division
+  for (uint32_t q = threadIdx.x; q < n; q += blockDim.x) {
+    uint32_t p[4];
+    load_granule<F>(in_s + q * (12u * F), p);
+    uint32_t dy[4], xb[4], xr[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dy[j] = fwd_y16(p[j]);
+    uint32_t haddr = 0;
+    if (HELD) {
+      haddr = meta->held_addr[row];
+      row += C.drow;
+      rem += C.drem;
+      if (rem >= C.gran_per_row) { rem -= C.gran_per_row; ++row; }
+    }
+    if (HELD && haddr != 0) {
+      const uint32_t hp = lds8(haddr) | (lds8(haddr + 1) << 8) | (lds8(haddr + 2) << 16);
+      const uint32_t hb = fwd_nc16<TRUNC>(hp, kCoefNCb), hr = fwd_nc16<TRUNC>(hp, kCoefNCr);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { xb[j] = hb; xr[j] = hr; }
+    } else {
+      // sample where j % HFE == 0, hold in between (ChromaSubsampler.scala:57-65)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j % HFE == 0) {
+          xb[j] = fwd_nc16<TRUNC>(p[j], kCoefNCb);
+          xr[j] = fwd_nc16<TRUNC>(p[j], kCoefNCr);
+        } else {
+          xb[j] = xb[j - 1];
+          xr[j] = xr[j - 1];
+        }
+      }
+    }
+
+    if (FMT == KF_YCC888) {
+      // byte 1 of dy is Y, byte 1 of xb/xr is ~Cb/~Cr: gather with PRMT, flip and quantise per word.
+      uint32_t t, u;
+      t = __byte_perm(dy[0], xb[0], 0x0051); u = __byte_perm(xr[0], dy[1], 0x0051);
+      const uint32_t w0 = (__byte_perm(t, u, 0x5410) ^ 0x00FFFF00u) & C.qm0;
+      t = __byte_perm(xb[1], xr[1], 0x0051); u = __byte_perm(dy[2], xb[2], 0x0051);
+      const uint32_t w1 = (__byte_perm(t, u, 0x5410) ^ 0xFF00FFFFu) & C.qm1;
+      t = __byte_perm(xr[2], dy[3], 0x0051); u = __byte_perm(xb[3], xr[3], 0x0051);
+      const uint32_t w2 = (__byte_perm(t, u, 0x5410) ^ 0xFFFF00FFu) & C.qm2;
+      const uint32_t a = out_s + q * 12u;
+      sts32(a, w0); sts32(a + 4, w1); sts32(a + 8, w2);
+    } else if (FMT == KF_RGB888) {
+      uint32_t v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int y = (int)((dy[j] >> 8) & C.my);
+        const int cb = (int)((255u - (xb[j] >> 8)) & C.mcb);
+        const int cr = (int)((255u - (xr[j] >> 8)) & C.mcr);
+        v[j] = inverse_rgb(y, cb, cr);
+      }
+      const uint32_t a = out_s + q * 12u;
+      sts32(a, v[0] | (v[1] << 24));
+      sts32(a + 4, (v[1] >> 8) | (v[2] << 16));
+      sts32(a + 8, (v[2] >> 16) | (v[3] << 8));
+    } else {
+      // bundle slots go straight to global memory: one coalesced 4/8/16-byte store per granule
+      uint32_t v[4];
+      if (Q8) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)   // (Cr, Cb, Y, 0): dy < 65536 so its byte 3 is the zero pad
+          v[j] = __byte_perm(__byte_perm(xr[j], xb[j], 0x0051), dy[j], 0x7510) ^ 0x0000FFFFu;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          v[j] = ((dy[j] >> C.shy) << C.ly) | (((xb[j] ^ 0xFFFFu) >> C.shb) << C.lb) | ((xr[j] ^ 0xFFFFu) >> C.shr);
+      }
+      if (FMT == KF_SLOT32) __stcs(reinterpret_cast<uint4*>(out_g) + q, make_uint4(v[0], v[1], v[2], v[3]));
+      else if (FMT == KF_SLOT16) __stcs(reinterpret_cast<uint2*>(out_g) + q, make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16)));
+      else __stcs(reinterpret_cast<uint32_t*>(out_g) + q, v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
+    }
+  }
+}
+
+template <int F, int FMT, bool Q8, bool TRUNC>
+__global__ void __launch_bounds__(512) csic_rows_kernel(const __grid_constant__ KPlan P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr bool kStaged = (FMT == KF_YCC888 || FMT == KF_RGB888);   // output leaves through smem + TMA store
+  const uint32_t tid = threadIdx.x;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t S = (uint32_t)P.stages;
+  const uint32_t n_my = (P.n_tiles > blockIdx.x) ? (P.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const uint64_t pol = policy_evict_first();   // every byte is touched exactly once: do not keep it in L2
+
+  // -- producer (thread 0): tile i of this CTA -> stage i % S ------------------------------------
+  auto issue_load = [&](uint32_t i) {
+    const uint32_t tile = blockIdx.x + i * gridDim.x;
+    const uint32_t t2 = tile / (uint32_t)P.nsplit;
+    const uint32_t seg = tile - t2 * (uint32_t)P.nsplit;
+    const uint32_t k = t2 / P.tiles_per_band;
+    const uint32_t tb = t2 - k * P.tiles_per_band;
+    const uint32_t ro0 = (uint32_t)P.row0 + tb * (uint32_t)P.tile_rows;
+    const uint32_t nrows = min((uint32_t)P.tile_rows, (uint32_t)(P.row0 + P.band_rows) - ro0);
+    const uint32_t s = i % S;
+    const uint8_t* frame = P.in + (uint64_t)k * P.in_frame_bytes;
+    const uint32_t bar = sbase + P.bar_off + s * 8u;
+    const uint32_t dst = sbase + s * P.stage_stride;
+    const uint32_t aux = dst + (uint32_t)P.tile_rows * P.tile_in_bytes;    // 32-byte window per row
+    TileMeta* m = reinterpret_cast<TileMeta*>(smem + P.meta_off) + s;
+
+    // Which rows replay a held chroma pair, and from where?  (KPlan::hfe covers the in-row hold.)
+    uint32_t n_aux = 0, any = 0;
+    const uint8_t* aux_src[kMaxTileRows];
+    if (P.vf == 2) {
+      for (uint32_t j = 0; j < nrows; ++j) {
+        const uint32_t ro = ro0 + j;
+        uint32_t h = 0;
+        const uint8_t* hp = nullptr;
+        if (!P.case_b) {
+          if (F == 1 && (ro & 1)) {          // odd line at full resolution: last sample point of the line above
+            if (j > 0 && P.nsplit == 1) h = dst + (j - 1) * P.tile_in_bytes + (uint32_t)P.last_sample_col * 3u;   // in this tile
+            else hp = frame + (uint64_t)(ro - 1) * P.in_row_bytes + (uint32_t)P.last_sample_col * 3u;
+          }
+        } else {
+          const uint32_t line = ro / F;      // W == F * Wo: one counter line spans F output rows
+          if (line & 1) {
+            const uint32_t srow = (line - 1) * F + (uint32_t)P.last_sample_col / (uint32_t)P.Wo;
+            const uint32_t scol = (uint32_t)P.last_sample_col % (uint32_t)P.Wo;
+            hp = frame + (uint64_t)(srow * (uint32_t)P.row_step) * P.in_row_bytes + (uint64_t)scol * (3u * F);
+          }
+        }
+        if (hp) {
+          const uint64_t a = reinterpret_cast<uint64_t>(hp);
+          h = aux + j * 32u + (uint32_t)(a & 15u);
+          aux_src[j] = reinterpret_cast<const uint8_t*>(a & ~(uint64_t)15);
+          ++n_aux;
+        } else {
+          aux_src[j] = nullptr;
+        }
+        m->held_addr[j] = h;
+        any |= h;
+      }
+    }
+    m->any_held = any;
+    m->n_granules = nrows * ((uint32_t)P.tile_px >> 2);
+    m->out_base = reinterpret_cast<uint64_t>(P.out) + (uint64_t)k * P.out_frame_bytes + (uint64_t)ro0 * P.out_row_bytes +
+                  (uint64_t)seg * P.tile_out_bytes;
+    mbar_expect_tx(bar, nrows * P.tile_in_bytes + n_aux * 32u);
+    const uint8_t* src = frame + (uint64_t)(ro0 * (uint32_t)P.row_step) * P.in_row_bytes + (uint64_t)seg * P.tile_in_bytes;
+    if (P.row_step == 1 && P.nsplit == 1) {  // consecutive rows are contiguous in memory: one bulk copy
+      tma_load_1d(dst, src, nrows * P.tile_in_bytes, bar, pol);
+    } else {
+      for (uint32_t j = 0; j < nrows; ++j)
+        tma_load_1d(dst + j * P.tile_in_bytes, src + (uint64_t)j * (uint32_t)P.row_step * P.in_row_bytes, P.tile_in_bytes, bar, pol);
+    }
+    if (n_aux) {
+      for (uint32_t j = 0; j < nrows; ++j)
+        if (aux_src[j]) tma_load_1d(aux + j * 32u, aux_src[j], 32u, bar, pol);
+    }
+  };
+
+  if (tid == 0) {
+    for (uint32_t s = 0; s < S; ++s) mbar_init(sbase + P.bar_off + s * 8u, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (uint32_t i = 0; i + 1 < S && i < n_my; ++i) issue_load(i);
+  }
+
+  LoopConst C;
+  {
+    const uint32_t my = P.qmask & 0xFFu, mcb = (P.qmask >> 8) & 0xFFu, mcr = (P.qmask >> 16) & 0xFFu;
+    C.qm0 = my | (mcb << 8) | (mcr << 16) | (my << 24);
+    C.qm1 = mcb | (mcr << 8) | (my << 16) | (mcb << 24);
+    C.qm2 = mcr | (my << 8) | (mcb << 16) | (mcr << 24);
+    C.my = my; C.mcb = mcb; C.mcr = mcr;
+    C.shy = 8 + P.sy; C.shb = 8 + P.scb; C.shr = 8 + P.scr;
+    C.ly = P.cb_bits + P.cr_bits; C.lb = P.cr_bits;
+    C.gran_per_row = (uint32_t)P.tile_px >> 2;
+    C.row0_of_thread = tid / C.gran_per_row;
+    C.rem0_of_thread = tid % C.gran_per_row;
+    C.drow = blockDim.x / C.gran_per_row;
+    C.drem = blockDim.x % C.gran_per_row;
+  }
+  const int hfe = P.hfe;
+
+  for (uint32_t i = 0; i < n_my; ++i) {
+    const uint32_t s = i % S;
+    // Refill the stage that was consumed in iteration i-1 (everyone passed that iteration's barrier).
+    if (tid == 0 && i + S - 1 < n_my) issue_load(i + S - 1);
+    mbar_wait(sbase + P.bar_off + s * 8u, (i / S) & 1u);
+
+    const uint32_t in_s = sbase + s * P.stage_stride;
+    const uint32_t out_s = sbase + P.out_buf_off + (i & 1u) * P.out_buf_stride;
+    const TileMeta* m = reinterpret_cast<const TileMeta*>(smem + P.meta_off) + s;
+    uint8_t* out_g = reinterpret_cast<uint8_t*>(m->out_base);
+    if (m->any_held) {
+      if (hfe == 1) tile_loop<F, FMT, 1, true, Q8, TRUNC>(in_s, out_s, out_g, m, C);
+      else if (hfe == 2) tile_loop<F, FMT, 2, true, Q8, TRUNC>(in_s, out_s, out_g, m, C);
+      else tile_loop<F, FMT, 4, true, Q8, TRUNC>(in_s, out_s, out_g, m, C);
+    } else {
+      if (hfe == 1) tile_loop<F, FMT, 1, false, Q8, TRUNC>(in_s, out_s, out_g, m, C);
+      else if (hfe == 2) tile_loop<F, FMT, 2, false, Q8, TRUNC>(in_s, out_s, out_g, m, C);
+      else tile_loop<F, FMT, 4, false, Q8, TRUNC>(in_s, out_s, out_g, m, C);
+    }
+
+    if (kStaged) {
+      // Hand the tile to the TMA engine.  Generic-proxy writes must be fenced before the async proxy
+      // reads them; the staging buffer used two tiles ago must have been read out before it is reused.
+      const uint32_t bytes = m->n_granules * 12u;
+      fence_proxy_async_smem();
+      if (tid == 0) tma_store_wait_read0();
+      __syncthreads();
+      if (tid == 0) {
+        tma_store_1d(out_g, out_s, bytes, pol);
+        tma_store_commit();
+      }
+    } else {
+      __syncthreads();    // everyone is done reading stage s (and its meta) before it is refilled
+    }
+  }
+  if (kStaged && tid == 0) tma_store_wait_all();
+}
+
+
+namespace {
+constexpr int kF = CSIC_ROWS_F;
+
+template <int FMT, bool Q8, bool TR>
+int launch_one(const KPlan& k, unsigned grid, cudaStream_t st) {
+  csic_rows_kernel<kF, FMT, Q8, TR><<<grid, (unsigned)k.block_threads, k.smem_bytes, st>>>(k);
+  return (int)cudaGetLastError();
+}
+template <int FMT>
+int launch_fmt(const KPlan& k, unsigned grid, cudaStream_t st) {
+  const bool q8 = FMT == KF_SLOT32 && k.sy == 0 && k.scb == 0 && k.scr == 0;
+  if (q8) return k.trunc ? launch_one<FMT, (FMT == KF_SLOT32), true>(k, grid, st) : launch_one<FMT, (FMT == KF_SLOT32), false>(k, grid, st);
+  return k.trunc ? launch_one<FMT, false, true>(k, grid, st) : launch_one<FMT, false, false>(k, grid, st);
+}
+template <int FMT, bool Q8, bool TR>
+cudaError_t attr_one(size_t bytes) {
+  return cudaFuncSetAttribute(csic_rows_kernel<kF, FMT, Q8, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+}  // namespace
+
+template <>
+int launch_rows_factor<CSIC_ROWS_F>(const KPlan& k, unsigned grid, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (k.kformat) {
+    case KF_YCC888: return launch_fmt<KF_YCC888>(k, grid, st);
+    case KF_RGB888: return launch_fmt<KF_RGB888>(k, grid, st);
+    case KF_SLOT8: return launch_fmt<KF_SLOT8>(k, grid, st);
+    case KF_SLOT16: return launch_fmt<KF_SLOT16>(k, grid, st);
+    default: return launch_fmt<KF_SLOT32>(k, grid, st);
+  }
+}
+
+template <>
+int rows_set_attributes_factor<CSIC_ROWS_F>(size_t b) {
+  cudaError_t e;
+#define CSIC_ATTR(FMT, Q8)                                                   \
+  if ((e = attr_one<FMT, Q8, false>(b)) != cudaSuccess) return (int)e;       \
+  if ((e = attr_one<FMT, Q8, true>(b)) != cudaSuccess) return (int)e;
+  CSIC_ATTR(KF_YCC888, false) CSIC_ATTR(KF_RGB888, false) CSIC_ATTR(KF_SLOT8, false) CSIC_ATTR(KF_SLOT16, false)
+  CSIC_ATTR(KF_SLOT32, false) CSIC_ATTR(KF_SLOT32, true)
+#undef CSIC_ATTR
+  return (int)cudaSuccess;
+}
+
+}  // namespace csic

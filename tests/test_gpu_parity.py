@@ -235,6 +235,28 @@ def test_host_pipeline_chunking_and_pinned(csic, ctx):
     pin_in.free(); pin_out.free()
 
 
+def test_host_path_ships_only_the_rows_decimate_reads(csic, ctx):
+    """With DECIMATE and f>1, csic_process_host copies every f-th input row only (1/f of the H2D bytes);
+    results must equal the full-frame copy path and the oracle, for both stage orders and both kernels."""
+    W, H, n = 128, 64, 5
+    rgb = synth_frames(n, H, W, seed=33)
+    for f, order, fmt in itertools.product((2, 4, 8), ("CSQ", "SQC"), (0, 3)):
+        p, po = both_params(csic, W, H, 2, 0, (8, 8, 8), f, order, 0, 0, fmt)
+        want = oracle.process(po, rgb)
+        for family in (0, 1):
+            ctx.set_option(0, family)
+            b0 = ctx.host_bytes()
+            got = ctx.process_host(p, rgb)
+            assert ctx.host_bytes() - b0 == n * (H // f) * W * 3
+            ctx.set_option(6, 1)
+            b0 = ctx.host_bytes()
+            full = ctx.process_host(p, rgb)
+            assert ctx.host_bytes() - b0 == n * H * W * 3
+            ctx.set_option(6, 0)
+            assert np.array_equal(got, want) and np.array_equal(full, want), (f, order, fmt, family)
+    ctx.set_option(0, 0)
+
+
 def test_empty_batch_and_errors(csic, ctx):
     p, _ = both_params(csic, 16, 16, 4, 4, (8, 8, 8), 1, "CSQ")
     out = ctx.process_host(p, np.zeros((0, 16, 16, 3), np.uint8))

@@ -1,0 +1,7 @@
+# focused A/B at full batch size; each point twice
+W=${W:-cfg4}
+for rep in ${REPS:-1}; do
+for nt in 128 256 512; do for tb in 24576 49152; do for st in 2 3; do
+  r=$(python bench.py --workload $W --no-e2e --no-cpu --steps 100 --tile-bytes $tb --stages $st --block-threads $nt 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['roofline']['frac'], d['ms_per_step'], d['step_ms_min'])" 2>&1 | tail -1)
+  echo "$W nt=$nt tile=$tb stages=$st -> $r"
+done; done; done; done
