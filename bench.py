@@ -146,7 +146,8 @@ def run_reference(args, wl, name):
         return
     W, H, _, a, b, q, f, order, fmt, desc = wl
     cores = os.cpu_count() or 1
-    frames = max(cores, min(4 * cores, int(2.0e9 / (W * H * 3 * 4)) or 1))   # bounded sample, ~<= 2 GB of staging
+    per_thread = max(1, min(4, int(3.0e9 / (W * H * 3 * 4 * cores))))          # bounded sample, <= ~3 GB of staging
+    frames = cores * per_thread                                                # whole frames per thread: no imbalance
     mps, ms = oracle_throughput(wl, frames, cores, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": "input megapixels/s", "value": round(mps, 2), "unit": "MP/s",
@@ -347,7 +348,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        fr = max(cores, min(2 * cores, 64))
+        fr = cores * max(1, min(4, int(3.0e9 / (W * H * 3 * 4 * cores))))
         mps, _ = oracle_throughput(wl, fr, cores, steps=2, warmup=1)
         cpu = {"value": round(mps, 2), "unit": "MP/s", "cores": cores, "kind": "port",
                "sample": f"{fr} frames of {W}x{H}, 2 timed passes, {cores} host threads (oracle/csic_oracle.c)"}
