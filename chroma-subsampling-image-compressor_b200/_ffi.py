@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcsic.so")
+# CSIC_LIB_PATH lets tools/ A/B two builds of the library on the same GPU box; default is the in-tree build.
+LIB_PATH = os.environ.get("CSIC_LIB_PATH") or os.path.join(_HERE, "libcsic.so")
 
 
 class CsicParams(ctypes.Structure):

@@ -35,6 +35,7 @@ struct KPlan {
   int32_t f;
   int32_t hf, vf, last_sample_col;       // ((W-1)/hf)*hf : last chroma sample column of a line
   int32_t case_b;                        // spatial before chroma with f > 1 (misaligned counters)
+  uint32_t caseb_row_add, caseb_col_bytes; // case B: held pixel = decimated-stream element (line-1)*W + last_sample_col
   int32_t quant_first, trunc, average;
   int32_t kformat, slot_bytes, slots_per_row;
   int32_t sy, scb, scr;                  // 8 - target bits
@@ -69,7 +70,8 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
 // Both return a cudaError_t as int.
 int launch_generic(const KPlan& k, void* stream);
 int launch_rows(const KPlan& k, int sm_count, int force_ctas_per_sm, void* stream);
-constexpr int kDefaultBlockThreads = 256;
+constexpr int kDefaultBlockThreads = 256;   // consumer threads; one producer warp is added at launch
+constexpr int kMaxConsumerThreads = 512;
 int rows_kernel_set_attributes(size_t max_smem_optin);
 
 // Implemented once per spatial factor in csic_rows_kernel.cu (explicit specialisations for F = 1, 2, 4, 8).

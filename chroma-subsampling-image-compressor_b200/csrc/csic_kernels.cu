@@ -181,6 +181,11 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
   if (k.case_b && k.Wo < 4) return false;
   if (k.band_rows <= 0 || k.n_frames == 0) return false;
   if (k.block_threads <= 0) k.block_threads = kDefaultBlockThreads;
+  if (k.block_threads > kMaxConsumerThreads) return false;
+  if (k.case_b) {
+    k.caseb_row_add = (uint32_t)k.last_sample_col / (uint32_t)k.Wo;
+    k.caseb_col_bytes = ((uint32_t)k.last_sample_col % (uint32_t)k.Wo) * 3u * (uint32_t)k.f;
+  }
 
   // hold width inside a granule, in output pixels
   if (!k.case_b) k.hfe = std::max(1, k.hf / k.f);
@@ -225,7 +230,7 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
   };
   auto ctas_for = [&](int s) {
     const uint32_t by_smem = (uint32_t)(227u * 1024u / (need(s) + 1024u));
-    return std::min<uint32_t>(std::min<uint32_t>(by_smem, 2048u / (uint32_t)k.block_threads), 8u);
+    return std::min<uint32_t>(std::min<uint32_t>(by_smem, 2048u / ((uint32_t)k.block_threads + 32u)), 8u);
   };
   int stages = 2;
   if (force_stages >= 2) {
@@ -243,7 +248,7 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
   k.out_buf_off = (uint32_t)stages * k.stage_stride;
   k.meta_off = up128(k.out_buf_off + 2u * k.out_buf_stride);
   k.bar_off = up128(k.meta_off + (uint32_t)stages * (uint32_t)kTileMetaBytes);
-  k.smem_bytes = k.bar_off + (uint32_t)stages * 8u;
+  k.smem_bytes = k.bar_off + (uint32_t)stages * 16u;     // full[] and empty[] mbarriers
   return true;
 }
 

@@ -25,6 +25,13 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// named barrier 1 over the consumer threads only (the producer warp never joins it)
+__device__ __forceinline__ void consumer_barrier(uint32_t n_threads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   do {
@@ -118,6 +125,7 @@ struct LoopConst {
   uint32_t my, mcb, mcr;             // RGB888
   int shy, shb, shr, ly, lb;         // bundles
   uint32_t gran_per_row;
+  uint32_t nthreads;                         // consumer threads per CTA
   uint32_t row0_of_thread, rem0_of_thread;   // threadIdx.x / gran_per_row, threadIdx.x % gran_per_row
   uint32_t drow, drem;                       // blockDim.x / gran_per_row, blockDim.x % gran_per_row
 };
@@ -133,7 +141,7 @@ __device__ __forceinline__ void tile_loop(uint32_t in_s, uint32_t out_s, uint8_t
                                           const TileMeta* __restrict__ meta, const LoopConst& C) {
   const uint32_t n = meta->n_granules;
   uint32_t row = C.row0_of_thread, rem = C.rem0_of_thread;   // row of granule q, tracked without a division
-  for (uint32_t q = threadIdx.x; q < n; q += blockDim.x) {
+  for (uint32_t q = threadIdx.x; q < n; q += C.nthreads) {
     uint32_t p[4];
     load_granule<F>(in_s + q * (12u * F), p);
     uint32_t dy[4], xb[4], xr[4];
@@ -209,91 +217,101 @@ __device__ __forceinline__ void tile_loop(uint32_t in_s, uint32_t out_s, uint8_t
 }
 
 template <int F, int FMT, bool Q8, bool TRUNC>
-__global__ void __launch_bounds__(512) csic_rows_kernel(const __grid_constant__ KPlan P) {
+__global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(const __grid_constant__ KPlan P) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr bool kStaged = (FMT == KF_YCC888 || FMT == KF_RGB888);   // output leaves through smem + TMA store
   const uint32_t tid = threadIdx.x;
+  const uint32_t NC = blockDim.x - 32u;        // consumer threads; the last warp is the producer
   const uint32_t sbase = smem_u32(smem);
   const uint32_t S = (uint32_t)P.stages;
   const uint32_t n_my = (P.n_tiles > blockIdx.x) ? (P.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const uint64_t pol = policy_evict_first();   // every byte is touched exactly once: do not keep it in L2
-
-  // -- producer (thread 0): tile i of this CTA -> stage i % S ------------------------------------
-  auto issue_load = [&](uint32_t i) {
-    const uint32_t tile = blockIdx.x + i * gridDim.x;
-    const uint32_t t2 = tile / (uint32_t)P.nsplit;
-    const uint32_t seg = tile - t2 * (uint32_t)P.nsplit;
-    const uint32_t k = t2 / P.tiles_per_band;
-    const uint32_t tb = t2 - k * P.tiles_per_band;
-    const uint32_t ro0 = (uint32_t)P.row0 + tb * (uint32_t)P.tile_rows;
-    const uint32_t nrows = min((uint32_t)P.tile_rows, (uint32_t)(P.row0 + P.band_rows) - ro0);
-    const uint32_t s = i % S;
-    const uint8_t* frame = P.in + (uint64_t)k * P.in_frame_bytes;
-    const uint32_t bar = sbase + P.bar_off + s * 8u;
-    const uint32_t dst = sbase + s * P.stage_stride;
-    const uint32_t aux = dst + (uint32_t)P.tile_rows * P.tile_in_bytes;    // 32-byte window per row
-    TileMeta* m = reinterpret_cast<TileMeta*>(smem + P.meta_off) + s;
-
-    // Which rows replay a held chroma pair, and from where?  (KPlan::hfe covers the in-row hold.)
-    uint32_t n_aux = 0, any = 0;
-    const uint8_t* aux_src[kMaxTileRows];
-    if (P.vf == 2) {
-      for (uint32_t j = 0; j < nrows; ++j) {
-        const uint32_t ro = ro0 + j;
-        uint32_t h = 0;
-        const uint8_t* hp = nullptr;
-        if (!P.case_b) {
-          if (F == 1 && (ro & 1)) {          // odd line at full resolution: last sample point of the line above
-            if (j > 0 && P.nsplit == 1) h = dst + (j - 1) * P.tile_in_bytes + (uint32_t)P.last_sample_col * 3u;   // in this tile
-            else hp = frame + (uint64_t)(ro - 1) * P.in_row_bytes + (uint32_t)P.last_sample_col * 3u;
-          }
-        } else {
-          const uint32_t line = ro / F;      // W == F * Wo: one counter line spans F output rows
-          if (line & 1) {
-            const uint32_t srow = (line - 1) * F + (uint32_t)P.last_sample_col / (uint32_t)P.Wo;
-            const uint32_t scol = (uint32_t)P.last_sample_col % (uint32_t)P.Wo;
-            hp = frame + (uint64_t)(srow * (uint32_t)P.row_step) * P.in_row_bytes + (uint64_t)scol * (3u * F);
-          }
-        }
-        if (hp) {
-          const uint64_t a = reinterpret_cast<uint64_t>(hp);
-          h = aux + j * 32u + (uint32_t)(a & 15u);
-          aux_src[j] = reinterpret_cast<const uint8_t*>(a & ~(uint64_t)15);
-          ++n_aux;
-        } else {
-          aux_src[j] = nullptr;
-        }
-        m->held_addr[j] = h;
-        any |= h;
-      }
-    }
-    m->any_held = any;
-    m->n_granules = nrows * ((uint32_t)P.tile_px >> 2);
-    m->out_base = reinterpret_cast<uint64_t>(P.out) + (uint64_t)k * P.out_frame_bytes + (uint64_t)ro0 * P.out_row_bytes +
-                  (uint64_t)seg * P.tile_out_bytes;
-    mbar_expect_tx(bar, nrows * P.tile_in_bytes + n_aux * 32u);
-    const uint8_t* src = frame + (uint64_t)(ro0 * (uint32_t)P.row_step) * P.in_row_bytes + (uint64_t)seg * P.tile_in_bytes;
-    if (P.row_step == 1 && P.nsplit == 1) {  // consecutive rows are contiguous in memory: one bulk copy
-      tma_load_1d(dst, src, nrows * P.tile_in_bytes, bar, pol);
-    } else {
-      for (uint32_t j = 0; j < nrows; ++j)
-        tma_load_1d(dst + j * P.tile_in_bytes, src + (uint64_t)j * (uint32_t)P.row_step * P.in_row_bytes, P.tile_in_bytes, bar, pol);
-    }
-    if (n_aux) {
-      for (uint32_t j = 0; j < nrows; ++j)
-        if (aux_src[j]) tma_load_1d(aux + j * 32u, aux_src[j], 32u, bar, pol);
-    }
-  };
+  const uint32_t full_bar = sbase + P.bar_off, empty_bar = full_bar + S * 8u;
 
   if (tid == 0) {
-    for (uint32_t s = 0; s < S; ++s) mbar_init(sbase + P.bar_off + s * 8u, 1);
+    for (uint32_t s = 0; s < S; ++s) {
+      mbar_init(full_bar + s * 8u, 1);            // the producer's arrive.expect_tx
+      mbar_init(empty_bar + s * 8u, NC / 32u);    // one arrive per consumer warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (tid == 0) {
-    for (uint32_t i = 0; i + 1 < S && i < n_my; ++i) issue_load(i);
+
+  // ============================== producer warp ==============================================
+  // One lane walks this CTA's tiles, S deep ahead of the consumers: describe the tile in the stage's
+  // TileMeta, arm the stage's mbarrier with the byte count, and hand the copies to the TMA engine.
+  if (tid >= NC) {
+    if (tid != NC) return;
+    for (uint32_t i = 0; i < n_my; ++i) {
+      const uint32_t s = i % S;
+      if (i >= S) mbar_wait(empty_bar + s * 8u, ((i / S) - 1u) & 1u);   // consumers drained the previous use
+      const uint32_t tile = blockIdx.x + i * gridDim.x;
+      const uint32_t t2 = tile / (uint32_t)P.nsplit;
+      const uint32_t seg = tile - t2 * (uint32_t)P.nsplit;
+      const uint32_t k = t2 / P.tiles_per_band;
+      const uint32_t tb = t2 - k * P.tiles_per_band;
+      const uint32_t ro0 = (uint32_t)P.row0 + tb * (uint32_t)P.tile_rows;
+      const uint32_t nrows = min((uint32_t)P.tile_rows, (uint32_t)(P.row0 + P.band_rows) - ro0);
+      const uint8_t* frame = P.in + (uint64_t)k * P.in_frame_bytes;
+      const uint32_t bar = full_bar + s * 8u;
+      const uint32_t dst = sbase + s * P.stage_stride;
+      const uint32_t aux = dst + (uint32_t)P.tile_rows * P.tile_in_bytes;    // 32-byte window per row
+      TileMeta* m = reinterpret_cast<TileMeta*>(smem + P.meta_off) + s;
+
+      // Which rows replay a held chroma pair, and from where?  (KPlan::hfe covers the in-row hold.)
+      uint32_t n_aux = 0, any = 0;
+      const uint8_t* aux_src[kMaxTileRows];
+      if (P.vf == 2) {
+        for (uint32_t j = 0; j < nrows; ++j) {
+          const uint32_t ro = ro0 + j;
+          uint32_t h = 0;
+          const uint8_t* hp = nullptr;
+          if (!P.case_b) {
+            if (F == 1 && (ro & 1)) {          // odd line at full resolution: last sample point of the line above
+              if (j > 0 && P.nsplit == 1) h = dst + (j - 1) * P.tile_in_bytes + (uint32_t)P.last_sample_col * 3u;   // in this tile
+              else hp = frame + (uint64_t)(ro - 1) * P.in_row_bytes + (uint32_t)P.last_sample_col * 3u;
+            }
+          } else {
+            const uint32_t line = ro / F;      // W == F * Wo: one counter line spans F output rows
+            if (line & 1) {                    // held from (line-1, lastSampleCol) of the decimated stream
+              const uint32_t srow = (line - 1) * F + P.caseb_row_add;
+              hp = frame + (uint64_t)(srow * (uint32_t)P.row_step) * P.in_row_bytes + P.caseb_col_bytes;
+            }
+          }
+          if (hp) {
+            const uint64_t a = reinterpret_cast<uint64_t>(hp);
+            h = aux + j * 32u + (uint32_t)(a & 15u);
+            aux_src[j] = reinterpret_cast<const uint8_t*>(a & ~(uint64_t)15);
+            ++n_aux;
+          } else {
+            aux_src[j] = nullptr;
+          }
+          m->held_addr[j] = h;
+          any |= h;
+        }
+      }
+      m->any_held = any;
+      m->n_granules = nrows * ((uint32_t)P.tile_px >> 2);
+      m->out_base = reinterpret_cast<uint64_t>(P.out) + (uint64_t)k * P.out_frame_bytes + (uint64_t)ro0 * P.out_row_bytes +
+                    (uint64_t)seg * P.tile_out_bytes;
+      // meta is published by the release of this arrive and observed after the consumers' acquire-wait
+      mbar_expect_tx(bar, nrows * P.tile_in_bytes + n_aux * 32u);
+      const uint8_t* src = frame + (uint64_t)(ro0 * (uint32_t)P.row_step) * P.in_row_bytes + (uint64_t)seg * P.tile_in_bytes;
+      if (P.row_step == 1 && P.nsplit == 1) {  // consecutive rows are contiguous in memory: one bulk copy
+        tma_load_1d(dst, src, nrows * P.tile_in_bytes, bar, pol);
+      } else {
+        for (uint32_t j = 0; j < nrows; ++j)
+          tma_load_1d(dst + j * P.tile_in_bytes, src + (uint64_t)j * (uint32_t)P.row_step * P.in_row_bytes, P.tile_in_bytes, bar, pol);
+      }
+      if (n_aux) {
+        for (uint32_t j = 0; j < nrows; ++j)
+          if (aux_src[j]) tma_load_1d(aux + j * 32u, aux_src[j], 32u, bar, pol);
+      }
+    }
+    return;
   }
 
+  // ============================== consumer warps =============================================
   LoopConst C;
   {
     const uint32_t my = P.qmask & 0xFFu, mcb = (P.qmask >> 8) & 0xFFu, mcr = (P.qmask >> 16) & 0xFFu;
@@ -304,23 +322,23 @@ __global__ void __launch_bounds__(512) csic_rows_kernel(const __grid_constant__ 
     C.shy = 8 + P.sy; C.shb = 8 + P.scb; C.shr = 8 + P.scr;
     C.ly = P.cb_bits + P.cr_bits; C.lb = P.cr_bits;
     C.gran_per_row = (uint32_t)P.tile_px >> 2;
+    C.nthreads = NC;
     C.row0_of_thread = tid / C.gran_per_row;
     C.rem0_of_thread = tid % C.gran_per_row;
-    C.drow = blockDim.x / C.gran_per_row;
-    C.drem = blockDim.x % C.gran_per_row;
+    C.drow = NC / C.gran_per_row;
+    C.drem = NC % C.gran_per_row;
   }
   const int hfe = P.hfe;
 
   for (uint32_t i = 0; i < n_my; ++i) {
     const uint32_t s = i % S;
-    // Refill the stage that was consumed in iteration i-1 (everyone passed that iteration's barrier).
-    if (tid == 0 && i + S - 1 < n_my) issue_load(i + S - 1);
-    mbar_wait(sbase + P.bar_off + s * 8u, (i / S) & 1u);
+    mbar_wait(full_bar + s * 8u, (i / S) & 1u);
 
     const uint32_t in_s = sbase + s * P.stage_stride;
     const uint32_t out_s = sbase + P.out_buf_off + (i & 1u) * P.out_buf_stride;
     const TileMeta* m = reinterpret_cast<const TileMeta*>(smem + P.meta_off) + s;
     uint8_t* out_g = reinterpret_cast<uint8_t*>(m->out_base);
+    const uint32_t out_bytes = m->n_granules * 12u;
     if (m->any_held) {
       if (hfe == 1) tile_loop<F, FMT, 1, true, Q8, TRUNC>(in_s, out_s, out_g, m, C);
       else if (hfe == 2) tile_loop<F, FMT, 2, true, Q8, TRUNC>(in_s, out_s, out_g, m, C);
@@ -331,19 +349,20 @@ __global__ void __launch_bounds__(512) csic_rows_kernel(const __grid_constant__ 
       else tile_loop<F, FMT, 4, false, Q8, TRUNC>(in_s, out_s, out_g, m, C);
     }
 
+    // This warp is done with stage s and its meta: give it back to the producer.
+    __syncwarp();
+    if ((tid & 31u) == 0) mbar_arrive(empty_bar + s * 8u);
+
     if (kStaged) {
       // Hand the tile to the TMA engine.  Generic-proxy writes must be fenced before the async proxy
       // reads them; the staging buffer used two tiles ago must have been read out before it is reused.
-      const uint32_t bytes = m->n_granules * 12u;
       fence_proxy_async_smem();
       if (tid == 0) tma_store_wait_read0();
-      __syncthreads();
+      consumer_barrier(NC);
       if (tid == 0) {
-        tma_store_1d(out_g, out_s, bytes, pol);
+        tma_store_1d(out_g, out_s, out_bytes, pol);
         tma_store_commit();
       }
-    } else {
-      __syncthreads();    // everyone is done reading stage s (and its meta) before it is refilled
     }
   }
   if (kStaged && tid == 0) tma_store_wait_all();
@@ -355,7 +374,7 @@ constexpr int kF = CSIC_ROWS_F;
 
 template <int FMT, bool Q8, bool TR>
 int launch_one(const KPlan& k, unsigned grid, cudaStream_t st) {
-  csic_rows_kernel<kF, FMT, Q8, TR><<<grid, (unsigned)k.block_threads, k.smem_bytes, st>>>(k);
+  csic_rows_kernel<kF, FMT, Q8, TR><<<grid, (unsigned)k.block_threads + 32u, k.smem_bytes, st>>>(k);   // + producer warp
   return (int)cudaGetLastError();
 }
 template <int FMT>
