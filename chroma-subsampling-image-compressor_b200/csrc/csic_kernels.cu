@@ -223,27 +223,21 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
   auto up128 = [](uint32_t v) { return (v + 127u) & ~127u; };
   k.stage_stride = up128((uint32_t)rows * (k.tile_in_bytes + 32u));
   k.out_buf_stride = staged ? up128((uint32_t)rows * k.tile_out_bytes) : 0u;
-  // Ring depth: measured on B200 (profiles/r1/sweep2_*.txt) the kernel wants resident CTAs first (up to 4
-  // per SM) and ring depth second, so pick the depth that maximises (min(CTAs/SM, 4), depth).
+  // Ring depth and residency, fitted to B200 sweeps (profiles/r1/exp_ctas_v4.txt): the kernel is fastest with
+  // about four ~24 KB tiles in flight per SM -- 2 resident CTAs x 2 stages (cfg4 0.996 of the measured copy peak
+  // vs 0.953 with 4 CTAs; cfg2 0.97 vs 0.94 with 6 tiles in flight).  Only when a tile carries little compute
+  // per byte (f >= 4: one pixel in 16 is converted) does a third stage pay (cfg5 0.98 vs 0.92).
   auto need = [&](int s) {
-    return (uint32_t)s * k.stage_stride + 2u * k.out_buf_stride + (uint32_t)s * (uint32_t)kTileMetaBytes + (uint32_t)s * 8u + 384u;
+    return (uint32_t)s * k.stage_stride + 2u * k.out_buf_stride + (uint32_t)s * kTileMetaBytes + (uint32_t)s * 16u + 384u;
   };
   auto ctas_for = [&](int s) {
     const uint32_t by_smem = (uint32_t)(227u * 1024u / (need(s) + 1024u));
     return std::min<uint32_t>(std::min<uint32_t>(by_smem, 2048u / ((uint32_t)k.block_threads + 32u)), 8u);
   };
-  int stages = 2;
-  if (force_stages >= 2) {
-    stages = force_stages;
-  } else {
-    for (int s = 3; s <= 4; ++s)
-      if (std::min<uint32_t>(ctas_for(s), 4u) >= std::min<uint32_t>(ctas_for(stages), 4u) && ctas_for(s) >= 1) stages = s;
-    // Tiles made of many short rows cost the producer one TMA copy per row; a deeper ring hides that
-    // (cfg2, 16 rows of 1.5 KB: 0.995 of peak with 3 stages x 2 CTAs vs 0.935 with 2 stages x 3 CTAs).
-    if (stages == 2 && k.tile_rows >= 8 && k.row_step > 1 && ctas_for(3) >= 2) stages = 3;
-  }
+  int stages = force_stages >= 2 ? force_stages : (k.f >= 4 ? 3 : 2);
+  while (force_stages < 2 && stages > 2 && ctas_for(stages) < 2) --stages;
   if (need(stages) > max_smem_optin || ctas_for(stages) < 1) return false;
-  k.ctas_per_sm = (int32_t)ctas_for(stages);
+  k.ctas_per_sm = (int32_t)std::min<uint32_t>(ctas_for(stages), 2u);
   k.stages = stages;
   k.out_buf_off = (uint32_t)stages * k.stage_stride;
   k.meta_off = up128(k.out_buf_off + 2u * k.out_buf_stride);
@@ -264,7 +258,7 @@ int rows_kernel_set_attributes(size_t max_smem_optin) {
 int launch_rows(const KPlan& k, int sm_count, int force_ctas_per_sm, void* stream) {
   // Persistent grid: a whole number of CTAs per SM, as many as the shared-memory footprint allows.
   uint32_t per_sm = (uint32_t)std::max(1, k.ctas_per_sm);
-  if (force_ctas_per_sm > 0) per_sm = std::min<uint32_t>(per_sm, (uint32_t)force_ctas_per_sm);
+  if (force_ctas_per_sm > 0) per_sm = (uint32_t)force_ctas_per_sm;   // tuning knob; the hardware caps residency
   const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)k.n_tiles, (uint64_t)sm_count * per_sm);
   switch (k.f) {
     case 1: return launch_rows_factor<1>(k, grid, stream);
