@@ -376,8 +376,10 @@ def main():
         cores = os.cpu_count() or 1
         fr = cores * max(1, min(4, int(3.0e9 / (W * H * 3 * 4 * cores))))
         mps, _ = oracle_throughput(wl, fr, cores, steps=2, warmup=1)
+        mps1, _ = oracle_throughput(wl, 2, 1, steps=1, warmup=0)      # one thread, streaming form
         cpu = {"value": round(mps, 2), "unit": "MP/s", "cores": cores, "kind": "port",
-               "sample": f"{fr} frames of {W}x{H}, 2 timed passes, {cores} host threads (oracle/csic_oracle.c)"}
+               "sample": f"{fr} frames of {W}x{H}, 2 timed passes, {cores} host threads (oracle/csic_oracle.c)",
+               "value_1thread": round(mps1, 2), "sample_1thread": f"2 frames of {W}x{H}, 1 thread"}
 
     if rank == 0:
         line = {

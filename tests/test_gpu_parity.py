@@ -265,3 +265,60 @@ def test_empty_batch_and_errors(csic, ctx):
         ctx.process_band(p, 1, 1, 1, 10, 10)      # band outside the frame
     with pytest.raises(csic.IllegalArgumentException):
         csic.ImageCompressorTop(4, 4, 4, 4, 8, 8, 8, 3, 1, 2, 3)
+
+
+def test_randomised_parameter_space(csic, ctx):
+    """Property-style sweep: 400 random legal parameter sets (sizes incl. odd / prime / 1-pixel, every
+    (a,b), order, factor, format, rounding, bit depth, pooling mode), both kernels vs the oracle."""
+    rng = np.random.default_rng(20261018)
+    widths = [1, 2, 3, 5, 16, 17, 31, 32, 48, 64, 96, 100, 128, 160, 256, 272, 320]
+    seen = {1: 0, 2: 0}
+    for it in range(400):
+        f = int(rng.choice([1, 2, 4, 8]))
+        pool = int(rng.random() < 0.15)
+        W = int(rng.choice(widths)) * (f if (pool or rng.random() < 0.6) else 1)
+        H = int(rng.integers(1, 24)) * (f if (pool or rng.random() < 0.6) else 1)
+        a, b = ALL_AB[int(rng.integers(0, 6))]
+        order = ALL_ORDERS[int(rng.integers(0, 6))]
+        q = tuple(int(v) for v in rng.integers(1, 9, size=3))
+        fmt = int(rng.integers(0, 4))
+        rm = int(rng.random() < 0.3)
+        n = int(rng.integers(1, 4))
+        rgb = rng.integers(0, 256, size=(n, H, W, 3), dtype=np.uint8)
+        p, po = both_params(csic, W, H, a, b, q, f, order, rm, pool, fmt)
+        out, fam = run_both_kernels(ctx, p, rgb)
+        seen[fam] += 1
+        assert np.array_equal(out, oracle.process(po, rgb)), (it, W, H, a, b, order, q, f, fmt, rm, pool, fam)
+    assert seen[1] > 50 and seen[2] > 50, seen        # both kernel families were exercised
+
+
+def test_writes_stay_inside_the_output_buffer(csic, ctx):
+    """compute-sanitizer is closed on this GPU pool, so bound the writes ourselves: the output lives
+    between two canary regions which must survive every format / factor / kernel family, full-frame and
+    banded; the input is placed at the very end of its allocation-sized tensor."""
+    import torch
+    G = 8192
+    for (W, H), f, fmt, q, order in itertools.product([(256, 32), (64, 16), (40, 9)], (1, 2, 4, 8),
+                                                      (0, 1, 2, 3), [(8, 8, 8), (3, 3, 2)], ("CSQ", "SQC")):
+        p, po = both_params(csic, W, H, 2, 0, q, f, order, 0, 0, fmt)
+        _, oh, _, fb = csic.out_shape(p)
+        n = 3
+        rgb = torch.randint(0, 256, (n, H, W, 3), dtype=torch.uint8, device="cuda")
+        want = torch.from_numpy(oracle.process(po, rgb.cpu().numpy())).cuda()
+        for fam in (0, 1):
+            ctx.set_option(0, fam)
+            buf = torch.full((G + n * fb + G,), 0xA5, dtype=torch.uint8, device="cuda")
+            out = buf[G:G + n * fb].view(n, fb)
+            ctx.process_torch(p, rgb, out=out)
+            ctx.synchronize(); torch.cuda.synchronize()
+            assert torch.equal(out, want)
+            assert bool((buf[:G] == 0xA5).all()) and bool((buf[G + n * fb:] == 0xA5).all()), (W, H, f, fmt, fam)
+            if oh >= 3:      # a middle band must not touch rows outside itself
+                buf.fill_(0xA5)
+                ctx.process_torch(p, rgb, out=out, out_row0=1, out_rows=oh - 2)
+                ctx.synchronize(); torch.cuda.synchronize()
+                rb = fb // oh
+                o3 = out.view(n, oh, rb)
+                assert torch.equal(o3[:, 1:oh - 1], want.view(n, oh, rb)[:, 1:oh - 1])
+                assert bool((o3[:, 0] == 0xA5).all()) and bool((o3[:, oh - 1] == 0xA5).all())
+    ctx.set_option(0, 0)
