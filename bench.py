@@ -50,10 +50,10 @@ WORKLOADS = {
 ORD = {"S": 1, "Q": 2, "C": 3}
 
 
-def algorithmic_bytes_per_frame(W, H, f, out_frame_bytes, average=False):
+def algorithmic_bytes_per_frame(W, H, f, out_frame_bytes, average=False, ipb=3):
     """in_required + out_bytes; DECIMATE with f>1 needs only every f-th row."""
     rows = H if (f == 1 or average) else -(-H // f)
-    return 3 * W * rows + out_frame_bytes
+    return ipb * W * rows + out_frame_bytes
 
 
 def load_peak():
@@ -169,7 +169,7 @@ def config_dict(name, wl, frames_per_gpu, note=None):
     c = {"workload": f"{name}: {desc}", "width": W, "height": H, "frames_per_gpu": frames_per_gpu,
          "chroma": f"4:{a}:{b}", "quant_bits": list(q), "factor": f, "order": order,
          "out_format": ["YCC888", "RGB888", "BUNDLE64", "BUNDLE128"][fmt], "round_mode": "FLOOR",
-         "pool_mode": "DECIMATE", "sharding": "frames split across ranks, no collective",
+         "pool_mode": "DECIMATE", "in_format": "RGB24", "sharding": "frames split across ranks, no collective",
          "l2": "inputs (>=1 GB per step) far larger than the 126 MB L2; no flush needed"}
     if note:
         c["note"] = note
@@ -186,6 +186,8 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default: the workload's)")
     ap.add_argument("--graph", action="store_true",
                     help="capture the K timed launches into one CUDA graph and time its replay (launch-bound workloads)")
+    ap.add_argument("--in-format", type=int, default=0, choices=[0, 1, 2], help="0 RGB24, 1 RGBA32, 2 BGRA32")
+    ap.add_argument("--generic", action="store_true", help="force the generic gather kernel (family 1)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
@@ -220,9 +222,12 @@ def main():
     W, H, frames, a, b, q, f, order, fmt, desc = wl
     frames = args.frames or frames
     ops = tuple(ORD[c] for c in order)
-    p = csic.make_params(W, H, a, b, q[0], q[1], q[2], f, ops, out_format=fmt)
+    p = csic.make_params(W, H, a, b, q[0], q[1], q[2], f, ops, out_format=fmt, in_format=args.in_format)
+    ipb = 3 if args.in_format == 0 else 4
     _, out_h, _, out_fb = csic.out_shape(p)
     ctx = csic.Context(local)
+    if args.generic:
+        ctx.set_option(0, 1)
     if args.ctas_per_sm:
         ctx.set_option(2, args.ctas_per_sm)
     if args.stages:
@@ -234,7 +239,7 @@ def main():
 
     # ---- synthetic input, resident in HBM --------------------------------------------------------
     gen = torch.Generator(device="cuda").manual_seed(0x5EED + rank)
-    rgb = torch.empty((frames, H, W, 3), dtype=torch.uint8, device="cuda")
+    rgb = torch.empty((frames, H, W, ipb), dtype=torch.uint8, device="cuda")
     for i in range(0, frames, 64):      # chunked: randint materialises int64 temporaries for some dtypes
         rgb[i:i + 64] = torch.randint(0, 256, rgb[i:i + 64].shape, dtype=torch.uint8, device="cuda", generator=gen)
     out = torch.empty((frames, out_fb), dtype=torch.uint8, device="cuda")
@@ -246,7 +251,8 @@ def main():
         nchk = min(2, frames)
         ctx.process_torch(p, rgb[:nchk], out=out[:nchk])
         torch.cuda.synchronize()
-        want = oracle.process(oracle.make_params(W, H, a, b, q, f, order, out_format=fmt), rgb[nchk - 1].cpu().numpy())
+        want = oracle.process(oracle.make_params(W, H, a, b, q, f, order, out_format=fmt, in_format=args.in_format),
+                              rgb[nchk - 1].cpu().numpy())
         parity = bool(np.array_equal(out[nchk - 1].cpu().numpy(), want[0]))
 
     # row-band sharding: rank r processes output rows [r0, r0+rows) of every frame, zero halo (aligned bands)
@@ -313,7 +319,7 @@ def main():
     mp_per_step_all = frames * W * H * (world if band is None else 1) / 1e6
     value = mp_per_step_all * args.steps / (total_ms_max / 1e3)
 
-    alg_bytes = algorithmic_bytes_per_frame(W, H, f, out_fb) * frames          # per launch (one rank)
+    alg_bytes = algorithmic_bytes_per_frame(W, H, f, out_fb, ipb=ipb) * frames          # per launch (one rank)
     if band is not None:
         alg_bytes = alg_bytes * band[1] // out_h
     kernel_ms = statistics.mean(step_ms)                                      # one launch per step
@@ -332,14 +338,14 @@ def main():
     # ---- end to end through the C ABI with host buffers --------------------------------------------
     e2e = None
     if not args.no_e2e and band is None:
-        hb = min(frames, max(1, int(3.2e9 // (W * H * 3))))         # frames per pinned host batch (~3.2 GB)
+        hb = min(frames, max(1, int(3.2e9 // (W * H * ipb))))         # frames per pinned host batch (~3.2 GB)
         calls = -(-frames // hb)
-        pin_in = csic.PinnedBuffer(hb * H * W * 3)
+        pin_in = csic.PinnedBuffer(hb * H * W * ipb)
         pin_out = csic.PinnedBuffer(hb * out_fb)
         hin = torch.from_numpy(pin_in.array)
         hin.copy_(rgb[:hb].reshape(-1))                               # real pixel data in the pinned buffer
         torch.cuda.synchronize()
-        hin_np = pin_in.array.reshape(hb, H, W, 3)
+        hin_np = pin_in.array.reshape(hb, H, W, ipb)
         hout_np = pin_out.array.reshape(hb, out_fb)
         e2e_steps = max(1, min(args.steps, 3))
 
@@ -387,8 +393,9 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms_max / args.steps, 4),
             "higher_is_better": True, "scaling": "weak" if band is None else "strong", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic (uniform random bytes, torch.randint, seed 0x5EED+rank, generated in HBM)",
-            "config": config_dict(args.workload, wl, frames, note=None if band is None else
+            "config": dict(config_dict(args.workload, wl, frames, note=None if band is None else
                                   f"row-band sharding: {world} aligned bands per frame, zero halo, rank 0 band = rows {band}"),
+                           in_format=["RGB24", "RGBA32", "BGRA32"][args.in_format]),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(kernel_ms, 4),

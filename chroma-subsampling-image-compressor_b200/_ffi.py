@@ -19,7 +19,7 @@ class CsicParams(ctypes.Structure):
                 ("y_bits", ctypes.c_int32), ("cb_bits", ctypes.c_int32), ("cr_bits", ctypes.c_int32),
                 ("factor", ctypes.c_int32), ("op", ctypes.c_int32 * 3),
                 ("round_mode", ctypes.c_int32), ("pool_mode", ctypes.c_int32), ("out_format", ctypes.c_int32),
-                ("reserved", ctypes.c_int32 * 2)]
+                ("in_format", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 # every symbol include/csic.h declares (tests/test_abi.py checks header <-> library <-> this table)

@@ -44,6 +44,13 @@ class PoolMode(enum.IntEnum):
     AVERAGE = 1
 
 
+class InFormat(enum.IntEnum):
+    """Input pixel layout; BGRA32 == a little-endian Java/AWT/scrimage ARGB int (alpha ignored)."""
+    RGB24 = 0
+    RGBA32 = 1
+    BGRA32 = 2
+
+
 class OutFormat(enum.IntEnum):
     YCC888 = 0
     RGB888 = 1
@@ -98,12 +105,14 @@ def parse_processing_step(name):
 
 def make_params(width, height, a=4, b=4, y_bits=8, cb_bits=8, cr_bits=8, factor=1,
                 ops=(ProcessingStep.ChromaSubsampling, ProcessingStep.SpatialSampling, ProcessingStep.ColorQuantization),
-                round_mode=RoundMode.FLOOR, pool_mode=PoolMode.DECIMATE, out_format=OutFormat.YCC888):
+                round_mode=RoundMode.FLOOR, pool_mode=PoolMode.DECIMATE, out_format=OutFormat.YCC888,
+                in_format=InFormat.RGB24):
     p = CsicParams()
     p.width, p.height, p.chroma_a, p.chroma_b = int(width), int(height), int(a), int(b)
     p.y_bits, p.cb_bits, p.cr_bits, p.factor = int(y_bits), int(cb_bits), int(cr_bits), int(factor)
     p.op[0], p.op[1], p.op[2] = (int(o) for o in ops)
     p.round_mode, p.pool_mode, p.out_format = int(round_mode), int(pool_mode), int(out_format)
+    p.in_format = int(in_format)
     return validate(p)
 
 
@@ -207,8 +216,9 @@ class Context:
         rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
         if rgb.ndim == 3:
             rgb = rgb[None]
-        if rgb.shape[1:] != (p.height, p.width, 3):
-            raise IllegalArgumentException(-9, f"rgb must be [n,{p.height},{p.width},3], got {rgb.shape}")
+        ch = 3 if p.in_format == InFormat.RGB24 else 4
+        if rgb.shape[1:] != (p.height, p.width, ch):
+            raise IllegalArgumentException(-9, f"rgb must be [n,{p.height},{p.width},{ch}], got {rgb.shape}")
         n = rgb.shape[0]
         fb = out_shape(p)[3]
         if out is None:
@@ -221,7 +231,7 @@ class Context:
     def process_torch(self, p, rgb, out=None, out_row0=None, out_rows=None):
         import torch
         assert rgb.is_cuda and rgb.dtype == torch.uint8 and rgb.is_contiguous()
-        n = rgb.numel() // (p.height * p.width * 3)
+        n = rgb.numel() // (p.height * p.width * (3 if p.in_format == InFormat.RGB24 else 4))
         fb = out_shape(p)[3]
         if out is None:
             out = torch.empty((n, fb), dtype=torch.uint8, device=rgb.device)

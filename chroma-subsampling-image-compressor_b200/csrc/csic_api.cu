@@ -88,6 +88,12 @@ int build_plan(const csic_params& p, const void* d_rgb, void* d_out, size_t n_fr
     return CSIC_EINVAL_DIMS;   // the reference's counters are far narrower; 2^31 pixels per frame is our limit
   k.in_row_bytes = (uint32_t)g.in_row_bytes;
   k.out_row_bytes = (uint32_t)g.out_row_bytes;
+  k.in_px_bytes = g.in_px_bytes;
+  auto swap_rb = [](uint32_t c) { return (c & 0xFF00FF00u) | ((c & 0xFFu) << 16) | ((c >> 16) & 0xFFu); };
+  const bool bgr = p.in_format == CSIC_IN_BGRA32;
+  k.coef_y = bgr ? swap_rb(0x001D964Du) : 0x001D964Du;      //  77, 150,  29, 0
+  k.coef_ncb = bgr ? swap_rb(0x0080552Bu) : 0x0080552Bu;    //  43,  85,-128, 0  (negated Cb row)
+  k.coef_ncr = bgr ? swap_rb(0x00156B80u) : 0x00156B80u;    //-128, 107,  21, 0  (negated Cr row)
   k.W = p.width;
   k.H = p.height;
   k.Wo = g.out_w;

@@ -31,12 +31,14 @@ __device__ __forceinline__ int32_t dp4a_us(uint32_t a, uint32_t b_s8x4, int32_t 
   return d;
 }
 
+// Coefficient words for pixels stored R,G,B,(x).  For B,G,R,(x) input the host swaps bytes 0 and 2
+// (KPlan::coef_*), so the kernels never permute pixel bytes.
 constexpr uint32_t kCoefY = 0x001D964Du;     //  77, 150,  29, 0   (u8)
 constexpr uint32_t kCoefNCb = 0x0080552Bu;   //  43,  85,-128, 0   (s8)  == -cb row
 constexpr uint32_t kCoefNCr = 0x00156B80u;   //-128, 107,  21, 0   (s8)  == -cr row
 
 // byte 1 of the result is Y
-__device__ __forceinline__ uint32_t fwd_y16(uint32_t p) { return dp4a_uu(p, kCoefY, 128u); }
+__device__ __forceinline__ uint32_t fwd_y16(uint32_t p, uint32_t coef_y) { return dp4a_uu(p, coef_y, 128u); }
 // byte 1 of the result is ~Cb / ~Cr; result < 65536
 template <bool TRUNC>
 __device__ __forceinline__ uint32_t fwd_nc16(uint32_t p, uint32_t coef) {

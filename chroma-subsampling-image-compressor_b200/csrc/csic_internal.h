@@ -14,6 +14,7 @@ struct Geometry {
   size_t in_row_bytes, in_frame_bytes;
   size_t out_row_bytes, out_frame_bytes;
   int32_t out_px_bytes;      // 3 for YCC888/RGB888, slot bytes (1/2/4) for bundles
+  int32_t in_px_bytes;       // 3 (RGB24) or 4 (RGBA32 / BGRA32, fourth byte ignored)
   bool chroma_first;         // ChromaSubsampling precedes SpatialSampling in op1..op3
   bool quant_first;          // ColorQuantization precedes SpatialSampling (only matters for AVERAGE)
   int32_t hf, vf;            // ChromaSubsampler.scala:26-27
@@ -32,6 +33,8 @@ struct KPlan {
   uint64_t in_frame_bytes, out_frame_bytes;
   uint32_t in_row_bytes, out_row_bytes;
   int32_t W, H, Wo, Ho;
+  int32_t in_px_bytes;                   // 3 or 4
+  uint32_t coef_y, coef_ncb, coef_ncr;   // dp4a coefficient words in the byte order of the input pixels
   int32_t f;
   int32_t hf, vf, last_sample_col;       // ((W-1)/hf)*hf : last chroma sample column of a line
   int32_t case_b;                        // spatial before chroma with f > 1 (misaligned counters)

@@ -28,9 +28,9 @@ namespace csic {
 // ================================================================================================
 // Generic gather kernel
 // ================================================================================================
-__device__ __forceinline__ uint32_t load_px(const uint8_t* __restrict__ frame, uint32_t row_bytes, int r, int c) {
-  // r is a row of the frame as stored (see KPlan::compact)
-  const uint8_t* q = frame + (size_t)r * row_bytes + (size_t)c * 3;
+__device__ __forceinline__ uint32_t load_px(const uint8_t* __restrict__ frame, uint32_t row_bytes, int r, int c, int ipb) {
+  // r is a row of the frame as stored (see KPlan::compact); ipb = bytes per input pixel (3 or 4)
+  const uint8_t* q = frame + (size_t)r * row_bytes + (size_t)c * (size_t)ipb;
   return (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16);
 }
 
@@ -58,12 +58,6 @@ __device__ __forceinline__ void chroma_src_case_b(const KPlan& P, int ro, int co
   sco = (int)(src % (uint32_t)P.Wo);
 }
 
-template <bool TRUNC>
-__device__ __forceinline__ void ycc_of(uint32_t p, int& y, int& cb, int& cr) {
-  y = (int)(fwd_y16(p) >> 8);
-  cb = 255 - (int)(fwd_nc16<TRUNC>(p, kCoefNCb) >> 8);
-  cr = 255 - (int)(fwd_nc16<TRUNC>(p, kCoefNCr) >> 8);
-}
 
 template <bool TRUNC>
 __global__ void __launch_bounds__(256) csic_generic_kernel(const __grid_constant__ KPlan P) {
@@ -96,14 +90,14 @@ __global__ void __launch_bounds__(256) csic_generic_kernel(const __grid_constant
         sc = sco * f;
       }
       if (P.compact) {   // only every f-th row is stored; DECIMATE with f > 1 never reads another one
-        y = (int)(fwd_y16(load_px(frame, P.in_row_bytes, yr / f, yc)) >> 8);
+        y = (int)(fwd_y16(load_px(frame, P.in_row_bytes, yr / f, yc, P.in_px_bytes), P.coef_y) >> 8);
         sr /= f;
       } else {
-        y = (int)(fwd_y16(load_px(frame, P.in_row_bytes, yr, yc)) >> 8);
+        y = (int)(fwd_y16(load_px(frame, P.in_row_bytes, yr, yc, P.in_px_bytes), P.coef_y) >> 8);
       }
-      const uint32_t pc = load_px(frame, P.in_row_bytes, sr, sc);
-      cb = 255 - (int)(fwd_nc16<TRUNC>(pc, kCoefNCb) >> 8);
-      cr = 255 - (int)(fwd_nc16<TRUNC>(pc, kCoefNCr) >> 8);
+      const uint32_t pc = load_px(frame, P.in_row_bytes, sr, sc, P.in_px_bytes);
+      cb = 255 - (int)(fwd_nc16<TRUNC>(pc, P.coef_ncb) >> 8);
+      cr = 255 - (int)(fwd_nc16<TRUNC>(pc, P.coef_ncr) >> 8);
       y = (y >> P.sy) << P.sy;
       cb = (cb >> P.scb) << P.scb;
       cr = (cr >> P.scr) << P.scr;
@@ -116,7 +110,7 @@ __global__ void __launch_bounds__(256) csic_generic_kernel(const __grid_constant
       for (int dr = 0; dr < f; ++dr)
         for (int dc = 0; dc < f; ++dc) {
           const int r = ro * f + dr, c = co * f + dc;
-          int yy = (int)(fwd_y16(load_px(frame, P.in_row_bytes, r, c)) >> 8);
+          int yy = (int)(fwd_y16(load_px(frame, P.in_row_bytes, r, c, P.in_px_bytes), P.coef_y) >> 8);
           sy_ += (yy >> qy) << qy;
           int sr, sc;
           if (!P.case_b) {
@@ -125,9 +119,9 @@ __global__ void __launch_bounds__(256) csic_generic_kernel(const __grid_constant
             sr = bro * f + dr;                  // pooling first: own chroma of the source block
             sc = bco * f + dc;
           }
-          const uint32_t pc = load_px(frame, P.in_row_bytes, sr, sc);
-          const int b0 = 255 - (int)(fwd_nc16<TRUNC>(pc, kCoefNCb) >> 8);
-          const int r0 = 255 - (int)(fwd_nc16<TRUNC>(pc, kCoefNCr) >> 8);
+          const uint32_t pc = load_px(frame, P.in_row_bytes, sr, sc, P.in_px_bytes);
+          const int b0 = 255 - (int)(fwd_nc16<TRUNC>(pc, P.coef_ncb) >> 8);
+          const int r0 = 255 - (int)(fwd_nc16<TRUNC>(pc, P.coef_ncr) >> 8);
           scb_ += (b0 >> qcb) << qcb;
           scr_ += (r0 >> qcr) << qcr;
         }
@@ -184,7 +178,7 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
   if (k.block_threads > kMaxConsumerThreads) return false;
   if (k.case_b) {
     k.caseb_row_add = (uint32_t)k.last_sample_col / (uint32_t)k.Wo;
-    k.caseb_col_bytes = ((uint32_t)k.last_sample_col % (uint32_t)k.Wo) * 3u * (uint32_t)k.f;
+    k.caseb_col_bytes = ((uint32_t)k.last_sample_col % (uint32_t)k.Wo) * (uint32_t)k.in_px_bytes * (uint32_t)k.f;
   }
 
   // hold width inside a granule, in output pixels
@@ -195,21 +189,27 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
   const uint32_t opx = staged ? 3u : (uint32_t)k.slot_bytes;
   // Tile budget: input bytes of one tile.  Staged formats also hold two output buffers per CTA.
   const uint32_t tile_budget = force_tile_bytes ? force_tile_bytes : 24u * 1024u;
-  const uint32_t row_in = (uint32_t)k.Wo * 3u * (uint32_t)k.f;  // == in_row_bytes
+  const uint32_t ipb = (uint32_t)k.in_px_bytes;
+  const uint32_t row_in = (uint32_t)k.Wo * ipb * (uint32_t)k.f;  // == in_row_bytes
   int nsplit = 0;
-  for (int n = (int)((row_in + tile_budget - 1) / tile_budget); n <= 64; ++n) {
+  const uint32_t tile_max = tile_budget + tile_budget / 3;        // a tile may overshoot the budget by a third
+  for (int n = (int)((row_in + tile_max - 1) / tile_max); n <= 64; ++n) {
     if (k.Wo % (16 * n) == 0) { nsplit = n; break; }
   }
   if (nsplit == 0) return false;
   k.nsplit = nsplit;
   k.tile_px = k.Wo / nsplit;
-  k.tile_in_bytes = (uint32_t)k.tile_px * 3u * (uint32_t)k.f;    // one row segment
+  k.tile_in_bytes = (uint32_t)k.tile_px * ipb * (uint32_t)k.f;    // one row segment
   k.tile_out_bytes = (uint32_t)k.tile_px * opx;
   // Rows per tile: whole rows only (so the tile's output is contiguous), as many as fit the budget,
   // but keep at least ~4 tiles per SM so small batches still spread over the chip.
   int rows = 1;
   if (nsplit == 1) {
     rows = (int)std::min<uint32_t>((uint32_t)kMaxTileRows, std::max<uint32_t>(1u, tile_budget / k.tile_in_bytes));
+    // e.g. 15 KB RGBA 4K rows: one row leaves the ring too shallow, two rows (30 KB) are within the slack
+    if ((uint32_t)rows * k.tile_in_bytes < tile_budget * 7u / 10u && (uint32_t)(rows + 1) * k.tile_in_bytes <= tile_max &&
+        rows < kMaxTileRows)
+      ++rows;
     rows = std::min(rows, k.band_rows);
     auto tiles_for = [&](int r) { return (uint64_t)k.n_frames * (uint64_t)((k.band_rows + r - 1) / r); };
     while (rows > 1 && tiles_for(rows) < (uint64_t)sm_count * 4u) rows = (rows + 1) / 2;

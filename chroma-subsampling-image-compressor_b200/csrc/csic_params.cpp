@@ -124,8 +124,9 @@ int csic_validate(const csic_params* p, char* msg, size_t n) {
     return fail(CSIC_EINVAL_MODE, msg, n, "pool_mode must be 0 (DECIMATE) or 1 (AVERAGE)");
   if (p->out_format < CSIC_OUT_YCC888 || p->out_format > CSIC_OUT_BUNDLE128)
     return fail(CSIC_EINVAL_MODE, msg, n, "out_format must be 0..3");
-  if (p->reserved[0] != 0 || p->reserved[1] != 0)
-    return fail(CSIC_EINVAL_MODE, msg, n, "reserved fields must be 0");
+  if (p->in_format < CSIC_IN_RGB24 || p->in_format > CSIC_IN_BGRA32)
+    return fail(CSIC_EINVAL_MODE, msg, n, "in_format must be 0 (RGB24), 1 (RGBA32) or 2 (BGRA32)");
+  if (p->reserved != 0) return fail(CSIC_EINVAL_MODE, msg, n, "reserved field must be 0");
   // The AVERAGE extension is defined on whole f x f blocks only (same predicate as ImageProcessor.scala:25).
   if (p->pool_mode == CSIC_POOL_AVERAGE && (p->width % p->factor != 0 || p->height % p->factor != 0))
     return fail(CSIC_EINVAL_DIVISIBLE, msg, n,
@@ -190,7 +191,8 @@ Geometry geometry(const csic_params& p) {
   const int f = p.factor;
   g.out_w = (p.width + f - 1) / f;   // what the DUT emits: SpatialDownsamplerSpec.scala:120-123
   g.out_h = (p.height + f - 1) / f;
-  g.in_row_bytes = (size_t)p.width * 3;
+  g.in_px_bytes = p.in_format == CSIC_IN_RGB24 ? 3 : 4;
+  g.in_row_bytes = (size_t)p.width * (size_t)g.in_px_bytes;
   g.in_frame_bytes = g.in_row_bytes * (size_t)p.height;
   if (p.out_format == CSIC_OUT_BUNDLE64 || p.out_format == CSIC_OUT_BUNDLE128) {
     const size_t word = p.out_format == CSIC_OUT_BUNDLE64 ? 8 : 16;

@@ -89,8 +89,29 @@ __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
 // The four sampled pixels of a granule, each as a word whose low three bytes are R,G,B.
 // A granule is 4 consecutive output pixels = 4 input pixels at a stride of F pixels (3F bytes);
 // `a` is the shared-memory address of its first byte.
-template <int F>
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+
+// IN4: 4-byte input pixels (RGBA32 / BGRA32); every pixel is an aligned word, the fourth byte meets a zero
+// coefficient.  Granule = 16F bytes.
+template <int F, bool IN4>
 __device__ __forceinline__ void load_granule(uint32_t a, uint32_t (&p)[4]) {
+  if (IN4) {
+    if (F == 1) {
+      const uint4 v = lds128(a);
+      p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w;
+    } else if (F == 2) {
+      const uint4 v = lds128(a), w = lds128(a + 16);
+      p[0] = v.x; p[1] = v.z; p[2] = w.x; p[3] = w.z;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) p[j] = lds32(a + j * 4u * F);
+    }
+    return;
+  }
   if (F == 1) {                                  // 12 bytes; word stride 3 across lanes: conflict free
     const uint32_t w0 = lds32(a), w1 = lds32(a + 4), w2 = lds32(a + 8);
     p[0] = w0;
@@ -124,6 +145,7 @@ struct LoopConst {
   uint32_t qm0, qm1, qm2;            // YCC888: quantiser keep-masks over the three packed words
   uint32_t my, mcb, mcr;             // RGB888
   int shy, shb, shr, ly, lb;         // bundles
+  uint32_t coef_y, coef_ncb, coef_ncr;       // dp4a coefficient words (byte order of the input pixels)
   uint32_t gran_per_row;
   uint32_t nthreads;                         // consumer threads per CTA
   uint32_t row0_of_thread, rem0_of_thread;   // threadIdx.x / gran_per_row, threadIdx.x % gran_per_row
@@ -136,17 +158,17 @@ struct LoopConst {
 //   HFE   chroma hold width inside a granule, in output pixels (1, 2 or 4)
 //   HELD  the tile may contain rows that replay a held pair (odd 4:2:0 / 4:1:0 lines)
 //   Q8    8/8/8 bits in a 32-bit slot: pure byte permutes
-template <int F, int FMT, int HFE, bool HELD, bool Q8, bool TRUNC>
+template <int F, int FMT, int HFE, bool HELD, bool Q8, bool TRUNC, bool IN4>
 __device__ __forceinline__ void tile_loop(uint32_t in_s, uint32_t out_s, uint8_t* __restrict__ out_g,
                                           const TileMeta* __restrict__ meta, const LoopConst& C) {
   const uint32_t n = meta->n_granules;
   uint32_t row = C.row0_of_thread, rem = C.rem0_of_thread;   // row of granule q, tracked without a division
   for (uint32_t q = threadIdx.x; q < n; q += C.nthreads) {
     uint32_t p[4];
-    load_granule<F>(in_s + q * (12u * F), p);
+    load_granule<F, IN4>(in_s + q * ((IN4 ? 16u : 12u) * F), p);
     uint32_t dy[4], xb[4], xr[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) dy[j] = fwd_y16(p[j]);
+    for (int j = 0; j < 4; ++j) dy[j] = fwd_y16(p[j], C.coef_y);
     uint32_t haddr = 0;
     if (HELD) {
       haddr = meta->held_addr[row];
@@ -156,7 +178,7 @@ __device__ __forceinline__ void tile_loop(uint32_t in_s, uint32_t out_s, uint8_t
     }
     if (HELD && haddr != 0) {
       const uint32_t hp = lds8(haddr) | (lds8(haddr + 1) << 8) | (lds8(haddr + 2) << 16);
-      const uint32_t hb = fwd_nc16<TRUNC>(hp, kCoefNCb), hr = fwd_nc16<TRUNC>(hp, kCoefNCr);
+      const uint32_t hb = fwd_nc16<TRUNC>(hp, C.coef_ncb), hr = fwd_nc16<TRUNC>(hp, C.coef_ncr);
 #pragma unroll
       for (int j = 0; j < 4; ++j) { xb[j] = hb; xr[j] = hr; }
     } else {
@@ -164,8 +186,8 @@ __device__ __forceinline__ void tile_loop(uint32_t in_s, uint32_t out_s, uint8_t
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (j % HFE == 0) {
-          xb[j] = fwd_nc16<TRUNC>(p[j], kCoefNCb);
-          xr[j] = fwd_nc16<TRUNC>(p[j], kCoefNCr);
+          xb[j] = fwd_nc16<TRUNC>(p[j], C.coef_ncb);
+          xr[j] = fwd_nc16<TRUNC>(p[j], C.coef_ncr);
         } else {
           xb[j] = xb[j - 1];
           xr[j] = xr[j - 1];
@@ -216,6 +238,21 @@ __device__ __forceinline__ void tile_loop(uint32_t in_s, uint32_t out_s, uint8_t
   }
 }
 
+// Per-tile specialisation: hold width, held rows, input pixel size.
+template <int F, int FMT, bool Q8, bool TRUNC, bool IN4>
+__device__ __forceinline__ void tile_dispatch(bool held, int hfe, uint32_t in_s, uint32_t out_s, uint8_t* out_g,
+                                              const TileMeta* m, const LoopConst& C) {
+  if (held) {
+    if (hfe == 1) tile_loop<F, FMT, 1, true, Q8, TRUNC, IN4>(in_s, out_s, out_g, m, C);
+    else if (hfe == 2) tile_loop<F, FMT, 2, true, Q8, TRUNC, IN4>(in_s, out_s, out_g, m, C);
+    else tile_loop<F, FMT, 4, true, Q8, TRUNC, IN4>(in_s, out_s, out_g, m, C);
+  } else {
+    if (hfe == 1) tile_loop<F, FMT, 1, false, Q8, TRUNC, IN4>(in_s, out_s, out_g, m, C);
+    else if (hfe == 2) tile_loop<F, FMT, 2, false, Q8, TRUNC, IN4>(in_s, out_s, out_g, m, C);
+    else tile_loop<F, FMT, 4, false, Q8, TRUNC, IN4>(in_s, out_s, out_g, m, C);
+  }
+}
+
 template <int F, int FMT, bool Q8, bool TRUNC>
 __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(const __grid_constant__ KPlan P) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -259,6 +296,7 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(con
       TileMeta* m = reinterpret_cast<TileMeta*>(smem + P.meta_off) + s;
 
       // Which rows replay a held chroma pair, and from where?  (KPlan::hfe covers the in-row hold.)
+      const uint32_t ipb = (uint32_t)P.in_px_bytes;
       uint32_t n_aux = 0, any = 0;
       const uint8_t* aux_src[kMaxTileRows];
       if (P.vf == 2) {
@@ -268,8 +306,8 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(con
           const uint8_t* hp = nullptr;
           if (!P.case_b) {
             if (F == 1 && (ro & 1)) {          // odd line at full resolution: last sample point of the line above
-              if (j > 0 && P.nsplit == 1) h = dst + (j - 1) * P.tile_in_bytes + (uint32_t)P.last_sample_col * 3u;   // in this tile
-              else hp = frame + (uint64_t)(ro - 1) * P.in_row_bytes + (uint32_t)P.last_sample_col * 3u;
+              if (j > 0 && P.nsplit == 1) h = dst + (j - 1) * P.tile_in_bytes + (uint32_t)P.last_sample_col * ipb;   // in this tile
+              else hp = frame + (uint64_t)(ro - 1) * P.in_row_bytes + (uint32_t)P.last_sample_col * ipb;
             }
           } else {
             const uint32_t line = ro / F;      // W == F * Wo: one counter line spans F output rows
@@ -321,6 +359,7 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(con
     C.my = my; C.mcb = mcb; C.mcr = mcr;
     C.shy = 8 + P.sy; C.shb = 8 + P.scb; C.shr = 8 + P.scr;
     C.ly = P.cb_bits + P.cr_bits; C.lb = P.cr_bits;
+    C.coef_y = P.coef_y; C.coef_ncb = P.coef_ncb; C.coef_ncr = P.coef_ncr;
     C.gran_per_row = (uint32_t)P.tile_px >> 2;
     C.nthreads = NC;
     C.row0_of_thread = tid / C.gran_per_row;
@@ -329,6 +368,7 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(con
     C.drem = NC % C.gran_per_row;
   }
   const int hfe = P.hfe;
+  const bool in4 = P.in_px_bytes == 4;
 
   for (uint32_t i = 0; i < n_my; ++i) {
     const uint32_t s = i % S;
@@ -339,15 +379,8 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(con
     const TileMeta* m = reinterpret_cast<const TileMeta*>(smem + P.meta_off) + s;
     uint8_t* out_g = reinterpret_cast<uint8_t*>(m->out_base);
     const uint32_t out_bytes = m->n_granules * 12u;
-    if (m->any_held) {
-      if (hfe == 1) tile_loop<F, FMT, 1, true, Q8, TRUNC>(in_s, out_s, out_g, m, C);
-      else if (hfe == 2) tile_loop<F, FMT, 2, true, Q8, TRUNC>(in_s, out_s, out_g, m, C);
-      else tile_loop<F, FMT, 4, true, Q8, TRUNC>(in_s, out_s, out_g, m, C);
-    } else {
-      if (hfe == 1) tile_loop<F, FMT, 1, false, Q8, TRUNC>(in_s, out_s, out_g, m, C);
-      else if (hfe == 2) tile_loop<F, FMT, 2, false, Q8, TRUNC>(in_s, out_s, out_g, m, C);
-      else tile_loop<F, FMT, 4, false, Q8, TRUNC>(in_s, out_s, out_g, m, C);
-    }
+    if (in4) tile_dispatch<F, FMT, Q8, TRUNC, true>(m->any_held != 0, hfe, in_s, out_s, out_g, m, C);
+    else tile_dispatch<F, FMT, Q8, TRUNC, false>(m->any_held != 0, hfe, in_s, out_s, out_g, m, C);
 
     if (kStaged) {
       // Hand the tile to the TMA engine.  Generic-proxy writes must be fenced before the async proxy

@@ -19,7 +19,7 @@ import os
 import numpy as np
 
 from . import api
-from .api import (IllegalArgumentException, OutFormat, PoolMode, ProcessingStep, RoundMode)
+from .api import (IllegalArgumentException, InFormat, OutFormat, PoolMode, ProcessingStep, RoundMode)
 
 _default_ctx = {}
 
@@ -39,10 +39,12 @@ class ImageCompressorTop:
 
     def __init__(self, width, height, chroma_param_a_config, chroma_param_b_config, yTargetQuantBitsConfig,
                  cbTargetQuantBitsConfig, crTargetQuantBitsConfig, downFactorConfig, op1Type, op2Type, op3Type,
-                 round_mode=RoundMode.FLOOR, pool_mode=PoolMode.DECIMATE, out_format=OutFormat.YCC888, ctx=None):
+                 round_mode=RoundMode.FLOOR, pool_mode=PoolMode.DECIMATE, out_format=OutFormat.YCC888,
+                 in_format=InFormat.RGB24, ctx=None):
         self.params = api.make_params(width, height, chroma_param_a_config, chroma_param_b_config,
                                       yTargetQuantBitsConfig, cbTargetQuantBitsConfig, crTargetQuantBitsConfig,
-                                      downFactorConfig, (op1Type, op2Type, op3Type), round_mode, pool_mode, out_format)
+                                      downFactorConfig, (op1Type, op2Type, op3Type), round_mode, pool_mode, out_format,
+                                      in_format)
         self._ctx = ctx
 
     @classmethod
@@ -63,7 +65,8 @@ class ImageCompressorTop:
         return h, w
 
     def process(self, rgb):
-        """rgb: uint8 [H,W,3] or [n,H,W,3] -> uint8 [n, out_h, out_w, 3] (YCC888/RGB888) or [n, bytes] (bundles)."""
+        """rgb: uint8 [H,W,3] or [n,H,W,3] (4 channels for in_format RGBA32/BGRA32) -> uint8 [n, out_h, out_w, 3]
+        (YCC888/RGB888) or [n, bytes] (bundles)."""
         out = self.ctx.process_host(self.params, rgb)
         if self.params.out_format in (OutFormat.YCC888, OutFormat.RGB888):
             h, w = self.out_shape

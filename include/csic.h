@@ -63,6 +63,12 @@ enum csic_pool_mode { CSIC_POOL_DECIMATE = 0, CSIC_POOL_AVERAGE = 1 };
  *            each output row is padded with zero slots to a whole word. */
 enum csic_out_format { CSIC_OUT_YCC888 = 0, CSIC_OUT_RGB888 = 1, CSIC_OUT_BUNDLE64 = 2, CSIC_OUT_BUNDLE128 = 3 };
 
+/* Input pixel layout.  RGB24 = 3 bytes R,G,B (pixel.red/green/blue, ImageCompressorTopApp.scala:86-89).
+ * RGBA32 / BGRA32 = 4 bytes per pixel with the fourth ignored, exactly as the reference ignores alpha;
+ * BGRA32 is the in-memory layout of a little-endian Java / AWT / scrimage ARGB int (0xAARRGGBB), so a JVM host
+ * can pass its pixel array without repacking. */
+enum csic_in_format { CSIC_IN_RGB24 = 0, CSIC_IN_RGBA32 = 1, CSIC_IN_BGRA32 = 2 };
+
 /* Legacy enums (removed from the reference's HEAD, recovered from its committed outputs). */
 enum csic_chroma_mode { CSIC_CHROMA_444 = 0, CSIC_CHROMA_422 = 1, CSIC_CHROMA_420 = 2 };
 enum csic_quant_mode { CSIC_Q_24BIT = 0, CSIC_Q_16BIT = 1, CSIC_Q_8BIT = 2 };
@@ -96,7 +102,8 @@ typedef struct csic_params {
   int32_t round_mode;               /* csic_round_mode */
   int32_t pool_mode;                /* csic_pool_mode */
   int32_t out_format;               /* csic_out_format */
-  int32_t reserved[2];              /* must be 0 */
+  int32_t in_format;                /* csic_in_format (0 = RGB24, the reference's pixel stream) */
+  int32_t reserved;                 /* must be 0 */
 } csic_params;
 
 typedef struct csic_ctx csic_ctx;   /* one per (host thread, GPU); not thread-safe */
@@ -148,7 +155,7 @@ CSIC_API int csic_destroy(csic_ctx* ctx);
 
 /* The hot path.  Replaces the body `chiseltest.RawTester.test(new ImageCompressorTop(...)){...}` of
  * ImageCompressionApp.processImage (ImageCompressorTopApp.scala:53-131) for n_frames independent frames
- * (the reference builds a fresh DUT per image, :53).  d_rgb: n_frames x H x W x 3 bytes, packed RGB24,
+ * (the reference builds a fresh DUT per image, :53).  d_rgb: n_frames x H x W x (3|4) bytes per in_format,
  * raster order (pixel.red/green/blue, :86-89).  d_out: n_frames x bytes_per_frame.  Both device
  * pointers on ctx's GPU.  Asynchronous on `cuda_stream` (a cudaStream_t; NULL = the context's own
  * non-blocking stream -- pass cudaStreamLegacy (0x1) / cudaStreamPerThread (0x2) to name a default

@@ -25,7 +25,7 @@ class Params(ctypes.Structure):
                 ("y_bits", ctypes.c_int32), ("cb_bits", ctypes.c_int32), ("cr_bits", ctypes.c_int32),
                 ("factor", ctypes.c_int32), ("op", ctypes.c_int32 * 3),
                 ("round_mode", ctypes.c_int32), ("pool_mode", ctypes.c_int32), ("out_format", ctypes.c_int32),
-                ("reserved", ctypes.c_int32 * 2)]
+                ("in_format", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 def build(force=False):
@@ -65,7 +65,7 @@ ORDERS = {"SQC": (1, 2, 3), "SCQ": (1, 3, 2), "QSC": (2, 1, 3), "QCS": (2, 3, 1)
 
 
 def make_params(width, height, a=4, b=4, q=(8, 8, 8), factor=1, order="CSQ", round_mode=0, pool_mode=0,
-                out_format=0):
+                out_format=0, in_format=0):
     p = Params()
     p.width, p.height, p.chroma_a, p.chroma_b = width, height, a, b
     p.y_bits, p.cb_bits, p.cr_bits = q
@@ -73,17 +73,18 @@ def make_params(width, height, a=4, b=4, q=(8, 8, 8), factor=1, order="CSQ", rou
     ops = ORDERS[order] if isinstance(order, str) else tuple(order)
     p.op[0], p.op[1], p.op[2] = ops
     p.round_mode, p.pool_mode, p.out_format = round_mode, pool_mode, out_format
+    p.in_format = in_format
     return p
 
 
 def process(p, rgb, threads=1):
-    """rgb: uint8 array [n, H, W, 3] (or [H, W, 3]).  Returns uint8 [n, bytes_per_frame]."""
+    """rgb: uint8 array [n, H, W, 3] (or [H, W, 3]; 4 channels for in_format 1/2).  Returns uint8 [n, bytes_per_frame]."""
     L = lib()
     rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
     if rgb.ndim == 3:
         rgb = rgb[None]
     n = rgb.shape[0]
-    assert rgb.shape[1:] == (p.height, p.width, 3), (rgb.shape, p.height, p.width)
+    assert rgb.shape[1:] == (p.height, p.width, 3 if p.in_format == 0 else 4), (rgb.shape, p.height, p.width)
     out = np.empty((n, L.csic_oracle_out_bytes_per_frame(ctypes.byref(p))), dtype=np.uint8)
     rc = L.csic_oracle_process(ctypes.byref(p), rgb.ctypes.data, n, out.ctypes.data, threads)
     if rc != 0:

@@ -186,9 +186,12 @@ size_t csic_oracle_out_bytes_per_frame(const csic_params* p) {
 static int process_frame(const csic_params* p, const uint8_t* rgb, uint8_t* out, ycc_t* s0, ycc_t* s1) {
   const int W = p->width, H = p->height;
   size_t n = (size_t)W * H;
+  /* pixel.red()/green()/blue() -- alpha is never read (ImageCompressorTopApp.scala:86-89) */
+  const size_t ipb = p->in_format == CSIC_IN_RGB24 ? 3 : 4;
+  const int ir = p->in_format == CSIC_IN_BGRA32 ? 2 : 0, ib = p->in_format == CSIC_IN_BGRA32 ? 0 : 2;
   for (size_t i = 0; i < n; ++i) {           /* raster order, ImageCompressorTopApp.scala:77-89 */
     int y, cb, cr;
-    csic_oracle_rgb2ycbcr(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], p->round_mode, &y, &cb, &cr);
+    csic_oracle_rgb2ycbcr(rgb[ipb * i + ir], rgb[ipb * i + 1], rgb[ipb * i + ib], p->round_mode, &y, &cb, &cr);
     s0[i].y = (uint8_t)y; s0[i].cb = (uint8_t)cb; s0[i].cr = (uint8_t)cr;
   }
   ycc_t *cur = s0, *nxt = s1;
@@ -263,7 +266,7 @@ int csic_oracle_process(const csic_params* p, const uint8_t* rgb, size_t n_frame
   if (!p || !rgb || !out) return CSIC_EINVAL_ARG;
   if (threads < 1) threads = 1;
   if ((size_t)threads > n_frames) threads = n_frames ? (int)n_frames : 1;
-  size_t in_stride = (size_t)p->width * p->height * 3, out_stride = csic_oracle_out_bytes_per_frame(p);
+  size_t in_stride = (size_t)p->width * p->height * (p->in_format == CSIC_IN_RGB24 ? 3 : 4), out_stride = csic_oracle_out_bytes_per_frame(p);
   job_t* jobs = (job_t*)calloc((size_t)threads, sizeof(job_t));
   pthread_t* th = (pthread_t*)calloc((size_t)threads, sizeof(pthread_t));
   if (!jobs || !th) { free(jobs); free(th); return CSIC_ENOMEM; }

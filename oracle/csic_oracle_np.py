@@ -81,9 +81,11 @@ def slot_bits(q):
     return 8 if t <= 8 else (16 if t <= 16 else 32)
 
 
-def process_frame(rgb, a=4, b=4, q=(8, 8, 8), factor=1, ops=(3, 1, 2), round_mode=0, pool_mode=0, out_format=0):
-    """One frame [H,W,3] uint8 -> flat uint8 output in the csic_out_format layout."""
+def process_frame(rgb, a=4, b=4, q=(8, 8, 8), factor=1, ops=(3, 1, 2), round_mode=0, pool_mode=0, out_format=0,
+                  in_format=0):
+    """One frame [H,W,3|4] uint8 -> flat uint8 output in the csic_out_format layout."""
     H, W = rgb.shape[:2]
+    rgb = rgb[..., [2, 1, 0]] if in_format == 2 else rgb[..., :3]      # alpha is never read
     ops = tuple(ops)
     chroma_first = ops.index(3) < ops.index(1)
     quant_first = ops.index(2) < ops.index(1)
@@ -129,4 +131,4 @@ def process(p, rgb):
     if rgb.ndim == 3:
         rgb = rgb[None]
     return np.stack([process_frame(fr, p.chroma_a, p.chroma_b, (p.y_bits, p.cb_bits, p.cr_bits), p.factor,
-                                   tuple(p.op), p.round_mode, p.pool_mode, p.out_format) for fr in rgb])
+                                   tuple(p.op), p.round_mode, p.pool_mode, p.out_format, getattr(p, 'in_format', 0)) for fr in rgb])

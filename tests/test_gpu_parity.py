@@ -29,10 +29,10 @@ def ctx(csic):
     c.close()
 
 
-def both_params(csic, W, H, a, b, q, f, order, round_mode=0, pool_mode=0, out_format=0):
+def both_params(csic, W, H, a, b, q, f, order, round_mode=0, pool_mode=0, out_format=0, in_format=0):
     ops = tuple(ORD[ch] for ch in order)
-    p = csic.make_params(W, H, a, b, q[0], q[1], q[2], f, ops, round_mode, pool_mode, out_format)
-    po = oracle.make_params(W, H, a, b, q, f, order, round_mode, pool_mode, out_format)
+    p = csic.make_params(W, H, a, b, q[0], q[1], q[2], f, ops, round_mode, pool_mode, out_format, in_format)
+    po = oracle.make_params(W, H, a, b, q, f, order, round_mode, pool_mode, out_format, in_format)
     return p, po
 
 
@@ -322,3 +322,22 @@ def test_writes_stay_inside_the_output_buffer(csic, ctx):
                 assert torch.equal(o3[:, 1:oh - 1], want.view(n, oh, rb)[:, 1:oh - 1])
                 assert bool((o3[:, 0] == 0xA5).all()) and bool((o3[:, oh - 1] == 0xA5).all())
     ctx.set_option(0, 0)
+
+
+@pytest.mark.parametrize("in_format", [1, 2], ids=["RGBA32", "BGRA32"])
+def test_four_byte_input_formats(csic, ctx, in_format):
+    """RGBA32 / BGRA32 input (alpha ignored, as pixel.red/green/blue ignores it): equals the oracle, and
+    equals the RGB24 path on the same colours, on aligned (row kernel) and odd (generic kernel) shapes."""
+    sel = [0, 1, 2] if in_format == 1 else [2, 1, 0]
+    seen = set()
+    for (W, H), f, ab, order, (fmt, q) in itertools.product(
+            [(64, 16), (256, 12), (128, 9), (40, 12), (33, 7)], (1, 2, 4, 8), [(4, 4), (2, 0), (1, 0)],
+            ("CSQ", "SQC"), [(0, (8, 8, 8)), (1, (6, 5, 5)), (3, (8, 8, 8)), (2, (3, 3, 2))]):
+        rgba = np.random.default_rng(W * 13 + f).integers(0, 256, size=(3, H, W, 4), dtype=np.uint8)
+        p4, po4 = both_params(csic, W, H, ab[0], ab[1], q, f, order, 0, 0, fmt, in_format)
+        p3, _ = both_params(csic, W, H, ab[0], ab[1], q, f, order, 0, 0, fmt, 0)
+        out4, fam = run_both_kernels(ctx, p4, rgba)
+        seen.add(fam)
+        assert np.array_equal(out4, oracle.process(po4, rgba)), (W, H, f, ab, order, fmt)
+        assert np.array_equal(out4, ctx.process_host(p3, np.ascontiguousarray(rgba[..., sel])))
+    assert seen == {1, 2}
