@@ -44,6 +44,10 @@ WORKLOADS = {
              "BASELINE configs[1] batched: 512x512 x4096 frames, 4:2:2 + f=2, YCC888"),
     "cfg2x1": (512, 512, 1, 2, 2, (8, 8, 8), 2, "CSQ", 0,
                "BASELINE configs[1]: ONE 512x512 frame, 4:2:2 + f=2, YCC888 (launch-latency bound)"),
+    "cfg4avg": (3840, 2160, 1024, 2, 0, (8, 8, 8), 2, "CSQ", 3,
+                "AVERAGE-pooling extension on the cfg4 geometry: 4:2:0 + 2x2 mean + BUNDLE128 (reads every row)"),
+    "cfg5avg": (7680, 4320, 64, 2, 0, (6, 5, 5), 4, "CSQ", 1,
+                "AVERAGE-pooling extension on the cfg5 geometry: 4:2:0 + 4x4 mean + Q_16BIT + RGB888"),
     "cfg5": (7680, 4320, 64, 2, 0, (6, 5, 5), 4, "CSQ", 1,
              "BASELINE configs[4]: 7680x4320 x64 frames, 4:2:0 + f=4 + Q_16BIT + RGB888 reconstruct"),
 }
@@ -169,7 +173,7 @@ def config_dict(name, wl, frames_per_gpu, note=None):
     c = {"workload": f"{name}: {desc}", "width": W, "height": H, "frames_per_gpu": frames_per_gpu,
          "chroma": f"4:{a}:{b}", "quant_bits": list(q), "factor": f, "order": order,
          "out_format": ["YCC888", "RGB888", "BUNDLE64", "BUNDLE128"][fmt], "round_mode": "FLOOR",
-         "pool_mode": "DECIMATE", "in_format": "RGB24", "sharding": "frames split across ranks, no collective",
+         "pool_mode": "AVERAGE (extension)" if name.endswith("avg") else "DECIMATE", "in_format": "RGB24", "sharding": "frames split across ranks, no collective",
          "l2": "inputs (>=1 GB per step) far larger than the 126 MB L2; no flush needed"}
     if note:
         c["note"] = note
@@ -222,7 +226,8 @@ def main():
     W, H, frames, a, b, q, f, order, fmt, desc = wl
     frames = args.frames or frames
     ops = tuple(ORD[c] for c in order)
-    p = csic.make_params(W, H, a, b, q[0], q[1], q[2], f, ops, out_format=fmt, in_format=args.in_format)
+    pool = 1 if args.workload.endswith("avg") else 0
+    p = csic.make_params(W, H, a, b, q[0], q[1], q[2], f, ops, pool_mode=pool, out_format=fmt, in_format=args.in_format)
     ipb = 3 if args.in_format == 0 else 4
     _, out_h, _, out_fb = csic.out_shape(p)
     ctx = csic.Context(local)
@@ -251,7 +256,7 @@ def main():
         nchk = min(2, frames)
         ctx.process_torch(p, rgb[:nchk], out=out[:nchk])
         torch.cuda.synchronize()
-        want = oracle.process(oracle.make_params(W, H, a, b, q, f, order, out_format=fmt, in_format=args.in_format),
+        want = oracle.process(oracle.make_params(W, H, a, b, q, f, order, pool_mode=pool, out_format=fmt, in_format=args.in_format),
                               rgb[nchk - 1].cpu().numpy())
         parity = bool(np.array_equal(out[nchk - 1].cpu().numpy(), want[0]))
 
@@ -319,7 +324,7 @@ def main():
     mp_per_step_all = frames * W * H * (world if band is None else 1) / 1e6
     value = mp_per_step_all * args.steps / (total_ms_max / 1e3)
 
-    alg_bytes = algorithmic_bytes_per_frame(W, H, f, out_fb, ipb=ipb) * frames          # per launch (one rank)
+    alg_bytes = algorithmic_bytes_per_frame(W, H, f, out_fb, average=bool(pool), ipb=ipb) * frames          # per launch (one rank)
     if band is not None:
         alg_bytes = alg_bytes * band[1] // out_h
     kernel_ms = statistics.mean(step_ms)                                      # one launch per step
@@ -399,7 +404,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(kernel_ms, 4),
-                         "kernel": "csic_rows_kernel" if fam == 2 else "csic_generic_kernel", "peak_source": peak_src},
+                         "kernel": {2: "csic_rows_kernel", 3: "csic_pool_kernel"}.get(fam, "csic_generic_kernel"),
+                         "peak_source": peak_src},
             "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches1 - launches0) * world,
             "timed_as": "cuda_graph_replay" if args.graph else "stream_launches",

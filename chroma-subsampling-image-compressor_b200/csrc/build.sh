@@ -12,6 +12,9 @@ pids=()
 for f in 1 2 4 8; do
   "$NVCC" "${FLAGS[@]}" -DCSIC_ROWS_F=$f -c csic_rows_kernel.cu -o "$OBJ/rows_f$f.o" 2> "$OBJ/rows_f$f.log" & pids+=($!)
 done
+for f in 2 4 8; do
+  "$NVCC" "${FLAGS[@]}" -DCSIC_POOL_F=$f -c csic_pool_kernel.cu -o "$OBJ/pool_f$f.o" 2> "$OBJ/pool_f$f.log" & pids+=($!)
+done
 "$NVCC" "${FLAGS[@]}" -c csic_kernels.cu -o "$OBJ/kernels.o" 2> "$OBJ/kernels.log" & pids+=($!)
 "$NVCC" "${FLAGS[@]}" -c csic_api.cu -o "$OBJ/api.o" 2> "$OBJ/api.log" & pids+=($!)
 "$NVCC" "${FLAGS[@]}" -x cu -c csic_params.cpp -o "$OBJ/params.o" 2> "$OBJ/params.log" & pids+=($!)
@@ -19,6 +22,6 @@ rc=0
 for p in "${pids[@]}"; do wait "$p" || rc=1; done
 cat "$OBJ"/*.log > build.log
 if [ $rc -ne 0 ]; then grep -v "ptxas info" build.log; exit 1; fi
-"$NVCC" -gencode arch=compute_100a,code=sm_100a --shared -cudart static -o "$OUT" "$OBJ"/rows_f1.o "$OBJ"/rows_f2.o "$OBJ"/rows_f4.o "$OBJ"/rows_f8.o "$OBJ"/kernels.o "$OBJ"/api.o "$OBJ"/params.o
+"$NVCC" -gencode arch=compute_100a,code=sm_100a --shared -cudart static -o "$OUT" "$OBJ"/rows_f1.o "$OBJ"/rows_f2.o "$OBJ"/rows_f4.o "$OBJ"/rows_f8.o "$OBJ"/pool_f2.o "$OBJ"/pool_f4.o "$OBJ"/pool_f8.o "$OBJ"/kernels.o "$OBJ"/api.o "$OBJ"/params.o
 grep -E "error|warning" build.log | grep -v "ptxas info" || true
 echo "built $(realpath $OUT)"

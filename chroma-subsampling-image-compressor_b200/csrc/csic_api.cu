@@ -142,6 +142,9 @@ int run(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t n_frames,
   if (ctx->opt_family != 1 && csic::plan_rows_kernel(k, ctx->sm_count, ctx->max_smem_optin, ctx->opt_stages, ctx->opt_tile_bytes)) {
     err = csic::launch_rows(k, ctx->sm_count, ctx->opt_ctas_per_sm, st);
     ctx->last_family = 2;
+  } else if (ctx->opt_family != 1 && csic::plan_pool_kernel(k, ctx->sm_count, ctx->max_smem_optin)) {
+    err = csic::launch_pool(k, ctx->sm_count, ctx->opt_ctas_per_sm, st);
+    ctx->last_family = 3;
   } else {
     err = csic::launch_generic(k, st);
     ctx->last_family = 1;

@@ -62,7 +62,7 @@ struct KPlan {
 };
 
 struct LaunchInfo {
-  int family;      // 1 generic gather kernel, 2 TMA-staged row kernel
+  int family;      // 1 generic gather kernel, 2 TMA-staged row kernel, 3 TMA-staged pooling kernel
   int launches;
 };
 
@@ -76,6 +76,12 @@ int launch_rows(const KPlan& k, int sm_count, int force_ctas_per_sm, void* strea
 constexpr int kDefaultBlockThreads = 256;   // consumer threads; one producer warp is added at launch
 constexpr int kMaxConsumerThreads = 512;
 int rows_kernel_set_attributes(size_t max_smem_optin);
+
+// AVERAGE extension: TMA-staged pooling kernel (csic_pool_kernel.cu), chroma-first orders only.
+bool plan_pool_kernel(KPlan& k, int sm_count, size_t max_smem_optin);
+int launch_pool(const KPlan& k, int sm_count, int force_ctas_per_sm, void* stream);
+template <int F> int launch_pool_factor(const KPlan& k, unsigned grid, void* stream);
+template <int F> int pool_set_attributes_factor(size_t max_smem_optin);
 
 // Implemented once per spatial factor in csic_rows_kernel.cu (explicit specialisations for F = 1, 2, 4, 8).
 template <int F> int launch_rows_factor(const KPlan& k, unsigned grid, void* stream);

@@ -248,11 +248,78 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
 
 int rows_kernel_set_attributes(size_t max_smem_optin) {
   int e;
+  if ((e = pool_set_attributes_factor<2>(max_smem_optin)) != 0) return e;
+  if ((e = pool_set_attributes_factor<4>(max_smem_optin)) != 0) return e;
+  if ((e = pool_set_attributes_factor<8>(max_smem_optin)) != 0) return e;
   if ((e = rows_set_attributes_factor<1>(max_smem_optin)) != 0) return e;
   if ((e = rows_set_attributes_factor<2>(max_smem_optin)) != 0) return e;
   if ((e = rows_set_attributes_factor<4>(max_smem_optin)) != 0) return e;
   if ((e = rows_set_attributes_factor<8>(max_smem_optin)) != 0) return e;
   return 0;
+}
+
+// ---- AVERAGE extension: planning and dispatch of csic_pool_kernel --------------------------------
+bool plan_pool_kernel(KPlan& k, int sm_count, size_t max_smem_optin) {
+  if (!(k.average && k.f > 1)) return false;
+  if (k.case_b) return false;                                   // pooling before chroma: generic kernel
+  if (k.Wo % 16 != 0 || k.in_row_bytes % 16 != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(k.in) | reinterpret_cast<uintptr_t>(k.out)) & 15u) return false;
+  if ((k.in_frame_bytes | k.out_frame_bytes | k.out_row_bytes) & 15u) return false;
+  if (k.slots_per_row != k.Wo) return false;
+  if (k.band_rows <= 0 || k.n_frames == 0) return false;
+  if (k.block_threads <= 0) k.block_threads = kDefaultBlockThreads;
+  if (k.block_threads > kMaxConsumerThreads) return false;
+
+  const bool staged = k.kformat <= KF_RGB888;
+  const uint32_t opx = staged ? 3u : (uint32_t)k.slot_bytes;
+  const uint32_t f = (uint32_t)k.f, ipb = (uint32_t)k.in_px_bytes;
+  const uint32_t budget = 24u * 1024u, tile_max = budget + budget / 3;
+  const uint32_t block_row_bytes = (uint32_t)k.Wo * f * f * ipb;          // the f input rows of one output row
+  int nsplit = 0;
+  for (int n = (int)((block_row_bytes + tile_max - 1) / tile_max); n <= 256; ++n)
+    if (n >= 1 && k.Wo % (16 * n) == 0) { nsplit = n; break; }
+  if (nsplit == 0) return false;
+  k.nsplit = nsplit;
+  k.tile_px = k.Wo / nsplit;
+  k.tile_in_bytes = (uint32_t)k.tile_px * f * f * ipb;                   // per output-row segment: f row parts
+  k.tile_out_bytes = (uint32_t)k.tile_px * opx;
+  int rows = 1;
+  if (nsplit == 1) {
+    rows = (int)std::max<uint32_t>(1u, budget / k.tile_in_bytes);
+    rows = std::min(rows, (int)(2u * (uint32_t)kMaxTileRows / f));      // held_addr[] holds rows * f/2 entries
+    rows = std::min(rows, k.band_rows);
+    auto tiles_for = [&](int r) { return (uint64_t)k.n_frames * (uint64_t)((k.band_rows + r - 1) / r); };
+    while (rows > 1 && tiles_for(rows) < (uint64_t)sm_count * 4u) rows = (rows + 1) / 2;
+  }
+  k.tile_rows = rows;
+  k.tiles_per_band = (uint32_t)((k.band_rows + rows - 1) / rows);
+  const uint64_t n_tiles = (uint64_t)k.n_frames * (uint64_t)k.tiles_per_band * (uint64_t)nsplit;
+  if (n_tiles >= (1ull << 31)) return false;
+  k.n_tiles = (uint32_t)n_tiles;
+  auto up128 = [](uint32_t v) { return (v + 127u) & ~127u; };
+  k.stage_stride = up128((uint32_t)rows * k.tile_in_bytes + (uint32_t)kMaxTileRows * 32u);
+  k.out_buf_stride = staged ? up128((uint32_t)rows * k.tile_out_bytes) : 0u;
+  k.stages = 2;
+  const uint32_t need = 2u * k.stage_stride + 2u * k.out_buf_stride + 2u * kTileMetaBytes + 32u + 384u;
+  if (need > max_smem_optin) return false;
+  // pooling converts every input pixel: the kernel is issue-bound, so take all the warps that fit (measured:
+  // 4 CTAs 0.79 of the copy peak on the 4K 2x2 case vs 0.73 with 2)
+  k.ctas_per_sm = (int32_t)std::max<uint32_t>(1u, std::min<uint32_t>(4u, 227u * 1024u / (need + 1024u)));
+  k.out_buf_off = 2u * k.stage_stride;
+  k.meta_off = up128(k.out_buf_off + 2u * k.out_buf_stride);
+  k.bar_off = up128(k.meta_off + 2u * kTileMetaBytes);
+  k.smem_bytes = k.bar_off + 2u * 16u;
+  return true;
+}
+
+int launch_pool(const KPlan& k, int sm_count, int force_ctas_per_sm, void* stream) {
+  const int per_sm = force_ctas_per_sm > 0 ? force_ctas_per_sm : std::max(1, k.ctas_per_sm);
+  const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)k.n_tiles, (uint64_t)sm_count * (uint64_t)per_sm);
+  switch (k.f) {
+    case 2: return launch_pool_factor<2>(k, grid, stream);
+    case 4: return launch_pool_factor<4>(k, grid, stream);
+    default: return launch_pool_factor<8>(k, grid, stream);
+  }
 }
 
 int launch_rows(const KPlan& k, int sm_count, int force_ctas_per_sm, void* stream) {

@@ -1,0 +1,344 @@
+// csic_pool_kernel<F, FMT, IN4> -- TMA-staged kernel for the AVERAGE pooling extension (pool_mode = AVERAGE,
+// chroma stage before the spatial stage).  Not reference behaviour: the reference's SpatialDownsampler is point
+// decimation (SpatialDownsampler.scala:33-55); README.md:44 only *says* "average pooling".  Semantics are the
+// oracle's: mean of the f x f block of the stream entering the spatial stage, per channel, round half up.
+//
+// Same machinery as csic_rows_kernel (producer warp + full/empty mbarriers + TMA bulk copies), but a tile needs
+// ALL f input rows of every output row, so the f x f block resolves on chip:
+//   stage layout   row part (j*F + dr) of the tile at  (j*F + dr) * seg_row_bytes      (j: output row, dr: 0..F-1)
+//   granule        4 output pixels = F rows x 4F input pixels
+//   chroma hold    in-row: sample at i % hf == 0 inside the 4F-pixel span; odd lines of 4:2:0 / 4:1:0 replay the
+//                  last sample of the line above, which is the previous row part of the same block
+//                  (ChromaSubsampler.scala:52-65); when rows are split into segments it is TMA-fetched instead.
+// Compiled once per F = CSIC_POOL_F (2, 4, 8).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+
+#include "csic_internal.h"
+#include "csic_device_math.cuh"
+#include "csic_tma.cuh"
+
+#ifndef CSIC_POOL_F
+#error "compile with -DCSIC_POOL_F=2|4|8"
+#endif
+
+namespace csic {
+
+struct PoolMeta {
+  uint64_t out_base;
+  uint32_t n_granules;
+  uint32_t pad;
+  uint32_t held_addr[kMaxTileRows];   // index j * (F/2) + dr/2: shared address of the pixel an odd line replays
+};
+static_assert(sizeof(PoolMeta) == kTileMetaBytes, "kTileMetaBytes out of sync");
+
+struct PoolConst {
+  uint32_t coef_y, coef_ncb, coef_ncr;
+  uint32_t pre_y, pre_cb, pre_cr;     // quantiser keep-masks applied BEFORE pooling (0xFF when quant follows)
+  uint32_t pre_y4;                    // pre_y replicated into the four bytes of a word
+  uint32_t post_y, post_cb, post_cr;  // ... and AFTER pooling (0xFF when quant came first)
+  int sy, scb, scr, ly, lb;           // bundle slot shifts
+  uint32_t gran_per_row, nthreads, row0_of_thread, rem0_of_thread, drow, drem;
+  uint32_t seg_row_bytes;
+  bool trunc, vhold;
+};
+
+// 4F consecutive input pixels of one row part, each as a word whose low three bytes are the colour bytes.
+template <int F, bool IN4>
+__device__ __forceinline__ void load_row_part(uint32_t a, uint32_t (&p)[4 * F]) {
+  if (IN4) {
+#pragma unroll
+    for (int k = 0; k < F; ++k) {
+      const uint4 v = lds128(a + 16u * k);
+      p[4 * k] = v.x; p[4 * k + 1] = v.y; p[4 * k + 2] = v.z; p[4 * k + 3] = v.w;
+    }
+  } else {
+    uint32_t w[3 * F];
+    if (F == 2) {                      // 24 bytes, 8-byte aligned
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { const uint2 v = lds64(a + 8u * k); w[2 * k] = v.x; w[2 * k + 1] = v.y; }
+    } else {                           // 48 / 96 bytes, 16-byte aligned
+#pragma unroll
+      for (int k = 0; k < 3 * F / 4; ++k) {
+        const uint4 v = lds128(a + 16u * k);
+        w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4 * F; ++i) {
+      const int k = (3 * i) >> 2, sh = ((3 * i) & 3) * 8;
+      p[i] = (sh == 0) ? w[k] : ((k + 1 < 3 * F) ? __funnelshift_r(w[k], w[k + 1], sh) : (w[k] >> sh));
+    }
+  }
+}
+
+template <int F, int FMT, bool IN4, int HF, bool TRUNC>
+__device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t* __restrict__ out_g,
+                                          const PoolMeta* __restrict__ meta, const PoolConst& C) {
+  constexpr uint32_t kGranBytes = (IN4 ? 16u : 12u) * F;     // one row part of a granule
+  constexpr int kShift = (F == 2) ? 2 : (F == 4 ? 4 : 6);    // log2(F*F)
+  constexpr int kHalf = (F * F) / 2;
+  const uint32_t n = meta->n_granules;
+  uint32_t row = C.row0_of_thread, rem = C.rem0_of_thread;
+  for (uint32_t q = threadIdx.x; q < n; q += C.nthreads) {
+    int ay[4] = {0, 0, 0, 0}, ab[4] = {0, 0, 0, 0}, ar[4] = {0, 0, 0, 0};
+    const uint32_t base = in_s + row * (F * C.seg_row_bytes) + rem * kGranBytes;
+#pragma unroll 1
+    for (int dr = 0; dr < F; ++dr) {
+      uint32_t p[4 * F];
+      load_row_part<F, IN4>(base + (uint32_t)dr * C.seg_row_bytes, p);
+      // Y: byte 1 of each dp4a result is the pixel's Y.  Gather the F bytes of an output pixel's row part into
+      // words with PRMT (byte 3 of a result is zero: the pad), mask once, and let dp4a add the bytes up.
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        uint32_t d[F];
+#pragma unroll
+        for (int i = 0; i < F; ++i) d[i] = fwd_y16(p[o * F + i], C.coef_y);
+        if (F == 2) {
+          const uint32_t w = __byte_perm(d[0], d[1], 0x3351) & C.pre_y4;
+          ay[o] = (int)dp4a_uu(w, 0x01010101u, (uint32_t)ay[o]);
+        } else {
+#pragma unroll
+          for (int h = 0; h < F / 4; ++h) {
+            const uint32_t lo = __byte_perm(d[4 * h], d[4 * h + 1], 0x3351), hi = __byte_perm(d[4 * h + 2], d[4 * h + 3], 0x3351);
+            const uint32_t w = __byte_perm(lo, hi, 0x5410) & C.pre_y4;
+            ay[o] = (int)dp4a_uu(w, 0x01010101u, (uint32_t)ay[o]);
+          }
+        }
+      }
+      if (C.vhold && (dr & 1)) {
+        // nothing is sampled on an odd line: every pixel replays the last sample of the line above
+        const uint32_t ha = meta->held_addr[row * (F / 2) + (uint32_t)(dr >> 1)];
+        const uint32_t hp = lds8(ha) | (lds8(ha + 1) << 8) | (lds8(ha + 2) << 16);
+        const int hb = (int)(((fwd_nc16<TRUNC>(hp, C.coef_ncb) ^ 0xFFFFu) >> 8) & C.pre_cb) * F;
+        const int hr = (int)(((fwd_nc16<TRUNC>(hp, C.coef_ncr) ^ 0xFFFFu) >> 8) & C.pre_cr) * F;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) { ab[o] += hb; ar[o] += hr; }
+      } else {
+        int cb = 0, cr = 0;
+#pragma unroll
+        for (int i = 0; i < 4 * F; ++i) {
+          if (i % HF == 0) {          // sample point; held for the next HF-1 pixels (ChromaSubsampler.scala:57-65)
+            cb = (int)(((fwd_nc16<TRUNC>(p[i], C.coef_ncb) ^ 0xFFFFu) >> 8) & C.pre_cb);
+            cr = (int)(((fwd_nc16<TRUNC>(p[i], C.coef_ncr) ^ 0xFFFFu) >> 8) & C.pre_cr);
+          }
+          ab[i / F] += cb;
+          ar[i / F] += cr;
+        }
+      }
+    }
+    uint32_t y[4], cb[4], cr[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {      // round half up, then the quantiser if it follows the pooling
+      y[o] = (uint32_t)((ay[o] + kHalf) >> kShift) & C.post_y;
+      cb[o] = (uint32_t)((ab[o] + kHalf) >> kShift) & C.post_cb;
+      cr[o] = (uint32_t)((ar[o] + kHalf) >> kShift) & C.post_cr;
+    }
+    if (FMT == KF_YCC888 || FMT == KF_RGB888) {
+      uint32_t w0, w1, w2;
+      if (FMT == KF_YCC888) {
+        w0 = y[0] | (cb[0] << 8) | (cr[0] << 16) | (y[1] << 24);
+        w1 = cb[1] | (cr[1] << 8) | (y[2] << 16) | (cb[2] << 24);
+        w2 = cr[2] | (y[3] << 8) | (cb[3] << 16) | (cr[3] << 24);
+      } else {
+        uint32_t v[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) v[o] = inverse_rgb((int)y[o], (int)cb[o], (int)cr[o]);
+        w0 = v[0] | (v[1] << 24);
+        w1 = (v[1] >> 8) | (v[2] << 16);
+        w2 = (v[2] >> 16) | (v[3] << 8);
+      }
+      const uint32_t a = out_s + q * 12u;
+      sts32(a, w0); sts32(a + 4, w1); sts32(a + 8, w2);
+    } else {
+      uint32_t v[4];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) v[o] = ((y[o] >> C.sy) << C.ly) | ((cb[o] >> C.scb) << C.lb) | (cr[o] >> C.scr);
+      if (FMT == KF_SLOT32) __stcs(reinterpret_cast<uint4*>(out_g) + q, make_uint4(v[0], v[1], v[2], v[3]));
+      else if (FMT == KF_SLOT16) __stcs(reinterpret_cast<uint2*>(out_g) + q, make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16)));
+      else __stcs(reinterpret_cast<uint32_t*>(out_g) + q, v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
+    }
+    row += C.drow;
+    rem += C.drem;
+    if (rem >= C.gran_per_row) { rem -= C.gran_per_row; ++row; }
+  }
+}
+
+template <int F, int FMT, bool IN4>
+__global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_pool_kernel(const __grid_constant__ KPlan P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr bool kStaged = (FMT == KF_YCC888 || FMT == KF_RGB888);
+  const uint32_t tid = threadIdx.x;
+  const uint32_t NC = blockDim.x - 32u;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t S = (uint32_t)P.stages;
+  const uint32_t n_my = (P.n_tiles > blockIdx.x) ? (P.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const uint64_t pol = policy_evict_first();
+  const uint32_t full_bar = sbase + P.bar_off, empty_bar = full_bar + S * 8u;
+  const uint32_t seg_row_bytes = P.tile_in_bytes / F;          // one input row part of a segment
+
+  if (tid == 0) {
+    for (uint32_t s = 0; s < S; ++s) {
+      mbar_init(full_bar + s * 8u, 1);
+      mbar_init(empty_bar + s * 8u, NC / 32u);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // ============================== producer warp ==============================================
+  if (tid >= NC) {
+    if (tid != NC) return;
+    const uint32_t ipb = (uint32_t)P.in_px_bytes;
+    for (uint32_t i = 0; i < n_my; ++i) {
+      const uint32_t s = i % S;
+      if (i >= S) mbar_wait(empty_bar + s * 8u, ((i / S) - 1u) & 1u);
+      const uint32_t tile = blockIdx.x + i * gridDim.x;
+      const uint32_t t2 = tile / (uint32_t)P.nsplit;
+      const uint32_t seg = tile - t2 * (uint32_t)P.nsplit;
+      const uint32_t k = t2 / P.tiles_per_band;
+      const uint32_t tb = t2 - k * P.tiles_per_band;
+      const uint32_t ro0 = (uint32_t)P.row0 + tb * (uint32_t)P.tile_rows;
+      const uint32_t nrows = min((uint32_t)P.tile_rows, (uint32_t)(P.row0 + P.band_rows) - ro0);
+      const uint8_t* frame = P.in + (uint64_t)k * P.in_frame_bytes;
+      const uint32_t bar = full_bar + s * 8u;
+      const uint32_t dst = sbase + s * P.stage_stride;
+      const uint32_t aux = dst + (uint32_t)P.tile_rows * P.tile_in_bytes;    // kMaxTileRows windows of 32 bytes
+      PoolMeta* m = reinterpret_cast<PoolMeta*>(smem + P.meta_off) + s;
+
+      uint32_t n_aux = 0;
+      const uint8_t* aux_src[kMaxTileRows];
+      if (P.vf == 2) {
+        for (uint32_t j = 0; j < nrows; ++j)
+          for (uint32_t h = 0; h < F / 2; ++h) {       // odd input line dr = 2h+1 replays (dr-1, lastSampleCol)
+            const uint32_t e = j * (F / 2) + h;
+            if (P.nsplit == 1) {
+              m->held_addr[e] = dst + (j * F + 2 * h) * seg_row_bytes + (uint32_t)P.last_sample_col * ipb;
+              aux_src[e] = nullptr;
+            } else {
+              const uint8_t* hp = frame + (uint64_t)((ro0 + j) * F + 2 * h) * P.in_row_bytes + (uint32_t)P.last_sample_col * ipb;
+              const uint64_t a = reinterpret_cast<uint64_t>(hp);
+              m->held_addr[e] = aux + e * 32u + (uint32_t)(a & 15u);
+              aux_src[e] = reinterpret_cast<const uint8_t*>(a & ~(uint64_t)15);
+              ++n_aux;
+            }
+          }
+      }
+      m->n_granules = nrows * ((uint32_t)P.tile_px >> 2);
+      m->out_base = reinterpret_cast<uint64_t>(P.out) + (uint64_t)k * P.out_frame_bytes + (uint64_t)ro0 * P.out_row_bytes +
+                    (uint64_t)seg * P.tile_out_bytes;
+      mbar_expect_tx(bar, nrows * P.tile_in_bytes + n_aux * 32u);
+      const uint8_t* src = frame + (uint64_t)(ro0 * F) * P.in_row_bytes + (uint64_t)seg * seg_row_bytes;
+      if (P.nsplit == 1) {                   // whole rows: the F*nrows input rows are one contiguous range
+        tma_load_1d(dst, src, nrows * P.tile_in_bytes, bar, pol);
+      } else {
+        for (uint32_t r = 0; r < nrows * F; ++r)
+          tma_load_1d(dst + r * seg_row_bytes, src + (uint64_t)r * P.in_row_bytes, seg_row_bytes, bar, pol);
+      }
+      if (n_aux) {
+        for (uint32_t e = 0; e < nrows * (F / 2); ++e)
+          if (aux_src[e]) tma_load_1d(aux + e * 32u, aux_src[e], 32u, bar, pol);
+      }
+    }
+    return;
+  }
+
+  // ============================== consumer warps =============================================
+  PoolConst C;
+  {
+    const uint32_t my = P.qmask & 0xFFu, mcb = (P.qmask >> 8) & 0xFFu, mcr = (P.qmask >> 16) & 0xFFu;
+    C.coef_y = P.coef_y; C.coef_ncb = P.coef_ncb; C.coef_ncr = P.coef_ncr;
+    C.pre_y = P.quant_first ? my : 0xFFu;   C.pre_cb = P.quant_first ? mcb : 0xFFu;   C.pre_cr = P.quant_first ? mcr : 0xFFu;
+    C.pre_y4 = C.pre_y * 0x01010101u;
+    C.post_y = P.quant_first ? 0xFFu : my;  C.post_cb = P.quant_first ? 0xFFu : mcb;  C.post_cr = P.quant_first ? 0xFFu : mcr;
+    C.sy = P.sy; C.scb = P.scb; C.scr = P.scr;
+    C.ly = P.cb_bits + P.cr_bits; C.lb = P.cr_bits;
+    C.gran_per_row = (uint32_t)P.tile_px >> 2;
+    C.nthreads = NC;
+    C.row0_of_thread = tid / C.gran_per_row;
+    C.rem0_of_thread = tid % C.gran_per_row;
+    C.drow = NC / C.gran_per_row;
+    C.drem = NC % C.gran_per_row;
+    C.seg_row_bytes = seg_row_bytes;
+    C.trunc = P.trunc != 0;
+    C.vhold = P.vf == 2;
+  }
+  const int hf = P.hf;
+
+  for (uint32_t i = 0; i < n_my; ++i) {
+    const uint32_t s = i % S;
+    mbar_wait(full_bar + s * 8u, (i / S) & 1u);
+    const uint32_t in_s = sbase + s * P.stage_stride;
+    const uint32_t out_s = sbase + P.out_buf_off + (i & 1u) * P.out_buf_stride;
+    const PoolMeta* m = reinterpret_cast<const PoolMeta*>(smem + P.meta_off) + s;
+    uint8_t* out_g = reinterpret_cast<uint8_t*>(m->out_base);
+    const uint32_t out_bytes = m->n_granules * 12u;
+    if (C.trunc) {
+      if (hf == 1) pool_tile<F, FMT, IN4, 1, true>(in_s, out_s, out_g, m, C);
+      else if (hf == 2) pool_tile<F, FMT, IN4, 2, true>(in_s, out_s, out_g, m, C);
+      else pool_tile<F, FMT, IN4, 4, true>(in_s, out_s, out_g, m, C);
+    } else {
+      if (hf == 1) pool_tile<F, FMT, IN4, 1, false>(in_s, out_s, out_g, m, C);
+      else if (hf == 2) pool_tile<F, FMT, IN4, 2, false>(in_s, out_s, out_g, m, C);
+      else pool_tile<F, FMT, IN4, 4, false>(in_s, out_s, out_g, m, C);
+    }
+
+    if (kStaged) {
+      fence_proxy_async_smem();
+      if (tid == 0) tma_store_wait_read0();
+      consumer_barrier(NC);
+      if (tid == 0) {
+        tma_store_1d(out_g, out_s, out_bytes, pol);
+        tma_store_commit();
+      }
+    }
+    __syncwarp();
+    if ((tid & 31u) == 0) mbar_arrive(empty_bar + s * 8u);
+  }
+  if (kStaged && tid == 0) tma_store_wait_all();
+}
+
+namespace {
+constexpr int kF = CSIC_POOL_F;
+
+template <int FMT, bool IN4>
+int launch_one(const KPlan& k, unsigned grid, cudaStream_t st) {
+  csic_pool_kernel<kF, FMT, IN4><<<grid, (unsigned)k.block_threads + 32u, k.smem_bytes, st>>>(k);
+  return (int)cudaGetLastError();
+}
+template <int FMT>
+int launch_fmt(const KPlan& k, unsigned grid, cudaStream_t st) {
+  return k.in_px_bytes == 4 ? launch_one<FMT, true>(k, grid, st) : launch_one<FMT, false>(k, grid, st);
+}
+template <int FMT, bool IN4>
+cudaError_t attr_one(size_t bytes) {
+  return cudaFuncSetAttribute(csic_pool_kernel<kF, FMT, IN4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+}  // namespace
+
+template <>
+int launch_pool_factor<CSIC_POOL_F>(const KPlan& k, unsigned grid, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (k.kformat) {
+    case KF_YCC888: return launch_fmt<KF_YCC888>(k, grid, st);
+    case KF_RGB888: return launch_fmt<KF_RGB888>(k, grid, st);
+    case KF_SLOT8: return launch_fmt<KF_SLOT8>(k, grid, st);
+    case KF_SLOT16: return launch_fmt<KF_SLOT16>(k, grid, st);
+    default: return launch_fmt<KF_SLOT32>(k, grid, st);
+  }
+}
+
+template <>
+int pool_set_attributes_factor<CSIC_POOL_F>(size_t b) {
+  cudaError_t e;
+#define CSIC_ATTR(FMT)                                                  \
+  if ((e = attr_one<FMT, false>(b)) != cudaSuccess) return (int)e;      \
+  if ((e = attr_one<FMT, true>(b)) != cudaSuccess) return (int)e;
+  CSIC_ATTR(KF_YCC888) CSIC_ATTR(KF_RGB888) CSIC_ATTR(KF_SLOT8) CSIC_ATTR(KF_SLOT16) CSIC_ATTR(KF_SLOT32)
+#undef CSIC_ATTR
+  return (int)cudaSuccess;
+}
+
+}  // namespace csic

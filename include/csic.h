@@ -200,7 +200,7 @@ CSIC_API int csic_set_option(csic_ctx* ctx, int option, int64_t value);
 CSIC_API int csic_host_bytes(const csic_ctx* ctx, uint64_t* h2d_total);
 
 /* Diagnostics: which kernel family the last process call on this ctx used (0 none, 1 generic gather
- * kernel, 2 TMA-staged row kernel) and how many kernels it launched. */
+ * kernel, 2 TMA-staged row kernel, 3 TMA-staged pooling kernel of the AVERAGE extension) and how many kernels it launched. */
 CSIC_API int csic_last_kernel(const csic_ctx* ctx, int32_t* family, int64_t* launches_total);
 
 #ifdef __cplusplus

@@ -134,12 +134,23 @@ def test_mode_sweep(csic, ctx, ab, f):
 
 @pytest.mark.parametrize("order", ALL_ORDERS)
 def test_average_extension(csic, ctx, order):
-    for (W, H), ab, f in itertools.product([(64, 16), (32, 8), (128, 24)], ALL_AB, (2, 4, 8)):
-        rgb = synth_frames(2, H, W, seed=f)
-        for fmt, q in ((0, (5, 4, 3)), (1, (8, 8, 8)), (3, (8, 8, 8))):
-            p, po = both_params(csic, W, H, ab[0], ab[1], q, f, order, 0, 1, fmt)
-            out = ctx.process_host(p, rgb)
-            assert np.array_equal(out, oracle.process(po, rgb)), (W, H, ab, f, fmt)
+    """pool_mode=AVERAGE (extension, parity unpinned): the TMA pooling kernel (chroma-first orders, aligned shapes)
+    and the generic kernel both equal the oracle; 3- and 4-byte pixels; both roundings; held 4:2:0 lines both
+    inside the tile (whole rows) and TMA-fetched (rows split into segments)."""
+    fams = set()
+    shapes = [(64, 16), (32, 8), (128, 24), (40, 8), (2048, 8), (4096, 16)]
+    for (W, H), ab, f in itertools.product(shapes, ALL_AB, (2, 4, 8)):
+        if W >= 2048 and (ab not in ((2, 0), (4, 4)) or order not in ("CSQ", "QCS", "SQC")):
+            continue
+        for fmt, q, inf, rm in ((0, (5, 4, 3), 0, 0), (1, (8, 8, 8), 1, 0), (3, (8, 8, 8), 0, 1), (2, (3, 3, 2), 2, 0)):
+            ch = 3 if inf == 0 else 4
+            rgb = np.random.default_rng(W + f + inf).integers(0, 256, size=(2, H, W, ch), dtype=np.uint8)
+            p, po = both_params(csic, W, H, ab[0], ab[1], q, f, order, rm, 1, fmt, inf)
+            out, fam = run_both_kernels(ctx, p, rgb)
+            fams.add(fam)
+            assert np.array_equal(out, oracle.process(po, rgb, threads=2)), (W, H, ab, f, fmt, inf, fam)
+    chroma_first = order.index("C") < order.index("S")
+    assert (3 in fams) == chroma_first, fams
 
 
 # ---- BASELINE.json geometries: oracle on sampled frames + size-independent properties -------------
@@ -272,7 +283,7 @@ def test_randomised_parameter_space(csic, ctx):
     (a,b), order, factor, format, rounding, bit depth, pooling mode), both kernels vs the oracle."""
     rng = np.random.default_rng(20261018)
     widths = [1, 2, 3, 5, 16, 17, 31, 32, 48, 64, 96, 100, 128, 160, 256, 272, 320]
-    seen = {1: 0, 2: 0}
+    seen = {1: 0, 2: 0, 3: 0}
     for it in range(400):
         f = int(rng.choice([1, 2, 4, 8]))
         pool = int(rng.random() < 0.15)
