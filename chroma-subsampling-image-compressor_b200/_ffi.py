@@ -40,6 +40,7 @@ PROTOTYPES = {
     "csic_create": (_int, [_int, ctypes.POINTER(_vp)]),
     "csic_destroy": (_int, [_vp]),
     "csic_process_device": (_int, [_vp, _PP, _vp, _sz, _vp, _vp]),
+    "csic_process_device_pitched": (_int, [_vp, _PP, _vp, _sz, _sz, _sz, _vp, _sz, _sz, _vp]),
     "csic_process_band": (_int, [_vp, _PP, _vp, _sz, _vp, _i32, _i32, _vp]),
     "csic_band_input_rows": (_int, [_PP, _i32, _i32, ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
     "csic_process_host": (_int, [_vp, _PP, _vp, _sz, _vp]),

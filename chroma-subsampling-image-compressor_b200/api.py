@@ -207,6 +207,11 @@ class Context:
     def process_device(self, p, d_rgb, n_frames, d_out, stream=None):
         check(_ffi.lib().csic_process_device(self._h, ctypes.byref(p), d_rgb, n_frames, d_out, stream or None))
 
+    def process_device_pitched(self, p, d_rgb, in_pitch, in_frame_stride, n_frames, d_out, out_pitch, out_frame_stride,
+                               stream=None):
+        check(_ffi.lib().csic_process_device_pitched(self._h, ctypes.byref(p), d_rgb, in_pitch, in_frame_stride, n_frames,
+                                                     d_out, out_pitch, out_frame_stride, stream or None))
+
     def process_band(self, p, d_rgb, n_frames, d_out, out_row0, out_rows, stream=None):
         check(_ffi.lib().csic_process_band(self._h, ctypes.byref(p), d_rgb, n_frames, d_out, out_row0, out_rows,
                                            stream or None))

@@ -73,8 +73,13 @@ bool can_compact(const csic_params& p) {
   return p.pool_mode == CSIC_POOL_DECIMATE && p.factor > 1 && p.height % p.factor == 0;
 }
 
+// Optional non-dense device layout: row pitches and frame strides in bytes (0 = dense).
+struct Layout {
+  size_t in_pitch = 0, in_frame = 0, out_pitch = 0, out_frame = 0;
+};
+
 int build_plan(const csic_params& p, const void* d_rgb, void* d_out, size_t n_frames, int32_t row0,
-               int32_t rows, bool compact, csic::KPlan& k) {
+               int32_t rows, bool compact, const Layout& lay, csic::KPlan& k) {
   const csic::Geometry g = csic::geometry(p);
   std::memset(&k, 0, sizeof(k));
   k.in = static_cast<const uint8_t*>(d_rgb);
@@ -88,6 +93,24 @@ int build_plan(const csic_params& p, const void* d_rgb, void* d_out, size_t n_fr
     return CSIC_EINVAL_DIMS;   // the reference's counters are far narrower; 2^31 pixels per frame is our limit
   k.in_row_bytes = (uint32_t)g.in_row_bytes;
   k.out_row_bytes = (uint32_t)g.out_row_bytes;
+  if (lay.in_pitch) {
+    if (lay.in_pitch < g.in_row_bytes || lay.in_pitch > 0xFFFFFFFFull) return CSIC_EINVAL_ARG;
+    k.in_row_bytes = (uint32_t)lay.in_pitch;
+    k.in_frame_bytes = (size_t)lay.in_pitch * (size_t)(compact ? g.out_h : p.height);
+  }
+  if (lay.in_frame) {
+    if (lay.in_frame < k.in_frame_bytes) return CSIC_EINVAL_ARG;
+    k.in_frame_bytes = lay.in_frame;
+  }
+  if (lay.out_pitch) {
+    if (lay.out_pitch < g.out_row_bytes || lay.out_pitch > 0xFFFFFFFFull) return CSIC_EINVAL_ARG;
+    k.out_row_bytes = (uint32_t)lay.out_pitch;
+    k.out_frame_bytes = (size_t)lay.out_pitch * (size_t)g.out_h;
+  }
+  if (lay.out_frame) {
+    if (lay.out_frame < k.out_frame_bytes) return CSIC_EINVAL_ARG;
+    k.out_frame_bytes = lay.out_frame;
+  }
   k.in_px_bytes = g.in_px_bytes;
   auto swap_rb = [](uint32_t c) { return (c & 0xFF00FF00u) | ((c & 0xFFu) << 16) | ((c >> 16) & 0xFFu); };
   const bool bgr = p.in_format == CSIC_IN_BGRA32;
@@ -125,14 +148,14 @@ int build_plan(const csic_params& p, const void* d_rgb, void* d_out, size_t n_fr
 }
 
 int run(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t n_frames, void* d_out, int32_t row0,
-        int32_t rows, void* cuda_stream, bool compact = false) {
+        int32_t rows, void* cuda_stream, bool compact = false, const Layout& lay = Layout()) {
   if (!ctx || !p) return CSIC_EINVAL_ARG;
   int rc = csic_validate(p, nullptr, 0);
   if (rc != CSIC_OK) return rc;
   if (n_frames == 0 || rows == 0) return CSIC_OK;
   if (!d_rgb || !d_out) return CSIC_EINVAL_ARG;
   csic::KPlan k;
-  rc = build_plan(*p, d_rgb, d_out, n_frames, row0, rows, compact, k);
+  rc = build_plan(*p, d_rgb, d_out, n_frames, row0, rows, compact, lay, k);
   if (rc != CSIC_OK) return rc;
   if (row0 < 0 || rows < 0 || row0 + rows > k.Ho) return CSIC_EINVAL_ARG;
   DeviceGuard guard(ctx->device);
@@ -293,6 +316,21 @@ int csic_process_device(csic_ctx* ctx, const csic_params* p, const void* d_rgb, 
   return run(ctx, p, d_rgb, n_frames, d_out, 0, g.out_h, cuda_stream);
 }
 
+int csic_process_device_pitched(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t in_pitch_bytes,
+                                size_t in_frame_stride, size_t n_frames, void* d_out, size_t out_pitch_bytes,
+                                size_t out_frame_stride, void* cuda_stream) {
+  if (!p) return CSIC_EINVAL_ARG;
+  int rc = csic_validate(p, nullptr, 0);
+  if (rc != CSIC_OK) return rc;
+  const csic::Geometry g = csic::geometry(*p);
+  Layout lay;
+  lay.in_pitch = in_pitch_bytes;
+  lay.in_frame = in_frame_stride;
+  lay.out_pitch = out_pitch_bytes;
+  lay.out_frame = out_frame_stride;
+  return run(ctx, p, d_rgb, n_frames, d_out, 0, g.out_h, cuda_stream, false, lay);
+}
+
 int csic_process_band(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t n_frames, void* d_out,
                       int32_t out_row0, int32_t out_rows, void* cuda_stream) {
   return run(ctx, p, d_rgb, n_frames, d_out, out_row0, out_rows, cuda_stream);
@@ -343,11 +381,37 @@ int csic_process_host(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, s
 
   // DECIMATE with f > 1 reads only every f-th row: ship only those (a strided 2-D copy), 1/f of the H2D bytes.
   const bool compact = can_compact(*p) && !ctx->opt_no_compact;
-  const size_t dev_frame_bytes = compact ? g.in_row_bytes * (size_t)g.out_h : g.in_frame_bytes;
+  const size_t rows_stored = compact ? (size_t)g.out_h : (size_t)p->height;
+  // Staging layout.  Dense when the dense layout already satisfies a TMA kernel's 16-byte rules; otherwise the
+  // rows are re-pitched on the way in and out (the copies are 2-D anyway), so odd widths also avoid the
+  // generic kernel.
+  Layout lay;
+  if (ctx->opt_family != 1) {
+    auto eligible = [&](const Layout& l) {
+      csic::KPlan probe;
+      if (build_plan(*p, reinterpret_cast<const void*>(uintptr_t(4096)), reinterpret_cast<void*>(uintptr_t(4096)), 1, 0,
+                     g.out_h, compact, l, probe) != CSIC_OK)
+        return false;
+      probe.block_threads = ctx->opt_block_threads;
+      return csic::plan_rows_kernel(probe, ctx->sm_count, ctx->max_smem_optin, ctx->opt_stages, ctx->opt_tile_bytes) ||
+             csic::plan_pool_kernel(probe, ctx->sm_count, ctx->max_smem_optin);
+    };
+    if (!eligible(Layout())) {
+      const size_t wp = ((size_t)g.out_w + 15) & ~(size_t)15;
+      Layout cand;
+      cand.in_pitch = (std::max(g.in_row_bytes, wp * (size_t)p->factor * (size_t)g.in_px_bytes) + 15) & ~(size_t)15;
+      cand.out_pitch = (std::max(g.out_row_bytes, wp * (size_t)g.out_px_bytes) + 15) & ~(size_t)15;
+      if (eligible(cand)) lay = cand;
+    }
+  }
+  const size_t in_pitch = lay.in_pitch ? lay.in_pitch : g.in_row_bytes;
+  const size_t out_pitch = lay.out_pitch ? lay.out_pitch : g.out_row_bytes;
+  const size_t dev_frame_bytes = in_pitch * rows_stored;
+  const size_t dev_out_frame_bytes = out_pitch * (size_t)g.out_h;
   // Frames per chunk: ~opt_chunk_bytes of input, at least one frame, at most what is there.
   size_t per = std::max<size_t>(1, ctx->opt_chunk_bytes / std::max<size_t>(1, dev_frame_bytes));
   per = std::min(per, n_frames);
-  rc = ensure_staging(ctx, per * dev_frame_bytes, per * g.out_frame_bytes);
+  rc = ensure_staging(ctx, per * dev_frame_bytes, per * dev_out_frame_bytes);
   if (rc != CSIC_OK) return rc;
 
   const size_t n_chunks = (n_frames + per - 1) / per;
@@ -359,23 +423,28 @@ int csic_process_host(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, s
       CSIC_CUDA(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_k[b], 0));
       CSIC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));
     }
-    if (compact) {
-      CSIC_CUDA(cudaMemcpy2DAsync(ctx->d_in[b], g.in_row_bytes, rgb + f0 * g.in_frame_bytes,
-                                  g.in_row_bytes * (size_t)p->factor, g.in_row_bytes, nf * (size_t)g.out_h,
+    if (compact || lay.in_pitch) {
+      CSIC_CUDA(cudaMemcpy2DAsync(ctx->d_in[b], in_pitch, rgb + f0 * g.in_frame_bytes,
+                                  g.in_row_bytes * (size_t)(compact ? p->factor : 1), g.in_row_bytes, nf * rows_stored,
                                   cudaMemcpyHostToDevice, ctx->s_h2d));
     } else {
       CSIC_CUDA(cudaMemcpyAsync(ctx->d_in[b], rgb + f0 * g.in_frame_bytes, nf * g.in_frame_bytes,
                                 cudaMemcpyHostToDevice, ctx->s_h2d));
     }
-    ctx->h2d_bytes += compact ? nf * dev_frame_bytes : nf * g.in_frame_bytes;
+    ctx->h2d_bytes += nf * rows_stored * g.in_row_bytes;
     CSIC_CUDA(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
     CSIC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
-    rc = run(ctx, p, ctx->d_in[b], nf, ctx->d_out[b], 0, g.out_h, ctx->stream, compact);
+    rc = run(ctx, p, ctx->d_in[b], nf, ctx->d_out[b], 0, g.out_h, ctx->stream, compact, lay);
     if (rc != CSIC_OK) return rc;
     CSIC_CUDA(cudaEventRecord(ctx->ev_k[b], ctx->stream));
     CSIC_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_k[b], 0));
-    CSIC_CUDA(cudaMemcpyAsync(out + f0 * g.out_frame_bytes, ctx->d_out[b], nf * g.out_frame_bytes,
-                              cudaMemcpyDeviceToHost, ctx->s_d2h));
+    if (lay.out_pitch) {
+      CSIC_CUDA(cudaMemcpy2DAsync(out + f0 * g.out_frame_bytes, g.out_row_bytes, ctx->d_out[b], out_pitch,
+                                  g.out_row_bytes, nf * (size_t)g.out_h, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    } else {
+      CSIC_CUDA(cudaMemcpyAsync(out + f0 * g.out_frame_bytes, ctx->d_out[b], nf * g.out_frame_bytes,
+                                cudaMemcpyDeviceToHost, ctx->s_d2h));
+    }
     CSIC_CUDA(cudaEventRecord(ctx->ev_d2h[b], ctx->s_d2h));
   }
   CSIC_CUDA(cudaStreamSynchronize(ctx->s_d2h));

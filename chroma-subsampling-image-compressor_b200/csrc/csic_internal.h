@@ -31,8 +31,10 @@ struct KPlan {
   const uint8_t* in;
   uint8_t* out;
   uint64_t in_frame_bytes, out_frame_bytes;
-  uint32_t in_row_bytes, out_row_bytes;
+  uint32_t in_row_bytes, out_row_bytes;  // row PITCHES in bytes (== dense row size unless the caller pitched the buffers)
   int32_t W, H, Wo, Ho;
+  int32_t Wp;                            // row kernel: processing width in output pixels (Wo rounded up to 16)
+  int32_t in_dense, out_dense, ragged;   // rows of a tile contiguous in memory (no pitch gap); Wp != Wo
   int32_t in_px_bytes;                   // 3 or 4
   uint32_t coef_y, coef_ncb, coef_ncr;   // dp4a coefficient words in the byte order of the input pixels
   int32_t f;

@@ -165,21 +165,29 @@ int launch_generic(const KPlan& k, void* stream) {
 // TMA-staged row kernel: planning and dispatch (the kernel itself lives in csic_rows_kernel.cu)
 // ================================================================================================
 bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_stages, uint32_t force_tile_bytes) {
-  if (k.average && k.f > 1) return false;                       // AVERAGE extension: generic kernel
-  if (k.W % k.f != 0) return false;                             // a counter line must be whole output rows
-  if (k.Wo % 16 != 0) return false;                             // 16-byte TMA granularity on the output rows
-  if (k.in_row_bytes % 16 != 0) return false;                   // ... and on the input rows (W % 16 == 0)
-  if ((reinterpret_cast<uintptr_t>(k.in) | reinterpret_cast<uintptr_t>(k.out)) & 15u) return false;
-  if ((k.in_frame_bytes | k.out_frame_bytes | k.out_row_bytes) & 15u) return false;
-  if (k.slots_per_row != k.Wo) return false;                    // BUNDLE rows with padding
-  if (k.case_b && k.Wo < 4) return false;
+  if (k.average && k.f > 1) return false;                       // AVERAGE extension: csic_pool_kernel / generic
   if (k.band_rows <= 0 || k.n_frames == 0) return false;
   if (k.block_threads <= 0) k.block_threads = kDefaultBlockThreads;
   if (k.block_threads > kMaxConsumerThreads) return false;
+  // The kernel processes Wp = Wo rounded up to 16 output pixels per row; columns >= Wo are read from / written to
+  // the row padding, so both pitches must cover Wp (dense buffers qualify when Wo % 16 == 0).
+  k.Wp = (k.Wo + 15) & ~15;
+  const bool staged0 = k.kformat <= KF_RGB888;
+  const uint32_t opx0 = staged0 ? 3u : (uint32_t)k.slot_bytes;
+  const uint64_t need_in = (uint64_t)k.Wp * (uint32_t)k.f * (uint32_t)k.in_px_bytes, need_out = (uint64_t)k.Wp * opx0;
+  if (k.in_row_bytes < need_in || k.out_row_bytes < need_out) return false;
+  if ((k.in_row_bytes | k.out_row_bytes) & 15u) return false;    // 16-byte TMA granularity of every row start
+  if ((reinterpret_cast<uintptr_t>(k.in) | reinterpret_cast<uintptr_t>(k.out)) & 15u) return false;
+  if ((k.in_frame_bytes | k.out_frame_bytes) & 15u) return false;
   if (k.case_b) {
+    // spatial before chroma: a counter line must be exactly f output rows, each starting on a sample column
+    if (k.W % k.f != 0 || k.Wo % 4 != 0) return false;
     k.caseb_row_add = (uint32_t)k.last_sample_col / (uint32_t)k.Wo;
     k.caseb_col_bytes = ((uint32_t)k.last_sample_col % (uint32_t)k.Wo) * (uint32_t)k.in_px_bytes * (uint32_t)k.f;
   }
+  k.ragged = k.Wp != k.Wo;
+  k.in_dense = k.in_row_bytes == need_in;
+  k.out_dense = k.out_row_bytes == need_out;
 
   // hold width inside a granule, in output pixels
   if (!k.case_b) k.hfe = std::max(1, k.hf / k.f);
@@ -190,15 +198,15 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
   // Tile budget: input bytes of one tile.  Staged formats also hold two output buffers per CTA.
   const uint32_t tile_budget = force_tile_bytes ? force_tile_bytes : 24u * 1024u;
   const uint32_t ipb = (uint32_t)k.in_px_bytes;
-  const uint32_t row_in = (uint32_t)k.Wo * ipb * (uint32_t)k.f;  // == in_row_bytes
+  const uint32_t row_in = (uint32_t)k.Wp * ipb * (uint32_t)k.f;  // bytes of one processed input row
   int nsplit = 0;
   const uint32_t tile_max = tile_budget + tile_budget / 3;        // a tile may overshoot the budget by a third
   for (int n = (int)((row_in + tile_max - 1) / tile_max); n <= 64; ++n) {
-    if (k.Wo % (16 * n) == 0) { nsplit = n; break; }
+    if (n >= 1 && k.Wp % (16 * n) == 0) { nsplit = n; break; }
   }
   if (nsplit == 0) return false;
   k.nsplit = nsplit;
-  k.tile_px = k.Wo / nsplit;
+  k.tile_px = k.Wp / nsplit;
   k.tile_in_bytes = (uint32_t)k.tile_px * ipb * (uint32_t)k.f;    // one row segment
   k.tile_out_bytes = (uint32_t)k.tile_px * opx;
   // Rows per tile: whole rows only (so the tile's output is contiguous), as many as fit the budget,

@@ -58,7 +58,7 @@ __device__ __forceinline__ void load_granule(uint32_t a, uint32_t (&p)[4]) {
 struct TileMeta {
   uint64_t out_base;                 // global address of the tile's first output byte
   uint32_t n_granules;               // rows * granules per row segment
-  uint32_t any_held;                 // some row of the tile replays a held chroma pair
+  uint32_t any_held_col0;            // bit 31: some row replays a held chroma pair; bits 0..30: first output column
   uint32_t held_addr[kMaxTileRows];  // per row: 0, or shared address of the RGB pixel whose chroma the row replays
 };
 static_assert(sizeof(TileMeta) == kTileMetaBytes, "kTileMetaBytes out of sync");
@@ -70,6 +70,7 @@ struct LoopConst {
   int shy, shb, shr, ly, lb;         // bundles
   uint32_t coef_y, coef_ncb, coef_ncr;       // dp4a coefficient words (byte order of the input pixels)
   uint32_t gran_per_row;
+  uint32_t out_pitch, out_dense, ragged, Wo;  // pitched / padded output rows (see KPlan)
   uint32_t nthreads;                         // consumer threads per CTA
   uint32_t row0_of_thread, rem0_of_thread;   // threadIdx.x / gran_per_row, threadIdx.x % gran_per_row
   uint32_t drow, drem;                       // blockDim.x / gran_per_row, blockDim.x % gran_per_row
@@ -93,12 +94,12 @@ __device__ __forceinline__ void tile_loop(uint32_t in_s, uint32_t out_s, uint8_t
 #pragma unroll
     for (int j = 0; j < 4; ++j) dy[j] = fwd_y16(p[j], C.coef_y);
     uint32_t haddr = 0;
-    if (HELD) {
-      haddr = meta->held_addr[row];
-      row += C.drow;
-      rem += C.drem;
-      if (rem >= C.gran_per_row) { rem -= C.gran_per_row; ++row; }
-    }
+    if (HELD) haddr = meta->held_addr[row];
+    // byte offset of this granule's output inside the tile: rows are back to back unless the output is pitched
+    const uint32_t orow = row, orem = rem;
+    row += C.drow;
+    rem += C.drem;
+    if (rem >= C.gran_per_row) { rem -= C.gran_per_row; ++row; }
     if (HELD && haddr != 0) {
       const uint32_t hp = lds8(haddr) | (lds8(haddr + 1) << 8) | (lds8(haddr + 2) << 16);
       const uint32_t hb = fwd_nc16<TRUNC>(hp, C.coef_ncb), hr = fwd_nc16<TRUNC>(hp, C.coef_ncr);
@@ -154,9 +155,16 @@ __device__ __forceinline__ void tile_loop(uint32_t in_s, uint32_t out_s, uint8_t
         for (int j = 0; j < 4; ++j)
           v[j] = ((dy[j] >> C.shy) << C.ly) | (((xb[j] ^ 0xFFFFu) >> C.shb) << C.lb) | ((xr[j] ^ 0xFFFFu) >> C.shr);
       }
-      if (FMT == KF_SLOT32) __stcs(reinterpret_cast<uint4*>(out_g) + q, make_uint4(v[0], v[1], v[2], v[3]));
-      else if (FMT == KF_SLOT16) __stcs(reinterpret_cast<uint2*>(out_g) + q, make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16)));
-      else __stcs(reinterpret_cast<uint32_t*>(out_g) + q, v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
+      if (C.ragged) {                 // padded columns (>= Wo) are the row's zero pad slots
+        const uint32_t co = (meta->any_held_col0 & 0x7FFFFFFFu) + orem * 4u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (co + j < C.Wo) ? v[j] : 0u;
+      }
+      constexpr uint32_t kG = (FMT == KF_SLOT32) ? 16u : (FMT == KF_SLOT16 ? 8u : 4u);
+      uint8_t* dst = out_g + (C.out_dense ? q * kG : orow * C.out_pitch + orem * kG);
+      if (FMT == KF_SLOT32) __stcs(reinterpret_cast<uint4*>(dst), make_uint4(v[0], v[1], v[2], v[3]));
+      else if (FMT == KF_SLOT16) __stcs(reinterpret_cast<uint2*>(dst), make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16)));
+      else __stcs(reinterpret_cast<uint32_t*>(dst), v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
     }
   }
 }
@@ -251,14 +259,14 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(con
           any |= h;
         }
       }
-      m->any_held = any;
+      m->any_held_col0 = (any ? 0x80000000u : 0u) | (seg * (uint32_t)P.tile_px);
       m->n_granules = nrows * ((uint32_t)P.tile_px >> 2);
       m->out_base = reinterpret_cast<uint64_t>(P.out) + (uint64_t)k * P.out_frame_bytes + (uint64_t)ro0 * P.out_row_bytes +
                     (uint64_t)seg * P.tile_out_bytes;
       // meta is published by the release of this arrive and observed after the consumers' acquire-wait
       mbar_expect_tx(bar, nrows * P.tile_in_bytes + n_aux * 32u);
       const uint8_t* src = frame + (uint64_t)(ro0 * (uint32_t)P.row_step) * P.in_row_bytes + (uint64_t)seg * P.tile_in_bytes;
-      if (P.row_step == 1 && P.nsplit == 1) {  // consecutive rows are contiguous in memory: one bulk copy
+      if (P.row_step == 1 && P.nsplit == 1 && P.in_dense) {  // consecutive rows are contiguous in memory: one bulk copy
         tma_load_1d(dst, src, nrows * P.tile_in_bytes, bar, pol);
       } else {
         for (uint32_t j = 0; j < nrows; ++j)
@@ -284,6 +292,7 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(con
     C.ly = P.cb_bits + P.cr_bits; C.lb = P.cr_bits;
     C.coef_y = P.coef_y; C.coef_ncb = P.coef_ncb; C.coef_ncr = P.coef_ncr;
     C.gran_per_row = (uint32_t)P.tile_px >> 2;
+    C.out_pitch = P.out_row_bytes; C.out_dense = (uint32_t)P.out_dense; C.ragged = (uint32_t)P.ragged; C.Wo = (uint32_t)P.Wo;
     C.nthreads = NC;
     C.row0_of_thread = tid / C.gran_per_row;
     C.rem0_of_thread = tid % C.gran_per_row;
@@ -302,8 +311,8 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(con
     const TileMeta* m = reinterpret_cast<const TileMeta*>(smem + P.meta_off) + s;
     uint8_t* out_g = reinterpret_cast<uint8_t*>(m->out_base);
     const uint32_t out_bytes = m->n_granules * 12u;
-    if (in4) tile_dispatch<F, FMT, Q8, TRUNC, true>(m->any_held != 0, hfe, in_s, out_s, out_g, m, C);
-    else tile_dispatch<F, FMT, Q8, TRUNC, false>(m->any_held != 0, hfe, in_s, out_s, out_g, m, C);
+    if (in4) tile_dispatch<F, FMT, Q8, TRUNC, true>((m->any_held_col0 >> 31) != 0, hfe, in_s, out_s, out_g, m, C);
+    else tile_dispatch<F, FMT, Q8, TRUNC, false>((m->any_held_col0 >> 31) != 0, hfe, in_s, out_s, out_g, m, C);
 
     if (kStaged) {
       // Hand the tile to the TMA engine.  Generic-proxy writes must be fenced before the async proxy
@@ -314,7 +323,13 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(con
       if (tid == 0) tma_store_wait_read0();
       consumer_barrier(NC);
       if (tid == 0) {
-        tma_store_1d(out_g, out_s, out_bytes, pol);
+        if (P.out_dense) {
+          tma_store_1d(out_g, out_s, out_bytes, pol);
+        } else {                       // pitched output rows: one bulk store per row of the tile
+          const uint32_t nrows = out_bytes / P.tile_out_bytes;
+          for (uint32_t j = 0; j < nrows; ++j)
+            tma_store_1d(out_g + (uint64_t)j * P.out_row_bytes, out_s + j * P.tile_out_bytes, P.tile_out_bytes, pol);
+        }
         tma_store_commit();
       }
     }

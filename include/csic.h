@@ -163,6 +163,15 @@ CSIC_API int csic_destroy(csic_ctx* ctx);
 CSIC_API int csic_process_device(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t n_frames,
                         void* d_out, void* cuda_stream);
 
+/* Same, for pitched buffers (cudaMallocPitch-style): rows start every *_pitch_bytes, frames every *_frame_stride
+ * bytes (0 = dense).  When both pitches are multiples of 16 and cover the width rounded up to 16 output pixels
+ * (in: that many x factor x bytes-per-pixel; out: that many x 3 or slot bytes) ANY frame width takes the TMA row
+ * kernel; columns beyond the frame are read from / written into the row padding.  Dense buffers take it when
+ * ceil(W/f) % 16 == 0 and the input row size is a multiple of 16 bytes; everything else runs the generic kernel. */
+CSIC_API int csic_process_device_pitched(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t in_pitch_bytes,
+                                         size_t in_frame_stride, size_t n_frames, void* d_out, size_t out_pitch_bytes,
+                                         size_t out_frame_stride, void* cuda_stream);
+
 /* Row-band shard of ONE frame layout: processes output rows [out_row0, out_row0+out_rows) of every
  * frame, reading d_rgb / writing d_out at their whole-frame offsets (so bands of one frame may be
  * issued on different streams, or -- with per-GPU copies of the rows a band needs -- on different
@@ -176,7 +185,8 @@ CSIC_API int csic_band_input_rows(const csic_params* p, int32_t out_row0, int32_
  * context's streams, synchronous on return.  This is the call a Scala `processImage` replacement
  * makes (ImageCompressorTopApp.scala:23-145 minus PNG I/O).  rgb/out may be pageable or pinned.
  * With DECIMATE and f > 1 (and H % f == 0) only the input rows the pipeline reads -- every f-th -- are
- * copied to the device (strided 2-D copy); the result is identical. */
+ * copied to the device (strided 2-D copy); the result is identical.  Widths that break the TMA kernels' 16-byte
+ * rules are re-pitched in the staging buffers, so they avoid the generic kernel too. */
 CSIC_API int csic_process_host(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, size_t n_frames,
                       uint8_t* out);
 

@@ -352,3 +352,40 @@ def test_four_byte_input_formats(csic, ctx, in_format):
         assert np.array_equal(out4, oracle.process(po4, rgba)), (W, H, f, ab, order, fmt)
         assert np.array_equal(out4, ctx.process_host(p3, np.ascontiguousarray(rgba[..., sel])))
     assert seen == {1, 2}
+
+
+def test_pitched_layout_any_width(csic, ctx):
+    """csic_process_device_pitched: with 16-byte-multiple pitches covering the width rounded up to 16 output
+    pixels, ANY width runs the TMA row kernel (columns past the frame live in the row padding); result == oracle.
+    Also: csic_process_host re-pitches odd widths by itself."""
+    import torch
+    fams = set()
+    for (W, H), f, ab, order, (fmt, q), inf in itertools.product(
+            [(1000, 12), (37, 9), (5, 3), (130, 8), (250, 16)], (1, 2, 4), [(4, 4), (2, 0), (1, 1)], ("CSQ", "SQC"),
+            [(0, (8, 8, 8)), (1, (6, 5, 5)), (2, (3, 3, 2)), (3, (6, 5, 5)), (3, (8, 8, 8))], (0, 1)):
+        ipb = 3 if inf == 0 else 4
+        n = 2
+        rgb = np.random.default_rng(W * 3 + f).integers(0, 256, size=(n, H, W, ipb), dtype=np.uint8)
+        p, po = both_params(csic, W, H, ab[0], ab[1], q, f, order, 0, 0, fmt, inf)
+        want = oracle.process(po, rgb)
+        ow, oh, orb, ofb = csic.out_shape(p)
+        wp = (ow + 15) // 16 * 16
+        opx = 3 if fmt < 2 else (1 if sum(q) <= 8 else (2 if sum(q) <= 16 else 4))
+        in_pitch = (max(W * ipb, wp * f * ipb) + 15) // 16 * 16 + 32          # extra slack: any 16-multiple works
+        out_pitch = (max(orb, wp * opx) + 15) // 16 * 16 + 16
+        d_in = torch.full((n, H, in_pitch), 0x5A, dtype=torch.uint8, device="cuda")
+        d_in[:, :, :W * ipb] = torch.from_numpy(rgb.reshape(n, H, W * ipb)).cuda()
+        d_out = torch.full((n, oh, out_pitch), 0xA5, dtype=torch.uint8, device="cuda")
+        ctx.process_device_pitched(p, d_in.data_ptr(), in_pitch, 0, n, d_out.data_ptr(), out_pitch, 0,
+                                   torch.cuda.current_stream().cuda_stream or 1)
+        torch.cuda.synchronize()
+        fams.add(ctx.last_kernel()[0])
+        got = d_out[:, :, :orb].contiguous().view(n, ofb).cpu().numpy()
+        assert np.array_equal(got, want), (W, H, f, ab, order, fmt, q, inf, ctx.last_kernel()[0])
+        # host path: re-pitched staging must give the same bytes
+        assert np.array_equal(ctx.process_host(p, rgb), want)
+    assert 2 in fams
+    # a width no dense layout could serve takes the row kernel through the host path
+    p, po = both_params(csic, 1000, 16, 2, 0, (8, 8, 8), 4, "CSQ", 0, 0, 0)
+    rgb = synth_frames(2, 16, 1000, seed=4)
+    assert np.array_equal(ctx.process_host(p, rgb), oracle.process(po, rgb)) and ctx.last_kernel()[0] == 2
