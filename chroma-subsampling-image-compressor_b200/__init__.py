@@ -4,7 +4,7 @@ Product code.  It never imports `oracle/` (CPU restatement = test infrastructure
 compute path: importing works anywhere (parameter validation is host-only), processing needs a B200.
 """
 from . import _ffi
-from .api import (ChromaSubsamplingMode, Context, CsicError, IllegalArgumentException, InFormat, OutFormat, PinnedBuffer,
+from .api import (ChromaSubsamplingMode, Context, CsicError, IllegalArgumentException, InFormat, MultiContext, OutFormat, PinnedBuffer,
                   PoolMode, ProcessingStep, QuantizationMode, RoundMode, band_input_rows, device_count, make_params,
                   out_shape, params_from_legacy, parse_processing_step, validate)
 from .model import (ImageCompressorTop, ImageProcessor, ImageProcessorModel, ImageProcessorParams, default_context)

@@ -44,6 +44,11 @@ PROTOTYPES = {
     "csic_process_band": (_int, [_vp, _PP, _vp, _sz, _vp, _i32, _i32, _vp]),
     "csic_band_input_rows": (_int, [_PP, _i32, _i32, ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
     "csic_process_host": (_int, [_vp, _PP, _vp, _sz, _vp]),
+    "csic_process_host_band": (_int, [_vp, _PP, _vp, _sz, _vp, _i32, _i32]),
+    "csic_multi_create": (_int, [ctypes.POINTER(_int), _int, ctypes.POINTER(_vp)]),
+    "csic_multi_destroy": (_int, [_vp]),
+    "csic_multi_size": (_int, [_vp]),
+    "csic_multi_process_host": (_int, [_vp, _PP, _vp, _sz, _vp]),
     "csic_host_alloc": (_int, [_sz, ctypes.POINTER(_vp)]),
     "csic_host_free": (_int, [_vp]),
     "csic_synchronize": (_int, [_vp]),

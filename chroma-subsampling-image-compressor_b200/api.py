@@ -232,6 +232,16 @@ class Context:
         check(_ffi.lib().csic_process_host(self._h, ctypes.byref(p), rgb.ctypes.data, n, out.ctypes.data))
         return out
 
+    def process_host_band(self, p, rgb, out, out_row0, out_rows):
+        """Whole frames in host arrays; computes output rows [out_row0, out_row0+out_rows) of every frame in place
+        in `out` ([n, bytes_per_frame]); other rows of `out` are left untouched."""
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        n = rgb.shape[0]
+        assert out.dtype == np.uint8 and out.flags.c_contiguous and out.size == n * out_shape(p)[3]
+        check(_ffi.lib().csic_process_host_band(self._h, ctypes.byref(p), rgb.ctypes.data, n, out.ctypes.data,
+                                                out_row0, out_rows))
+        return out
+
     # -- torch CUDA tensors (plumbing only: torch owns the memory and the stream)
     def process_torch(self, p, rgb, out=None, out_row0=None, out_rows=None):
         import torch
@@ -247,4 +257,48 @@ class Context:
             self.process_device(p, rgb.data_ptr(), n, out.data_ptr(), stream)
         else:
             self.process_band(p, rgb.data_ptr(), n, out.data_ptr(), out_row0, out_rows, stream)
+        return out
+
+
+class MultiContext:
+    """`csic_multi`: one process driving several GPUs (frames split across them, or row bands of each frame when
+    there are fewer frames than GPUs)."""
+
+    def __init__(self, devices=None):
+        self._h = ctypes.c_void_p()
+        if devices is None:
+            check(_ffi.lib().csic_multi_create(None, 0, ctypes.byref(self._h)))
+        else:
+            arr = (ctypes.c_int * len(devices))(*devices)
+            check(_ffi.lib().csic_multi_create(arr, len(devices), ctypes.byref(self._h)))
+
+    def __len__(self):
+        return _ffi.lib().csic_multi_size(self._h)
+
+    def close(self):
+        if self._h:
+            _ffi.lib().csic_multi_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def process_host(self, p, rgb, out=None):
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        if rgb.ndim == 3:
+            rgb = rgb[None]
+        n = rgb.shape[0]
+        fb = out_shape(p)[3]
+        if out is None:
+            out = np.empty((n, fb), dtype=np.uint8)
+        check(_ffi.lib().csic_multi_process_host(self._h, ctypes.byref(p), rgb.ctypes.data, n, out.ctypes.data))
         return out

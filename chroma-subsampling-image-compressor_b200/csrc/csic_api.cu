@@ -7,6 +7,8 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "csic_internal.h"
 
@@ -76,6 +78,7 @@ bool can_compact(const csic_params& p) {
 // Optional non-dense device layout: row pitches and frame strides in bytes (0 = dense).
 struct Layout {
   size_t in_pitch = 0, in_frame = 0, out_pitch = 0, out_frame = 0;
+  bool short_frames = false;   // the buffers hold only one row band of each frame (host band path)
 };
 
 int build_plan(const csic_params& p, const void* d_rgb, void* d_out, size_t n_frames, int32_t row0,
@@ -99,7 +102,7 @@ int build_plan(const csic_params& p, const void* d_rgb, void* d_out, size_t n_fr
     k.in_frame_bytes = (size_t)lay.in_pitch * (size_t)(compact ? g.out_h : p.height);
   }
   if (lay.in_frame) {
-    if (lay.in_frame < k.in_frame_bytes) return CSIC_EINVAL_ARG;
+    if (lay.in_frame < k.in_frame_bytes && !lay.short_frames) return CSIC_EINVAL_ARG;
     k.in_frame_bytes = lay.in_frame;
   }
   if (lay.out_pitch) {
@@ -108,7 +111,7 @@ int build_plan(const csic_params& p, const void* d_rgb, void* d_out, size_t n_fr
     k.out_frame_bytes = (size_t)lay.out_pitch * (size_t)g.out_h;
   }
   if (lay.out_frame) {
-    if (lay.out_frame < k.out_frame_bytes) return CSIC_EINVAL_ARG;
+    if (lay.out_frame < k.out_frame_bytes && !lay.short_frames) return CSIC_EINVAL_ARG;
     k.out_frame_bytes = lay.out_frame;
   }
   k.in_px_bytes = g.in_px_bytes;
@@ -370,18 +373,27 @@ int csic_band_input_rows(const csic_params* p, int32_t out_row0, int32_t out_row
   return CSIC_OK;
 }
 
-int csic_process_host(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, size_t n_frames, uint8_t* out) {
-  if (!ctx || !p) return CSIC_EINVAL_ARG;
-  int rc = csic_validate(p, nullptr, 0);
-  if (rc != CSIC_OK) return rc;
-  if (n_frames == 0) return CSIC_OK;
-  if (!rgb || !out) return CSIC_EINVAL_ARG;
+// Host buffers in, host buffers out, for output rows [row0, row0+rows) of every frame (the whole frame or one
+// row band).  Frames are cut into chunks that flow through a kPipe-deep ring of device buffers on three streams.
+// Only what the band needs crosses PCIe: its input rows (every f-th one under DECIMATE) and its output rows; the
+// device buffers hold just those rows and the kernel is handed *virtual* frame bases (buffer - first_row * pitch).
+static int host_pipeline(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, size_t n_frames, uint8_t* out,
+                         int32_t row0, int32_t rows) {
   const csic::Geometry g = csic::geometry(*p);
   DeviceGuard guard(ctx->device);
+  const bool band = !(row0 == 0 && rows == g.out_h);
 
   // DECIMATE with f > 1 reads only every f-th row: ship only those (a strided 2-D copy), 1/f of the H2D bytes.
   const bool compact = can_compact(*p) && !ctx->opt_no_compact;
-  const size_t rows_stored = compact ? (size_t)g.out_h : (size_t)p->height;
+  int32_t in_row0 = 0, in_rows = p->height;
+  if (band) {
+    int rc = csic_band_input_rows(p, row0, rows, &in_row0, &in_rows);
+    if (rc != CSIC_OK) return rc;
+  }
+  // rows kept on the device, in stored-row units (a stored row is an input row, or every f-th one when compact)
+  const size_t first_stored = compact ? (size_t)(in_row0 / p->factor) : (size_t)in_row0;
+  const size_t rows_stored = compact ? (size_t)(row0 + rows) - first_stored : (size_t)in_rows;
+
   // Staging layout.  Dense when the dense layout already satisfies a TMA kernel's 16-byte rules; otherwise the
   // rows are re-pitched on the way in and out (the copies are 2-D anyway), so odd widths also avoid the
   // generic kernel.
@@ -407,11 +419,19 @@ int csic_process_host(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, s
   const size_t in_pitch = lay.in_pitch ? lay.in_pitch : g.in_row_bytes;
   const size_t out_pitch = lay.out_pitch ? lay.out_pitch : g.out_row_bytes;
   const size_t dev_frame_bytes = in_pitch * rows_stored;
-  const size_t dev_out_frame_bytes = out_pitch * (size_t)g.out_h;
+  const size_t dev_out_frame_bytes = out_pitch * (size_t)rows;
+  const size_t host_row_step = g.in_row_bytes * (size_t)(compact ? p->factor : 1);
+  if (band) {   // the device holds only the band's rows: frames are dev_*_frame_bytes apart
+    lay.in_pitch = in_pitch;
+    lay.out_pitch = out_pitch;
+    lay.in_frame = dev_frame_bytes;
+    lay.out_frame = dev_out_frame_bytes;
+    lay.short_frames = true;
+  }
   // Frames per chunk: ~opt_chunk_bytes of input, at least one frame, at most what is there.
   size_t per = std::max<size_t>(1, ctx->opt_chunk_bytes / std::max<size_t>(1, dev_frame_bytes));
   per = std::min(per, n_frames);
-  rc = ensure_staging(ctx, per * dev_frame_bytes, per * dev_out_frame_bytes);
+  int rc = ensure_staging(ctx, per * dev_frame_bytes, per * dev_out_frame_bytes);
   if (rc != CSIC_OK) return rc;
 
   const size_t n_chunks = (n_frames + per - 1) / per;
@@ -423,33 +443,148 @@ int csic_process_host(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, s
       CSIC_CUDA(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_k[b], 0));
       CSIC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));
     }
-    if (compact || lay.in_pitch) {
-      CSIC_CUDA(cudaMemcpy2DAsync(ctx->d_in[b], in_pitch, rgb + f0 * g.in_frame_bytes,
-                                  g.in_row_bytes * (size_t)(compact ? p->factor : 1), g.in_row_bytes, nf * rows_stored,
-                                  cudaMemcpyHostToDevice, ctx->s_h2d));
+    uint8_t* d_in = static_cast<uint8_t*>(ctx->d_in[b]);
+    uint8_t* d_out = static_cast<uint8_t*>(ctx->d_out[b]);
+    if (band) {
+      // one strided copy per frame: rows [first_stored, first_stored + rows_stored) of that frame
+      for (size_t k = 0; k < nf; ++k)
+        CSIC_CUDA(cudaMemcpy2DAsync(d_in + k * dev_frame_bytes, in_pitch,
+                                    rgb + (f0 + k) * g.in_frame_bytes + first_stored * host_row_step, host_row_step,
+                                    g.in_row_bytes, rows_stored, cudaMemcpyHostToDevice, ctx->s_h2d));
+    } else if (compact || lay.in_pitch) {
+      CSIC_CUDA(cudaMemcpy2DAsync(d_in, in_pitch, rgb + f0 * g.in_frame_bytes, host_row_step, g.in_row_bytes,
+                                  nf * rows_stored, cudaMemcpyHostToDevice, ctx->s_h2d));
     } else {
-      CSIC_CUDA(cudaMemcpyAsync(ctx->d_in[b], rgb + f0 * g.in_frame_bytes, nf * g.in_frame_bytes,
-                                cudaMemcpyHostToDevice, ctx->s_h2d));
+      CSIC_CUDA(cudaMemcpyAsync(d_in, rgb + f0 * g.in_frame_bytes, nf * g.in_frame_bytes, cudaMemcpyHostToDevice,
+                                ctx->s_h2d));
     }
     ctx->h2d_bytes += nf * rows_stored * g.in_row_bytes;
     CSIC_CUDA(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
     CSIC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
-    rc = run(ctx, p, ctx->d_in[b], nf, ctx->d_out[b], 0, g.out_h, ctx->stream, compact, lay);
+    // virtual frame bases: row r of the frame sits at base + r * pitch; only the band's rows are ever touched
+    rc = run(ctx, p, d_in - first_stored * in_pitch, nf, d_out - (size_t)row0 * out_pitch, row0, rows, ctx->stream,
+             compact, lay);
     if (rc != CSIC_OK) return rc;
     CSIC_CUDA(cudaEventRecord(ctx->ev_k[b], ctx->stream));
     CSIC_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_k[b], 0));
-    if (lay.out_pitch) {
-      CSIC_CUDA(cudaMemcpy2DAsync(out + f0 * g.out_frame_bytes, g.out_row_bytes, ctx->d_out[b], out_pitch,
-                                  g.out_row_bytes, nf * (size_t)g.out_h, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    if (band) {
+      for (size_t k = 0; k < nf; ++k)
+        CSIC_CUDA(cudaMemcpy2DAsync(out + (f0 + k) * g.out_frame_bytes + (size_t)row0 * g.out_row_bytes, g.out_row_bytes,
+                                    d_out + k * dev_out_frame_bytes, out_pitch, g.out_row_bytes, (size_t)rows,
+                                    cudaMemcpyDeviceToHost, ctx->s_d2h));
+    } else if (lay.out_pitch) {
+      CSIC_CUDA(cudaMemcpy2DAsync(out + f0 * g.out_frame_bytes, g.out_row_bytes, d_out, out_pitch, g.out_row_bytes,
+                                  nf * (size_t)g.out_h, cudaMemcpyDeviceToHost, ctx->s_d2h));
     } else {
-      CSIC_CUDA(cudaMemcpyAsync(out + f0 * g.out_frame_bytes, ctx->d_out[b], nf * g.out_frame_bytes,
-                                cudaMemcpyDeviceToHost, ctx->s_d2h));
+      CSIC_CUDA(cudaMemcpyAsync(out + f0 * g.out_frame_bytes, d_out, nf * g.out_frame_bytes, cudaMemcpyDeviceToHost,
+                                ctx->s_d2h));
     }
     CSIC_CUDA(cudaEventRecord(ctx->ev_d2h[b], ctx->s_d2h));
   }
   CSIC_CUDA(cudaStreamSynchronize(ctx->s_d2h));
   CSIC_CUDA(cudaStreamSynchronize(ctx->stream));
   CSIC_CUDA(cudaStreamSynchronize(ctx->s_h2d));
+  return CSIC_OK;
+}
+
+int csic_process_host(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, size_t n_frames, uint8_t* out) {
+  if (!ctx || !p) return CSIC_EINVAL_ARG;
+  int rc = csic_validate(p, nullptr, 0);
+  if (rc != CSIC_OK) return rc;
+  if (n_frames == 0) return CSIC_OK;
+  if (!rgb || !out) return CSIC_EINVAL_ARG;
+  return host_pipeline(ctx, p, rgb, n_frames, out, 0, csic::geometry(*p).out_h);
+}
+
+int csic_process_host_band(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, size_t n_frames, uint8_t* out,
+                           int32_t out_row0, int32_t out_rows) {
+  if (!ctx || !p) return CSIC_EINVAL_ARG;
+  int rc = csic_validate(p, nullptr, 0);
+  if (rc != CSIC_OK) return rc;
+  if (n_frames == 0 || out_rows == 0) return CSIC_OK;
+  if (!rgb || !out) return CSIC_EINVAL_ARG;
+  if (out_row0 < 0 || out_rows < 0 || out_row0 + out_rows > csic::geometry(*p).out_h) return CSIC_EINVAL_ARG;
+  return host_pipeline(ctx, p, rgb, n_frames, out, out_row0, out_rows);
+}
+
+// ---- one process, several GPUs ------------------------------------------------------------------
+// The reference's host is one JVM process.  csic_multi owns one context per GPU and one host thread per
+// context; a batch is split by frames (E1) -- or, when there are fewer frames than GPUs, every frame is cut into
+// aligned row bands (E2).  No data moves between GPUs.
+struct csic_multi {
+  std::vector<csic_ctx*> ctx;
+};
+
+int csic_multi_create(const int* devices, int n_devices, csic_multi** out) {
+  if (!out) return CSIC_EINVAL_ARG;
+  *out = nullptr;
+  const int avail = csic_device_count();
+  if (avail <= 0) return CSIC_ENODEVICE;
+  if (n_devices <= 0) { n_devices = avail; devices = nullptr; }
+  csic_multi* m = new (std::nothrow) csic_multi();
+  if (!m) return CSIC_ENOMEM;
+  for (int i = 0; i < n_devices; ++i) {
+    csic_ctx* c = nullptr;
+    int rc = csic_create(devices ? devices[i] : i, &c);
+    if (rc != CSIC_OK) {
+      for (csic_ctx* x : m->ctx) csic_destroy(x);
+      delete m;
+      return rc;
+    }
+    m->ctx.push_back(c);
+  }
+  *out = m;
+  return CSIC_OK;
+}
+
+int csic_multi_destroy(csic_multi* m) {
+  if (!m) return CSIC_OK;
+  for (csic_ctx* c : m->ctx) csic_destroy(c);
+  delete m;
+  return CSIC_OK;
+}
+
+int csic_multi_size(const csic_multi* m) { return m ? (int)m->ctx.size() : CSIC_EINVAL_ARG; }
+
+int csic_multi_process_host(csic_multi* m, const csic_params* p, const uint8_t* rgb, size_t n_frames, uint8_t* out) {
+  if (!m || !p) return CSIC_EINVAL_ARG;
+  int rc = csic_validate(p, nullptr, 0);
+  if (rc != CSIC_OK) return rc;
+  if (n_frames == 0) return CSIC_OK;
+  if (!rgb || !out) return CSIC_EINVAL_ARG;
+  const csic::Geometry g = csic::geometry(*p);
+  const size_t G = m->ctx.size();
+  std::vector<int> rcs(G, CSIC_OK);
+  std::vector<std::string> errs(G);
+  std::vector<std::thread> th;
+  if (n_frames >= G) {
+    for (size_t i = 0; i < G; ++i) {
+      const size_t lo = n_frames * i / G, hi = n_frames * (i + 1) / G;
+      th.emplace_back([=, &rcs, &errs] {
+        rcs[i] = csic_process_host(m->ctx[i], p, rgb + lo * g.in_frame_bytes, hi - lo, out + lo * g.out_frame_bytes);
+        if (rcs[i] != CSIC_OK) errs[i] = g_last_error;
+      });
+    }
+  } else {
+    // fewer frames than GPUs: aligned row bands of every frame (zero halo)
+    const bool case_b = !g.chroma_first && p->factor > 1;
+    const int unit = case_b ? p->factor * g.vf : std::max(1, (p->factor % g.vf == 0 ? p->factor : p->factor * g.vf) / p->factor);
+    const int units = (g.out_h + unit - 1) / unit;
+    for (size_t i = 0; i < G; ++i) {
+      const int r0 = std::min(g.out_h, (int)(units * i / G) * unit), r1 = std::min(g.out_h, (int)(units * (i + 1) / G) * unit);
+      if (r1 <= r0) continue;
+      th.emplace_back([=, &rcs, &errs] {
+        rcs[i] = csic_process_host_band(m->ctx[i], p, rgb, n_frames, out, r0, r1 - r0);
+        if (rcs[i] != CSIC_OK) errs[i] = g_last_error;
+      });
+    }
+  }
+  for (std::thread& t : th) t.join();
+  for (size_t i = 0; i < G; ++i)
+    if (rcs[i] != CSIC_OK) {
+      g_last_error = errs[i];
+      return rcs[i];
+    }
   return CSIC_OK;
 }
 

@@ -190,6 +190,22 @@ CSIC_API int csic_band_input_rows(const csic_params* p, int32_t out_row0, int32_
 CSIC_API int csic_process_host(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, size_t n_frames,
                       uint8_t* out);
 
+/* Row band of every frame, host buffers (whole frames on the host): only the band's input rows go to the device
+ * and only its output rows come back.  Lets several GPUs share ONE frame with no exchange. */
+CSIC_API int csic_process_host_band(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, size_t n_frames,
+                                    uint8_t* out, int32_t out_row0, int32_t out_rows);
+
+/* One host process, several GPUs (the reference's host is a single JVM process): one context and one host thread
+ * per device.  devices == NULL or n_devices <= 0 -> every visible GPU.  csic_multi_process_host splits the batch
+ * by frames, or -- with fewer frames than GPUs -- cuts every frame into aligned row bands; no collective, no
+ * peer traffic. */
+typedef struct csic_multi csic_multi;
+CSIC_API int csic_multi_create(const int* devices, int n_devices, csic_multi** out);
+CSIC_API int csic_multi_destroy(csic_multi* m);
+CSIC_API int csic_multi_size(const csic_multi* m);
+CSIC_API int csic_multi_process_host(csic_multi* m, const csic_params* p, const uint8_t* rgb, size_t n_frames,
+                                     uint8_t* out);
+
 /* Pinned host memory helpers for callers that want the fast H2D/D2H path. */
 CSIC_API int csic_host_alloc(size_t bytes, void** out);
 CSIC_API int csic_host_free(void* p);

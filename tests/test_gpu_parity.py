@@ -389,3 +389,37 @@ def test_pitched_layout_any_width(csic, ctx):
     p, po = both_params(csic, 1000, 16, 2, 0, (8, 8, 8), 4, "CSQ", 0, 0, 0)
     rgb = synth_frames(2, 16, 1000, seed=4)
     assert np.array_equal(ctx.process_host(p, rgb), oracle.process(po, rgb)) and ctx.last_kernel()[0] == 2
+
+
+def test_host_band_and_multi_context(csic, ctx):
+    """csic_process_host_band moves only a band's rows across PCIe and writes only its output rows;
+    csic_multi (one process, several contexts -- here three on the same GPU) splits by frames, or by aligned
+    row bands when there are fewer frames than contexts.  All equal the oracle."""
+    rng = np.random.default_rng(77)
+    multi = csic.MultiContext([0, 0, 0])
+    assert len(multi) == 3
+    for (W, H), f, ab, order, (fmt, q), pool in itertools.product(
+            [(128, 48), (250, 36), (64, 64)], (1, 2, 4), [(2, 0), (4, 4), (1, 0)], ("CSQ", "SQC"),
+            [(0, (8, 8, 8)), (3, (6, 5, 5)), (1, (3, 3, 2))], (0, 1)):
+        if pool and (W % f or H % f):
+            continue
+        n = 2
+        rgb = rng.integers(0, 256, size=(n, H, W, 3), dtype=np.uint8)
+        p, po = both_params(csic, W, H, ab[0], ab[1], q, f, order, 0, pool, fmt)
+        want = oracle.process(po, rgb)
+        _, oh, _, fb = csic.out_shape(p)
+        rb = fb // oh
+        # arbitrary (unaligned) bands tile the frame; rows outside a band stay untouched
+        out = np.full((n, fb), 0xA5, np.uint8)
+        cuts = sorted(set([0, oh] + [int(v) for v in rng.integers(1, oh, size=3)]))
+        for r0, r1 in zip(cuts[:-1], cuts[1:]):
+            before = out.copy()
+            ctx.process_host_band(p, rgb, out, r0, r1 - r0)
+            o3, b3 = out.reshape(n, oh, rb), before.reshape(n, oh, rb)
+            assert np.array_equal(o3[:, :r0], b3[:, :r0]) and np.array_equal(o3[:, r1:], b3[:, r1:])
+        assert np.array_equal(out, want), (W, H, f, ab, order, fmt, pool)
+        # fewer frames than contexts -> row bands; more -> frame shards
+        assert np.array_equal(multi.process_host(p, rgb), want)
+        rgb7 = np.concatenate([rgb] * 4)[:7]
+        assert np.array_equal(multi.process_host(p, rgb7), np.concatenate([want] * 4)[:7])
+    multi.close()
