@@ -44,6 +44,8 @@ WORKLOADS = {
              "BASELINE configs[1] batched: 512x512 x4096 frames, 4:2:2 + f=2, YCC888"),
     "cfg2x1": (512, 512, 1, 2, 2, (8, 8, 8), 2, "CSQ", 0,
                "BASELINE configs[1]: ONE 512x512 frame, 4:2:2 + f=2, YCC888 (launch-latency bound)"),
+    "cfg3p": (1920, 1080, 256, 2, 0, (4, 4, 4), 1, "CSQ", 4,
+              "cfg3 geometry with PLANAR 4:2:0 output (Y plane + quarter-size Cb/Cr planes, 1.5 B/px out)"),
     "cfg4avg": (3840, 2160, 1024, 2, 0, (8, 8, 8), 2, "CSQ", 3,
                 "AVERAGE-pooling extension on the cfg4 geometry: 4:2:0 + 2x2 mean + BUNDLE128 (reads every row)"),
     "cfg5avg": (7680, 4320, 64, 2, 0, (6, 5, 5), 4, "CSQ", 1,
@@ -172,7 +174,7 @@ def config_dict(name, wl, frames_per_gpu, note=None):
     W, H, _, a, b, q, f, order, fmt, desc = wl
     c = {"workload": f"{name}: {desc}", "width": W, "height": H, "frames_per_gpu": frames_per_gpu,
          "chroma": f"4:{a}:{b}", "quant_bits": list(q), "factor": f, "order": order,
-         "out_format": ["YCC888", "RGB888", "BUNDLE64", "BUNDLE128"][fmt], "round_mode": "FLOOR",
+         "out_format": ["YCC888", "RGB888", "BUNDLE64", "BUNDLE128", "PLANAR"][fmt], "round_mode": "FLOOR",
          "pool_mode": "AVERAGE (extension)" if name.endswith("avg") else "DECIMATE", "in_format": "RGB24", "sharding": "frames split across ranks, no collective",
          "l2": "inputs (>=1 GB per step) far larger than the 126 MB L2; no flush needed"}
     if note:

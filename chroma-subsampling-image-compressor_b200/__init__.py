@@ -6,7 +6,7 @@ compute path: importing works anywhere (parameter validation is host-only), proc
 from . import _ffi
 from .api import (ChromaSubsamplingMode, Context, CsicError, IllegalArgumentException, InFormat, MultiContext, OutFormat, PinnedBuffer,
                   PoolMode, ProcessingStep, QuantizationMode, RoundMode, band_input_rows, device_count, make_params,
-                  out_shape, params_from_legacy, parse_processing_step, validate)
+                  out_shape, planar_shape, params_from_legacy, parse_processing_step, validate)
 from .model import (ImageCompressorTop, ImageProcessor, ImageProcessorModel, ImageProcessorParams, default_context)
 from .sharding import band_plan, frame_shard
 

@@ -33,6 +33,7 @@ PROTOTYPES = {
     "csic_params_from_legacy": (_int, [_i32, _i32, _i32, _i32, _i32, _PP]),
     "csic_validate": (_int, [_PP, ctypes.c_char_p, _sz]),
     "csic_out_shape": (_int, [_PP, ctypes.POINTER(_i32), ctypes.POINTER(_i32), ctypes.POINTER(_sz), ctypes.POINTER(_sz)]),
+    "csic_planar_shape": (_int, [_PP, ctypes.POINTER(_i32), ctypes.POINTER(_i32), ctypes.POINTER(_sz), ctypes.POINTER(_sz)]),
     "csic_parse_step": (_int, [_cp]),
     "csic_strerror": (_cp, [_int]),
     "csic_last_error": (_cp, []),
@@ -41,6 +42,7 @@ PROTOTYPES = {
     "csic_destroy": (_int, [_vp]),
     "csic_process_device": (_int, [_vp, _PP, _vp, _sz, _vp, _vp]),
     "csic_process_device_pitched": (_int, [_vp, _PP, _vp, _sz, _sz, _sz, _vp, _sz, _sz, _vp]),
+    "csic_expand_planar_device": (_int, [_vp, _PP, _vp, _sz, _vp, _i32, _vp]),
     "csic_process_band": (_int, [_vp, _PP, _vp, _sz, _vp, _i32, _i32, _vp]),
     "csic_band_input_rows": (_int, [_PP, _i32, _i32, ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
     "csic_process_host": (_int, [_vp, _PP, _vp, _sz, _vp]),

@@ -56,6 +56,7 @@ class OutFormat(enum.IntEnum):
     RGB888 = 1
     BUNDLE64 = 2
     BUNDLE128 = 3
+    PLANAR = 4
 
 
 class ChromaSubsamplingMode(enum.IntEnum):
@@ -128,6 +129,14 @@ def out_shape(p):
     rb, fb = ctypes.c_size_t(), ctypes.c_size_t()
     check(_ffi.lib().csic_out_shape(ctypes.byref(p), ctypes.byref(w), ctypes.byref(h), ctypes.byref(rb), ctypes.byref(fb)))
     return w.value, h.value, rb.value, fb.value
+
+
+def planar_shape(p):
+    """(chroma_w, chroma_h, cb_offset, cr_offset) of the PLANAR output format."""
+    w, h = ctypes.c_int32(), ctypes.c_int32()
+    ob, orr = ctypes.c_size_t(), ctypes.c_size_t()
+    check(_ffi.lib().csic_planar_shape(ctypes.byref(p), ctypes.byref(w), ctypes.byref(h), ctypes.byref(ob), ctypes.byref(orr)))
+    return w.value, h.value, ob.value, orr.value
 
 
 def band_input_rows(p, out_row0, out_rows):
@@ -230,6 +239,18 @@ class Context:
             out = np.empty((n, fb), dtype=np.uint8)
         assert out.dtype == np.uint8 and out.flags.c_contiguous and out.size == n * fb
         check(_ffi.lib().csic_process_host(self._h, ctypes.byref(p), rgb.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def expand_planar_torch(self, p, planar, to_rgb=False):
+        """Decoder of OutFormat.PLANAR on the device: torch uint8 [n, bytes_per_frame] -> [n, out_h, out_w, 3]."""
+        import torch
+        assert planar.is_cuda and planar.dtype == torch.uint8 and planar.is_contiguous()
+        w, h, _, fb = out_shape(p)
+        n = planar.numel() // fb
+        out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=planar.device)
+        stream = torch.cuda.current_stream(planar.device).cuda_stream or 1
+        check(_ffi.lib().csic_expand_planar_device(self._h, ctypes.byref(p), planar.data_ptr(), n, out.data_ptr(),
+                                                   1 if to_rgb else 0, stream))
         return out
 
     def process_host_band(self, p, rgb, out, out_row0, out_rows):

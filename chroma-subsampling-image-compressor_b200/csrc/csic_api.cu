@@ -105,6 +105,8 @@ int build_plan(const csic_params& p, const void* d_rgb, void* d_out, size_t n_fr
     if (lay.in_frame < k.in_frame_bytes && !lay.short_frames) return CSIC_EINVAL_ARG;
     k.in_frame_bytes = lay.in_frame;
   }
+  if ((lay.out_pitch || lay.out_frame || lay.short_frames) && p.out_format == CSIC_OUT_PLANAR)
+    return CSIC_EINVAL_MODE;   // three planes per frame: no pitched / banded host layout
   if (lay.out_pitch) {
     if (lay.out_pitch < g.out_row_bytes || lay.out_pitch > 0xFFFFFFFFull) return CSIC_EINVAL_ARG;
     k.out_row_bytes = (uint32_t)lay.out_pitch;
@@ -134,9 +136,14 @@ int build_plan(const csic_params& p, const void* d_rgb, void* d_out, size_t n_fr
   k.average = (p.pool_mode == CSIC_POOL_AVERAGE && p.factor > 1) ? 1 : 0;
   if (p.out_format == CSIC_OUT_YCC888) k.kformat = csic::KF_YCC888;
   else if (p.out_format == CSIC_OUT_RGB888) k.kformat = csic::KF_RGB888;
+  else if (p.out_format == CSIC_OUT_PLANAR) k.kformat = csic::KF_PLANAR;
   else k.kformat = g.out_px_bytes == 1 ? csic::KF_SLOT8 : (g.out_px_bytes == 2 ? csic::KF_SLOT16 : csic::KF_SLOT32);
   k.slot_bytes = g.out_px_bytes;
-  k.slots_per_row = k.kformat <= csic::KF_RGB888 ? g.out_w : (int32_t)(g.out_row_bytes / (size_t)g.out_px_bytes);
+  k.slots_per_row = (k.kformat <= csic::KF_RGB888 || k.kformat == csic::KF_PLANAR)
+                        ? g.out_w : (int32_t)(g.out_row_bytes / (size_t)g.out_px_bytes);
+  k.planar_hs = g.planar_hs; k.planar_vs = g.planar_vs; k.planar_cw = g.planar_cw; k.planar_ch = g.planar_ch;
+  k.planar_cb_off = (uint64_t)g.out_w * (uint64_t)g.out_h;
+  k.planar_cr_off = k.planar_cb_off + (uint64_t)g.planar_cw * (uint64_t)g.planar_ch;
   k.sy = 8 - p.y_bits;
   k.scb = 8 - p.cb_bits;
   k.scr = 8 - p.cr_bits;
@@ -334,6 +341,28 @@ int csic_process_device_pitched(csic_ctx* ctx, const csic_params* p, const void*
   return run(ctx, p, d_rgb, n_frames, d_out, 0, g.out_h, cuda_stream, false, lay);
 }
 
+int csic_expand_planar_device(csic_ctx* ctx, const csic_params* p, const void* d_planar, size_t n_frames, void* d_out,
+                              int32_t expand_format, void* cuda_stream) {
+  if (!ctx || !p) return CSIC_EINVAL_ARG;
+  int rc = csic_validate(p, nullptr, 0);
+  if (rc != CSIC_OK) return rc;
+  if (p->out_format != CSIC_OUT_PLANAR || (expand_format != CSIC_OUT_YCC888 && expand_format != CSIC_OUT_RGB888))
+    return CSIC_EINVAL_MODE;
+  if (n_frames == 0) return CSIC_OK;
+  if (!d_planar || !d_out) return CSIC_EINVAL_ARG;
+  const csic::Geometry g = csic::geometry(*p);
+  csic::KPlan k;
+  rc = build_plan(*p, d_planar, d_out, n_frames, 0, g.out_h, false, Layout(), k);
+  if (rc != CSIC_OK) return rc;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+  int err = csic::launch_expand_planar(k, static_cast<const uint8_t*>(d_planar), static_cast<uint8_t*>(d_out),
+                                       expand_format == CSIC_OUT_RGB888, st);
+  ctx->launches += 1;
+  if (err != (int)cudaSuccess) return cuda_fail((cudaError_t)err, "expand kernel launch");
+  return CSIC_OK;
+}
+
 int csic_process_band(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t n_frames, void* d_out,
                       int32_t out_row0, int32_t out_rows, void* cuda_stream) {
   return run(ctx, p, d_rgb, n_frames, d_out, out_row0, out_rows, cuda_stream);
@@ -408,7 +437,7 @@ static int host_pipeline(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb
       return csic::plan_rows_kernel(probe, ctx->sm_count, ctx->max_smem_optin, ctx->opt_stages, ctx->opt_tile_bytes) ||
              csic::plan_pool_kernel(probe, ctx->sm_count, ctx->max_smem_optin);
     };
-    if (!eligible(Layout())) {
+    if (!eligible(Layout()) && p->out_format != CSIC_OUT_PLANAR) {
       const size_t wp = ((size_t)g.out_w + 15) & ~(size_t)15;
       Layout cand;
       cand.in_pitch = (std::max(g.in_row_bytes, wp * (size_t)p->factor * (size_t)g.in_px_bytes) + 15) & ~(size_t)15;
@@ -419,7 +448,8 @@ static int host_pipeline(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb
   const size_t in_pitch = lay.in_pitch ? lay.in_pitch : g.in_row_bytes;
   const size_t out_pitch = lay.out_pitch ? lay.out_pitch : g.out_row_bytes;
   const size_t dev_frame_bytes = in_pitch * rows_stored;
-  const size_t dev_out_frame_bytes = out_pitch * (size_t)rows;
+  if (band && p->out_format == CSIC_OUT_PLANAR) return CSIC_EINVAL_MODE;   // planes are not row bands
+  const size_t dev_out_frame_bytes = band ? out_pitch * (size_t)rows : std::max(out_pitch * (size_t)rows, g.out_frame_bytes);
   const size_t host_row_step = g.in_row_bytes * (size_t)(compact ? p->factor : 1);
   if (band) {   // the device holds only the band's rows: frames are dev_*_frame_bytes apart
     lay.in_pitch = in_pitch;
@@ -557,9 +587,10 @@ int csic_multi_process_host(csic_multi* m, const csic_params* p, const uint8_t* 
   std::vector<int> rcs(G, CSIC_OK);
   std::vector<std::string> errs(G);
   std::vector<std::thread> th;
-  if (n_frames >= G) {
+  if (n_frames >= G || p->out_format == CSIC_OUT_PLANAR) {
     for (size_t i = 0; i < G; ++i) {
       const size_t lo = n_frames * i / G, hi = n_frames * (i + 1) / G;
+      if (hi == lo) continue;
       th.emplace_back([=, &rcs, &errs] {
         rcs[i] = csic_process_host(m->ctx[i], p, rgb + lo * g.in_frame_bytes, hi - lo, out + lo * g.out_frame_bytes);
         if (rcs[i] != CSIC_OK) errs[i] = g_last_error;

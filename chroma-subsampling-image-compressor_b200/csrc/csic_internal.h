@@ -18,13 +18,14 @@ struct Geometry {
   bool chroma_first;         // ChromaSubsampling precedes SpatialSampling in op1..op3
   bool quant_first;          // ColorQuantization precedes SpatialSampling (only matters for AVERAGE)
   int32_t hf, vf;            // ChromaSubsampler.scala:26-27
+  int32_t planar_hs, planar_vs, planar_cw, planar_ch;   // CSIC_OUT_PLANAR chroma decimation / plane size
 };
 
 int slot_bits(const csic_params& p);
 Geometry geometry(const csic_params& p);
 
 // Kernel-side output format after resolving the bundle slot width.
-enum KFormat : int32_t { KF_YCC888 = 0, KF_RGB888 = 1, KF_SLOT8 = 2, KF_SLOT16 = 3, KF_SLOT32 = 4 };
+enum KFormat : int32_t { KF_YCC888 = 0, KF_RGB888 = 1, KF_SLOT8 = 2, KF_SLOT16 = 3, KF_SLOT32 = 4, KF_PLANAR = 5 };
 
 // Everything a kernel needs, passed by value (lives in the constant bank).
 struct KPlan {
@@ -43,6 +44,8 @@ struct KPlan {
   uint32_t caseb_row_add, caseb_col_bytes; // case B: held pixel = decimated-stream element (line-1)*W + last_sample_col
   int32_t quant_first, trunc, average;
   int32_t kformat, slot_bytes, slots_per_row;
+  int32_t planar_hs, planar_vs, planar_cw, planar_ch;   // PLANAR: chroma decimation (output px) and plane size
+  uint64_t planar_cb_off, planar_cr_off;                 // byte offsets of the Cb / Cr planes inside an output frame
   int32_t sy, scb, scr;                  // 8 - target bits
   int32_t cb_bits, cr_bits;
   int32_t row0, band_rows;               // output rows [row0, row0 + band_rows) of every frame
@@ -74,6 +77,7 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
 
 // Both return a cudaError_t as int.
 int launch_generic(const KPlan& k, void* stream);
+int launch_expand_planar(const KPlan& k, const uint8_t* planar, uint8_t* out, int to_rgb, void* stream);
 int launch_rows(const KPlan& k, int sm_count, int force_ctas_per_sm, void* stream);
 constexpr int kDefaultBlockThreads = 256;   // consumer threads; one producer warp is added at launch
 constexpr int kMaxConsumerThreads = 512;
@@ -89,7 +93,7 @@ template <int F> int pool_set_attributes_factor(size_t max_smem_optin);
 template <int F> int launch_rows_factor(const KPlan& k, unsigned grid, void* stream);
 template <int F> int rows_set_attributes_factor(size_t max_smem_optin);
 constexpr int kMaxTileRows = 16;        // rows per tile of the row kernel
-constexpr uint32_t kTileMetaBytes = 16 + 4 * kMaxTileRows;   // sizeof(TileMeta) in csic_rows_kernel.cu
+constexpr uint32_t kTileMetaBytes = 32 + 4 * kMaxTileRows;   // sizeof(TileMeta) in csic_rows_kernel.cu
 
 }  // namespace csic
 

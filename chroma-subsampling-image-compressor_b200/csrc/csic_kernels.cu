@@ -138,6 +138,14 @@ __global__ void __launch_bounds__(256) csic_generic_kernel(const __grid_constant
     if (P.kformat == KF_YCC888) {
       uint8_t* o = orow + (size_t)co * 3;
       o[0] = (uint8_t)y; o[1] = (uint8_t)cb; o[2] = (uint8_t)cr;
+    } else if (P.kformat == KF_PLANAR) {
+      orow[co] = (uint8_t)y;                        // Y plane; out_row_bytes == Wo
+      if (ro % P.planar_vs == 0 && co % P.planar_hs == 0) {   // a surviving chroma sample point
+        uint8_t* fo = P.out + k * P.out_frame_bytes;
+        const size_t ci = (size_t)(ro / P.planar_vs) * (size_t)P.planar_cw + (size_t)(co / P.planar_hs);
+        fo[P.planar_cb_off + ci] = (uint8_t)cb;
+        fo[P.planar_cr_off + ci] = (uint8_t)cr;
+      }
     } else if (P.kformat == KF_RGB888) {
       const uint32_t v = inverse_rgb(y, cb, cr);
       uint8_t* o = orow + (size_t)co * 3;
@@ -150,6 +158,41 @@ __global__ void __launch_bounds__(256) csic_generic_kernel(const __grid_constant
       else reinterpret_cast<uint32_t*>(orow)[co] = v;
     }
   }
+}
+
+// Decoder of the PLANAR format: one thread per output pixel, chroma fetched with the reference's replay rule
+// (ChromaSubsampler.scala:52-65) expressed in output coordinates (chroma before spatial, or f == 1).
+__global__ void __launch_bounds__(256) csic_expand_planar_kernel(const __grid_constant__ KPlan P, const uint8_t* __restrict__ planar,
+                                                                 uint8_t* __restrict__ out, int to_rgb) {
+  const uint64_t total = (uint64_t)P.n_frames * (uint64_t)P.Ho * (uint64_t)P.Wo;
+  const int last_o = P.last_sample_col / P.f;        // last sample column of a line, in output pixels
+  for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (uint64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(idx % (uint32_t)P.Wo);
+    const uint64_t t = idx / (uint32_t)P.Wo;
+    const int ro = (int)(t % (uint32_t)P.Ho);
+    const uint64_t k = t / (uint32_t)P.Ho;
+    const uint8_t* f = planar + k * P.out_frame_bytes;
+    const bool held = P.vf == 2 && ((ro * P.f) & 1);   // only possible for f == 1
+    const int sr = (held ? ro - 1 : ro) / P.planar_vs;
+    const int sc = (held ? last_o : co - co % P.planar_hs) / P.planar_hs;
+    const size_t ci = (size_t)sr * (size_t)P.planar_cw + (size_t)sc;
+    const int y = f[(size_t)ro * P.Wo + co], cb = f[P.planar_cb_off + ci], cr = f[P.planar_cr_off + ci];
+    uint8_t* o = out + (k * (uint64_t)P.Ho * P.Wo + (uint64_t)ro * P.Wo + co) * 3;
+    if (to_rgb) {
+      const uint32_t v = inverse_rgb(y, cb, cr);
+      o[0] = (uint8_t)v; o[1] = (uint8_t)(v >> 8); o[2] = (uint8_t)(v >> 16);
+    } else {
+      o[0] = (uint8_t)y; o[1] = (uint8_t)cb; o[2] = (uint8_t)cr;
+    }
+  }
+}
+
+int launch_expand_planar(const KPlan& k, const uint8_t* planar, uint8_t* out, int to_rgb, void* stream) {
+  const uint64_t total = (uint64_t)k.n_frames * (uint64_t)k.Ho * (uint64_t)k.Wo;
+  if (total == 0) return (int)cudaSuccess;
+  const uint64_t blocks = std::min<uint64_t>((total + 255) / 256, (uint64_t)148 * 64);
+  csic_expand_planar_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(k, planar, out, to_rgb);
+  return (int)cudaGetLastError();
 }
 
 int launch_generic(const KPlan& k, void* stream) {
@@ -172,8 +215,9 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
   // The kernel processes Wp = Wo rounded up to 16 output pixels per row; columns >= Wo are read from / written to
   // the row padding, so both pitches must cover Wp (dense buffers qualify when Wo % 16 == 0).
   k.Wp = (k.Wo + 15) & ~15;
-  const bool staged0 = k.kformat <= KF_RGB888;
-  const uint32_t opx0 = staged0 ? 3u : (uint32_t)k.slot_bytes;
+  const bool planar = k.kformat == KF_PLANAR;
+  const bool staged0 = k.kformat <= KF_RGB888 || planar;
+  const uint32_t opx0 = planar ? 1u : (staged0 ? 3u : (uint32_t)k.slot_bytes);
   const uint64_t need_in = (uint64_t)k.Wp * (uint32_t)k.f * (uint32_t)k.in_px_bytes, need_out = (uint64_t)k.Wp * opx0;
   if (k.in_row_bytes < need_in || k.out_row_bytes < need_out) return false;
   if ((k.in_row_bytes | k.out_row_bytes) & 15u) return false;    // 16-byte TMA granularity of every row start
@@ -188,13 +232,16 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
   k.ragged = k.Wp != k.Wo;
   k.in_dense = k.in_row_bytes == need_in;
   k.out_dense = k.out_row_bytes == need_out;
+  // PLANAR: three dense planes; chroma rows (Wo / hs bytes) must be 16-byte multiples too; bands start on a
+  // chroma row
+  if (planar && (k.ragged || !k.out_dense || k.Wo % (16 * k.planar_hs) != 0 || k.row0 % k.planar_vs != 0)) return false;
 
   // hold width inside a granule, in output pixels
   if (!k.case_b) k.hfe = std::max(1, k.hf / k.f);
   else k.hfe = k.hf;
 
-  const bool staged = k.kformat <= KF_RGB888;
-  const uint32_t opx = staged ? 3u : (uint32_t)k.slot_bytes;
+  const bool staged = k.kformat <= KF_RGB888 || planar;
+  const uint32_t opx = planar ? 1u : (staged ? 3u : (uint32_t)k.slot_bytes);
   // Tile budget: input bytes of one tile.  Staged formats also hold two output buffers per CTA.
   const uint32_t tile_budget = force_tile_bytes ? force_tile_bytes : 24u * 1024u;
   const uint32_t ipb = (uint32_t)k.in_px_bytes;
@@ -202,7 +249,7 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
   int nsplit = 0;
   const uint32_t tile_max = tile_budget + tile_budget / 3;        // a tile may overshoot the budget by a third
   for (int n = (int)((row_in + tile_max - 1) / tile_max); n <= 64; ++n) {
-    if (n >= 1 && k.Wp % (16 * n) == 0) { nsplit = n; break; }
+    if (n >= 1 && k.Wp % (16 * (planar ? k.planar_hs : 1) * n) == 0) { nsplit = n; break; }
   }
   if (nsplit == 0) return false;
   k.nsplit = nsplit;
@@ -221,6 +268,8 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
     rows = std::min(rows, k.band_rows);
     auto tiles_for = [&](int r) { return (uint64_t)k.n_frames * (uint64_t)((k.band_rows + r - 1) / r); };
     while (rows > 1 && tiles_for(rows) < (uint64_t)sm_count * 4u) rows = (rows + 1) / 2;
+    if (planar && rows > 1) rows &= ~(k.planar_vs - 1);          // tiles start on a chroma row
+    if (rows < 1) rows = 1;
   }
   k.tile_rows = rows;
   k.tiles_per_band = (uint32_t)((k.band_rows + rows - 1) / rows);
@@ -231,6 +280,9 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
   auto up128 = [](uint32_t v) { return (v + 127u) & ~127u; };
   k.stage_stride = up128((uint32_t)rows * (k.tile_in_bytes + 32u));
   k.out_buf_stride = staged ? up128((uint32_t)rows * k.tile_out_bytes) : 0u;
+  if (planar)   // [Y rows][Cb rows][Cr rows]
+    k.out_buf_stride = up128((uint32_t)rows * (uint32_t)k.tile_px +
+                             2u * (uint32_t)((rows + k.planar_vs - 1) / k.planar_vs) * ((uint32_t)k.tile_px / (uint32_t)k.planar_hs));
   // Ring depth and residency, fitted to B200 sweeps (profiles/r1/exp_ctas_v4.txt): the kernel is fastest with
   // about four ~24 KB tiles in flight per SM -- 2 resident CTAs x 2 stages (cfg4 0.996 of the measured copy peak
   // vs 0.953 with 4 CTAs; cfg2 0.97 vs 0.94 with 6 tiles in flight).  Only when a tile carries little compute

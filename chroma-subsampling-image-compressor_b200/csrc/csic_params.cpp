@@ -1,6 +1,7 @@
 // Host-only half of the C ABI: parameter construction, validation, geometry, names.
 // Mirrors the reference's constructor `require(...)` predicates and their message texts
 // (citations relative to the reference root, src/main/scala/jpeg/).  No CUDA in this file.
+#include <algorithm>
 #include <cctype>
 #include <cstdio>
 #include <cstring>
@@ -122,8 +123,8 @@ int csic_validate(const csic_params* p, char* msg, size_t n) {
     return fail(CSIC_EINVAL_MODE, msg, n, "round_mode must be 0 (FLOOR) or 1 (TRUNC)");
   if (p->pool_mode != CSIC_POOL_DECIMATE && p->pool_mode != CSIC_POOL_AVERAGE)
     return fail(CSIC_EINVAL_MODE, msg, n, "pool_mode must be 0 (DECIMATE) or 1 (AVERAGE)");
-  if (p->out_format < CSIC_OUT_YCC888 || p->out_format > CSIC_OUT_BUNDLE128)
-    return fail(CSIC_EINVAL_MODE, msg, n, "out_format must be 0..3");
+  if (p->out_format < CSIC_OUT_YCC888 || p->out_format > CSIC_OUT_PLANAR)
+    return fail(CSIC_EINVAL_MODE, msg, n, "out_format must be 0..4");
   if (p->in_format < CSIC_IN_RGB24 || p->in_format > CSIC_IN_BGRA32)
     return fail(CSIC_EINVAL_MODE, msg, n, "in_format must be 0 (RGB24), 1 (RGBA32) or 2 (BGRA32)");
   if (p->reserved != 0) return fail(CSIC_EINVAL_MODE, msg, n, "reserved field must be 0");
@@ -131,7 +132,29 @@ int csic_validate(const csic_params* p, char* msg, size_t n) {
   if (p->pool_mode == CSIC_POOL_AVERAGE && (p->width % p->factor != 0 || p->height % p->factor != 0))
     return fail(CSIC_EINVAL_DIVISIBLE, msg, n,
                 "Image dimensions must be divisible by spatial downsampling factor.");
+  if (p->out_format == CSIC_OUT_PLANAR) {
+    int ic = 0, is = 0;
+    for (int i = 0; i < 3; ++i) {
+      if (p->op[i] == CSIC_STEP_CHROMA) ic = i;
+      if (p->op[i] == CSIC_STEP_SPATIAL) is = i;
+    }
+    if (p->pool_mode != CSIC_POOL_DECIMATE || (p->factor > 1 && ic > is))
+      return fail(CSIC_EINVAL_MODE, msg, n,
+                  "PLANAR output needs ChromaSubsampling before SpatialSampling (or factor 1) and DECIMATE");
+  }
   if (msg && n) msg[0] = '\0';
+  return CSIC_OK;
+}
+
+int csic_planar_shape(const csic_params* p, int32_t* chroma_w, int32_t* chroma_h, size_t* cb_offset, size_t* cr_offset) {
+  int rc = csic_validate(p, nullptr, 0);
+  if (rc != CSIC_OK) return rc;
+  if (p->out_format != CSIC_OUT_PLANAR) return CSIC_EINVAL_MODE;
+  const csic::Geometry g = csic::geometry(*p);
+  if (chroma_w) *chroma_w = g.planar_cw;
+  if (chroma_h) *chroma_h = g.planar_ch;
+  if (cb_offset) *cb_offset = (size_t)g.out_w * (size_t)g.out_h;
+  if (cr_offset) *cr_offset = (size_t)g.out_w * (size_t)g.out_h + (size_t)g.planar_cw * (size_t)g.planar_ch;
   return CSIC_OK;
 }
 
@@ -143,7 +166,7 @@ int csic_out_shape(const csic_params* p, int32_t* out_w, int32_t* out_h, size_t*
   if (out_w) *out_w = g.out_w;
   if (out_h) *out_h = g.out_h;
   if (out_row_bytes) *out_row_bytes = g.out_row_bytes;
-  if (out_bytes_per_frame) *out_bytes_per_frame = g.out_row_bytes * (size_t)g.out_h;
+  if (out_bytes_per_frame) *out_bytes_per_frame = g.out_frame_bytes;
   return CSIC_OK;
 }
 
@@ -199,11 +222,22 @@ Geometry geometry(const csic_params& p) {
     g.out_px_bytes = slot_bits(p) / 8;
     const size_t bytes = (size_t)g.out_w * g.out_px_bytes;
     g.out_row_bytes = (bytes + word - 1) / word * word;
+  } else if (p.out_format == CSIC_OUT_PLANAR) {
+    g.out_px_bytes = 1;
+    g.out_row_bytes = (size_t)g.out_w;            // a row of the Y plane
   } else {
     g.out_px_bytes = 3;
     g.out_row_bytes = (size_t)g.out_w * 3;
   }
   g.out_frame_bytes = g.out_row_bytes * (size_t)g.out_h;
+  {
+    const int hf = 4 / p.chroma_a, vf = (p.chroma_b == 0) ? 2 : 1;
+    g.planar_hs = std::max(1, hf / f);
+    g.planar_vs = std::max(1, vf / f);
+    g.planar_cw = (g.out_w + g.planar_hs - 1) / g.planar_hs;
+    g.planar_ch = (g.out_h + g.planar_vs - 1) / g.planar_vs;
+    if (p.out_format == CSIC_OUT_PLANAR) g.out_frame_bytes += 2 * (size_t)g.planar_cw * (size_t)g.planar_ch;
+  }
   int ic = -1, is = -1, iq = -1;
   for (int i = 0; i < 3; ++i) {
     if (p.op[i] == CSIC_STEP_CHROMA) ic = i;

@@ -29,7 +29,7 @@ namespace csic {
 struct PoolMeta {
   uint64_t out_base;
   uint32_t n_granules;
-  uint32_t pad;
+  uint32_t pad[5];
   uint32_t held_addr[kMaxTileRows];   // index j * (F/2) + dr/2: shared address of the pixel an odd line replays
 };
 static_assert(sizeof(PoolMeta) == kTileMetaBytes, "kTileMetaBytes out of sync");

@@ -59,6 +59,7 @@ struct TileMeta {
   uint64_t out_base;                 // global address of the tile's first output byte
   uint32_t n_granules;               // rows * granules per row segment
   uint32_t any_held_col0;            // bit 31: some row replays a held chroma pair; bits 0..30: first output column
+  uint64_t cb_base, cr_base;         // PLANAR: global address of the tile's first Cb / Cr row (bits 24.. of n_granules: #rows)
   uint32_t held_addr[kMaxTileRows];  // per row: 0, or shared address of the RGB pixel whose chroma the row replays
 };
 static_assert(sizeof(TileMeta) == kTileMetaBytes, "kTileMetaBytes out of sync");
@@ -71,6 +72,7 @@ struct LoopConst {
   uint32_t coef_y, coef_ncb, coef_ncr;       // dp4a coefficient words (byte order of the input pixels)
   uint32_t gran_per_row;
   uint32_t out_pitch, out_dense, ragged, Wo;  // pitched / padded output rows (see KPlan)
+  uint32_t pl_cb_off, pl_cr_off, pl_crow_bytes, pl_vs_shift;   // PLANAR staging: region offsets, bytes per chroma row
   uint32_t nthreads;                         // consumer threads per CTA
   uint32_t row0_of_thread, rem0_of_thread;   // threadIdx.x / gran_per_row, threadIdx.x % gran_per_row
   uint32_t drow, drem;                       // blockDim.x / gran_per_row, blockDim.x % gran_per_row
@@ -85,7 +87,7 @@ struct LoopConst {
 template <int F, int FMT, int HFE, bool HELD, bool Q8, bool TRUNC, bool IN4>
 __device__ __forceinline__ void tile_loop(uint32_t in_s, uint32_t out_s, uint8_t* __restrict__ out_g,
                                           const TileMeta* __restrict__ meta, const LoopConst& C) {
-  const uint32_t n = meta->n_granules;
+  const uint32_t n = meta->n_granules & 0x00FFFFFFu;
   uint32_t row = C.row0_of_thread, rem = C.rem0_of_thread;   // row of granule q, tracked without a division
   for (uint32_t q = threadIdx.x; q < n; q += C.nthreads) {
     uint32_t p[4];
@@ -119,7 +121,30 @@ __device__ __forceinline__ void tile_loop(uint32_t in_s, uint32_t out_s, uint8_t
       }
     }
 
-    if (FMT == KF_YCC888) {
+    if (FMT == KF_PLANAR) {
+      // Y plane: four Y bytes per granule.  Chroma planes: only sampled lines contribute, 4/HFE samples each.
+      const uint32_t my4 = C.my * 0x01010101u, mb4 = C.mcb * 0x01010101u, mr4 = C.mcr * 0x01010101u;
+      const uint32_t yw = __byte_perm(__byte_perm(dy[0], dy[1], 0x0051), __byte_perm(dy[2], dy[3], 0x0051), 0x5410) & my4;
+      sts32(out_s + q * 4u, yw);
+      if (!(HELD && haddr != 0)) {
+        const uint32_t crow = (orow >> C.pl_vs_shift) * C.pl_crow_bytes;
+        if (HFE == 1) {
+          const uint32_t bw = ~__byte_perm(__byte_perm(xb[0], xb[1], 0x0051), __byte_perm(xb[2], xb[3], 0x0051), 0x5410) & mb4;
+          const uint32_t rw = ~__byte_perm(__byte_perm(xr[0], xr[1], 0x0051), __byte_perm(xr[2], xr[3], 0x0051), 0x5410) & mr4;
+          sts32(out_s + C.pl_cb_off + crow + orem * 4u, bw);
+          sts32(out_s + C.pl_cr_off + crow + orem * 4u, rw);
+        } else if (HFE == 2) {
+          const uint32_t bw = ~__byte_perm(xb[0], xb[2], 0x0051) & mb4 & 0xFFFFu;
+          const uint32_t rw = ~__byte_perm(xr[0], xr[2], 0x0051) & mr4 & 0xFFFFu;
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(out_s + C.pl_cb_off + crow + orem * 2u), "h"((unsigned short)bw) : "memory");
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(out_s + C.pl_cr_off + crow + orem * 2u), "h"((unsigned short)rw) : "memory");
+        } else {
+          const uint32_t bw = (~(xb[0] >> 8)) & C.mcb, rw = (~(xr[0] >> 8)) & C.mcr;
+          asm volatile("st.shared.u8 [%0], %1;" ::"r"(out_s + C.pl_cb_off + crow + orem), "r"(bw) : "memory");
+          asm volatile("st.shared.u8 [%0], %1;" ::"r"(out_s + C.pl_cr_off + crow + orem), "r"(rw) : "memory");
+        }
+      }
+    } else if (FMT == KF_YCC888) {
       // byte 1 of dy is Y, byte 1 of xb/xr is ~Cb/~Cr: gather with PRMT, flip and quantise per word.
       uint32_t t, u;
       t = __byte_perm(dy[0], xb[0], 0x0051); u = __byte_perm(xr[0], dy[1], 0x0051);
@@ -187,7 +212,7 @@ __device__ __forceinline__ void tile_dispatch(bool held, int hfe, uint32_t in_s,
 template <int F, int FMT, bool Q8, bool TRUNC>
 __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(const __grid_constant__ KPlan P) {
   extern __shared__ __align__(128) uint8_t smem[];
-  constexpr bool kStaged = (FMT == KF_YCC888 || FMT == KF_RGB888);   // output leaves through smem + TMA store
+  constexpr bool kStaged = (FMT == KF_YCC888 || FMT == KF_RGB888 || FMT == KF_PLANAR);   // output leaves through smem + TMA store
   const uint32_t tid = threadIdx.x;
   const uint32_t NC = blockDim.x - 32u;        // consumer threads; the last warp is the producer
   const uint32_t sbase = smem_u32(smem);
@@ -263,6 +288,16 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(con
       m->n_granules = nrows * ((uint32_t)P.tile_px >> 2);
       m->out_base = reinterpret_cast<uint64_t>(P.out) + (uint64_t)k * P.out_frame_bytes + (uint64_t)ro0 * P.out_row_bytes +
                     (uint64_t)seg * P.tile_out_bytes;
+      if (FMT == KF_PLANAR) {
+        // chroma rows of this tile: output rows with (ro % vs == 0); tiles of more than one row start on one
+        const uint32_t vs = (uint32_t)P.planar_vs, hs = (uint32_t)P.planar_hs;
+        const uint32_t nrc = (ro0 % vs == 0) ? (nrows + vs - 1) / vs : 0u;
+        const uint64_t coff = (uint64_t)(ro0 / vs) * (uint32_t)P.planar_cw + (uint64_t)seg * ((uint32_t)P.tile_px / hs);
+        const uint64_t fbase = reinterpret_cast<uint64_t>(P.out) + (uint64_t)k * P.out_frame_bytes;
+        m->cb_base = fbase + P.planar_cb_off + coff;
+        m->cr_base = fbase + P.planar_cr_off + coff;
+        m->n_granules |= nrc << 24;
+      }
       // meta is published by the release of this arrive and observed after the consumers' acquire-wait
       mbar_expect_tx(bar, nrows * P.tile_in_bytes + n_aux * 32u);
       const uint8_t* src = frame + (uint64_t)(ro0 * (uint32_t)P.row_step) * P.in_row_bytes + (uint64_t)seg * P.tile_in_bytes;
@@ -293,6 +328,10 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(con
     C.coef_y = P.coef_y; C.coef_ncb = P.coef_ncb; C.coef_ncr = P.coef_ncr;
     C.gran_per_row = (uint32_t)P.tile_px >> 2;
     C.out_pitch = P.out_row_bytes; C.out_dense = (uint32_t)P.out_dense; C.ragged = (uint32_t)P.ragged; C.Wo = (uint32_t)P.Wo;
+    C.pl_cb_off = (uint32_t)P.tile_rows * (uint32_t)P.tile_px;
+    C.pl_crow_bytes = (uint32_t)P.tile_px / (uint32_t)max(1, P.planar_hs);
+    C.pl_cr_off = C.pl_cb_off + (uint32_t)((P.tile_rows + P.planar_vs - 1) / max(1, P.planar_vs)) * C.pl_crow_bytes;
+    C.pl_vs_shift = P.planar_vs == 2 ? 1u : 0u;
     C.nthreads = NC;
     C.row0_of_thread = tid / C.gran_per_row;
     C.rem0_of_thread = tid % C.gran_per_row;
@@ -310,7 +349,9 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(con
     const uint32_t out_s = sbase + P.out_buf_off + (i & 1u) * P.out_buf_stride;
     const TileMeta* m = reinterpret_cast<const TileMeta*>(smem + P.meta_off) + s;
     uint8_t* out_g = reinterpret_cast<uint8_t*>(m->out_base);
-    const uint32_t out_bytes = m->n_granules * 12u;
+    const uint32_t ngr = m->n_granules & 0x00FFFFFFu, nrc = m->n_granules >> 24;
+    const uint32_t out_bytes = ngr * (FMT == KF_PLANAR ? 4u : 12u);
+    const uint64_t cb_g = m->cb_base, cr_g = m->cr_base;
     if (in4) tile_dispatch<F, FMT, Q8, TRUNC, true>((m->any_held_col0 >> 31) != 0, hfe, in_s, out_s, out_g, m, C);
     else tile_dispatch<F, FMT, Q8, TRUNC, false>((m->any_held_col0 >> 31) != 0, hfe, in_s, out_s, out_g, m, C);
 
@@ -323,7 +364,13 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(con
       if (tid == 0) tma_store_wait_read0();
       consumer_barrier(NC);
       if (tid == 0) {
-        if (P.out_dense) {
+        if (FMT == KF_PLANAR) {
+          tma_store_1d(out_g, out_s, out_bytes, pol);
+          if (nrc) {
+            tma_store_1d(reinterpret_cast<void*>(cb_g), out_s + C.pl_cb_off, nrc * C.pl_crow_bytes, pol);
+            tma_store_1d(reinterpret_cast<void*>(cr_g), out_s + C.pl_cr_off, nrc * C.pl_crow_bytes, pol);
+          }
+        } else if (P.out_dense) {
           tma_store_1d(out_g, out_s, out_bytes, pol);
         } else {                       // pitched output rows: one bulk store per row of the tile
           const uint32_t nrows = out_bytes / P.tile_out_bytes;
@@ -369,6 +416,7 @@ int launch_rows_factor<CSIC_ROWS_F>(const KPlan& k, unsigned grid, void* stream)
     case KF_RGB888: return launch_fmt<KF_RGB888>(k, grid, st);
     case KF_SLOT8: return launch_fmt<KF_SLOT8>(k, grid, st);
     case KF_SLOT16: return launch_fmt<KF_SLOT16>(k, grid, st);
+    case KF_PLANAR: return launch_fmt<KF_PLANAR>(k, grid, st);
     default: return launch_fmt<KF_SLOT32>(k, grid, st);
   }
 }
@@ -380,7 +428,7 @@ int rows_set_attributes_factor<CSIC_ROWS_F>(size_t b) {
   if ((e = attr_one<FMT, Q8, false>(b)) != cudaSuccess) return (int)e;       \
   if ((e = attr_one<FMT, Q8, true>(b)) != cudaSuccess) return (int)e;
   CSIC_ATTR(KF_YCC888, false) CSIC_ATTR(KF_RGB888, false) CSIC_ATTR(KF_SLOT8, false) CSIC_ATTR(KF_SLOT16, false)
-  CSIC_ATTR(KF_SLOT32, false) CSIC_ATTR(KF_SLOT32, true)
+  CSIC_ATTR(KF_SLOT32, false) CSIC_ATTR(KF_SLOT32, true) CSIC_ATTR(KF_PLANAR, false)
 #undef CSIC_ATTR
   return (int)cudaSuccess;
 }

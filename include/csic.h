@@ -60,8 +60,16 @@ enum csic_pool_mode { CSIC_POOL_DECIMATE = 0, CSIC_POOL_AVERAGE = 1 };
  *            slot = 8/16/32 bits for y_bits+cb_bits+cr_bits <= 8 / <= 16 / <= 24; pixel k of a row sits in
  *            bits [k*slot,(k+1)*slot) of a little-endian 64/128-bit word stream; inside a slot
  *            value = (Y>>sy) << (cb_bits+cr_bits) | (Cb>>scb) << cr_bits | (Cr>>scr), zero padded above;
- *            each output row is padded with zero slots to a whole word. */
-enum csic_out_format { CSIC_OUT_YCC888 = 0, CSIC_OUT_RGB888 = 1, CSIC_OUT_BUNDLE64 = 2, CSIC_OUT_BUNDLE128 = 3 };
+ *            each output row is padded with zero slots to a whole word.
+ *  PLANAR    build-defined: what a downstream JPEG / video encoder wants.  Per frame three
+ *            planes back to back: Y [out_h x out_w], Cb [ch x cw], Cr [ch x cw], one byte per sample, quantised.
+ *            The chroma planes hold ONLY the sample points that survive: cw = ceil(out_w / hs), ch = ceil(out_h / vs),
+ *            hs = max(1, (4/a)/f), vs = max(1, vf/f); Cb[rc][cc] is the chroma of output pixel (rc*vs, cc*hs).
+ *            The reference replays held chroma at full rate (3 bytes/pixel); 4:2:0 at f=1 is 1.5 bytes/pixel here.
+ *            csic_expand_planar_* re-applies the reference's replay rule and returns the YCC888 / RGB888 stream.
+ *            Needs ChromaSubsampling before SpatialSampling (or f == 1) and DECIMATE. */
+enum csic_out_format { CSIC_OUT_YCC888 = 0, CSIC_OUT_RGB888 = 1, CSIC_OUT_BUNDLE64 = 2, CSIC_OUT_BUNDLE128 = 3,
+                       CSIC_OUT_PLANAR = 4 };
 
 /* Input pixel layout.  RGB24 = 3 bytes R,G,B (pixel.red/green/blue, ImageCompressorTopApp.scala:86-89).
  * RGBA32 / BGRA32 = 4 bytes per pixel with the fourth ignored, exactly as the reference ignores alpha;
@@ -136,6 +144,10 @@ CSIC_API int csic_validate(const csic_params* p, char* msg, size_t n);
 CSIC_API int csic_out_shape(const csic_params* p, int32_t* out_w, int32_t* out_h, size_t* out_row_bytes,
                    size_t* out_bytes_per_frame);
 
+/* Geometry of CSIC_OUT_PLANAR: chroma plane size and the byte offsets of the Cb / Cr planes inside a frame. */
+CSIC_API int csic_planar_shape(const csic_params* p, int32_t* chroma_w, int32_t* chroma_h, size_t* cb_offset,
+                               size_t* cr_offset);
+
 /* `ImageCompressionApp.parseProcessingStep` (ImageCompressorTopApp.scala:154-161): case-insensitive
  * "spatial"|"spatialsampling" -> 1, "color"|"colorquantization" -> 2, "chroma"|"chromasubsampling" -> 3,
  * anything else -> CSIC_EINVAL_OPS. */
@@ -171,6 +183,12 @@ CSIC_API int csic_process_device(csic_ctx* ctx, const csic_params* p, const void
 CSIC_API int csic_process_device_pitched(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t in_pitch_bytes,
                                          size_t in_frame_stride, size_t n_frames, void* d_out, size_t out_pitch_bytes,
                                          size_t out_frame_stride, void* cuda_stream);
+
+/* Decoder of CSIC_OUT_PLANAR: replays the planes with the reference's sample-and-hold rule
+ * (ChromaSubsampler.scala:52-65) into the YCC888 (expand_format 0) or RGB888 (1) stream, byte for byte what
+ * csic_process_device would have produced with that out_format.  p->out_format must be CSIC_OUT_PLANAR. */
+CSIC_API int csic_expand_planar_device(csic_ctx* ctx, const csic_params* p, const void* d_planar, size_t n_frames,
+                                       void* d_out, int32_t expand_format, void* cuda_stream);
 
 /* Row-band shard of ONE frame layout: processes output rows [out_row0, out_row0+out_rows) of every
  * frame, reading d_rgb / writing d_out at their whole-frame offsets (so bands of one frame may be

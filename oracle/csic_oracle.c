@@ -162,10 +162,18 @@ static int slot_bits(const csic_params* p) {
   return t <= 8 ? 8 : (t <= 16 ? 16 : 32);
 }
 
+/* CSIC_OUT_PLANAR chroma decimation in output pixels (include/csic.h). */
+static void planar_factors(const csic_params* p, int* hs, int* vs) {
+  int hf = 4 / p->chroma_a, vf = (p->chroma_b == 0) ? 2 : 1, f = p->factor;
+  *hs = hf / f > 1 ? hf / f : 1;
+  *vs = vf / f > 1 ? vf / f : 1;
+}
+
 static void out_geometry(const csic_params* p, int* ow, int* oh, size_t* row_bytes) {
   int f = p->factor;
   *ow = (p->width + f - 1) / f;
   *oh = (p->height + f - 1) / f;
+  if (p->out_format == CSIC_OUT_PLANAR) { *row_bytes = (size_t)*ow; return; }
   if (p->out_format == CSIC_OUT_BUNDLE64 || p->out_format == CSIC_OUT_BUNDLE128) {
     size_t word = p->out_format == CSIC_OUT_BUNDLE64 ? 8 : 16;
     size_t bytes = (size_t)*ow * slot_bits(p) / 8;
@@ -178,6 +186,11 @@ static void out_geometry(const csic_params* p, int* ow, int* oh, size_t* row_byt
 size_t csic_oracle_out_bytes_per_frame(const csic_params* p) {
   int ow, oh; size_t rb;
   out_geometry(p, &ow, &oh, &rb);
+  if (p->out_format == CSIC_OUT_PLANAR) {
+    int hs, vs;
+    planar_factors(p, &hs, &vs);
+    return (size_t)ow * oh + 2 * (size_t)((ow + hs - 1) / hs) * ((oh + vs - 1) / vs);
+  }
   return rb * oh;
 }
 
@@ -218,6 +231,22 @@ static int process_frame(const csic_params* p, const uint8_t* rgb, uint8_t* out,
   out_geometry(p, &ow, &oh, &row_bytes);
   if (n != (size_t)ow * oh) return CSIC_EINVAL_DIMS;
 
+  if (p->out_format == CSIC_OUT_PLANAR) {
+    /* Y plane, then the chroma of the surviving sample points: output pixel (rc*vs, cc*hs) carries its own
+     * (just sampled) chroma in the stream, so the planes can be read straight off it. */
+    int hs, vs;
+    planar_factors(p, &hs, &vs);
+    int cw = (ow + hs - 1) / hs, ch = (oh + vs - 1) / vs;
+    uint8_t *yp = out, *cbp = out + (size_t)ow * oh, *crp = cbp + (size_t)cw * ch;
+    for (size_t i = 0; i < n; ++i) yp[i] = cur[i].y;
+    for (int rc = 0; rc < ch; ++rc)
+      for (int cc = 0; cc < cw; ++cc) {
+        const ycc_t* q = &cur[(size_t)(rc * vs) * ow + (size_t)cc * hs];
+        cbp[(size_t)rc * cw + cc] = q->cb;
+        crp[(size_t)rc * cw + cc] = q->cr;
+      }
+    return CSIC_OK;
+  }
   if (p->out_format == CSIC_OUT_YCC888) {
     for (size_t i = 0; i < n; ++i) { out[3 * i] = cur[i].y; out[3 * i + 1] = cur[i].cb; out[3 * i + 2] = cur[i].cr; }
   } else if (p->out_format == CSIC_OUT_RGB888) {     /* ImageCompressorTopApp.scala:118 */

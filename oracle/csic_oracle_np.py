@@ -76,6 +76,30 @@ def _avg(x, f):
     return ((s + (f * f) // 2) >> (2 * (f.bit_length() - 1))).astype(np.uint8)
 
 
+def planar_factors(a, b, f):
+    hf, vf = 4 // a, (2 if b == 0 else 1)
+    return max(1, hf // f), max(1, vf // f)
+
+
+def expand_planar(planar, W, H, a, b, f, to_rgb=False):
+    """Decoder of the PLANAR format: re-applies the replay rule of ChromaSubsampler.scala:52-65 in output
+    coordinates (chroma before spatial, or f == 1).  planar: flat uint8 of one frame.  Returns [Ho, Wo, 3]."""
+    hf, vf = 4 // a, (2 if b == 0 else 1)
+    hs, vs = planar_factors(a, b, f)
+    Wo, Ho = -(-W // f), -(-H // f)
+    cw, ch = -(-Wo // hs), -(-Ho // vs)
+    y = planar[:Wo * Ho].reshape(Ho, Wo)
+    cb = planar[Wo * Ho:Wo * Ho + cw * ch].reshape(ch, cw)
+    cr = planar[Wo * Ho + cw * ch:].reshape(ch, cw)
+    ro, co = np.mgrid[0:Ho, 0:Wo]
+    held = ((ro * f) % vf) != 0                              # only possible for f == 1
+    last = (((W - 1) // hf) * hf) // f                       # last sample column, in output pixels
+    src_r = np.where(held, ro - 1, ro) // vs
+    src_c = np.where(held, last, co - co % hs) // hs
+    out = np.stack([y, cb[src_r, src_c], cr[src_r, src_c]], -1)
+    return inverse(out) if to_rgb else out
+
+
 def slot_bits(q):
     t = sum(q)
     return 8 if t <= 8 else (16 if t <= 16 else 32)
@@ -110,6 +134,9 @@ def process_frame(rgb, a=4, b=4, q=(8, 8, 8), factor=1, ops=(3, 1, 2), round_mod
         yr, yc, cr_, cc_ = source_maps(W, H, a, b, f, chroma_first)
         o = quant(np.stack([ycc[yr, yc, 0], ycc[cr_, cc_, 1], ycc[cr_, cc_, 2]], -1), q)
     Ho, Wo = o.shape[:2]
+    if out_format == 4:                                   # PLANAR: Y plane + surviving chroma sample points
+        hs, vs = planar_factors(a, b, f)
+        return np.concatenate([o[..., 0].reshape(-1), o[::vs, ::hs, 1].reshape(-1), o[::vs, ::hs, 2].reshape(-1)])
     if out_format == 0:
         return o.reshape(-1)
     if out_format == 1:

@@ -423,3 +423,32 @@ def test_host_band_and_multi_context(csic, ctx):
         rgb7 = np.concatenate([rgb] * 4)[:7]
         assert np.array_equal(multi.process_host(p, rgb7), np.concatenate([want] * 4)[:7])
     multi.close()
+
+
+def test_planar_output_and_decoder(csic, ctx):
+    """out_format PLANAR (SURVEY 8(f) N3): Y plane + the chroma samples that survive.  Both kernels equal the oracle;
+    csic_expand_planar_device replays the planes into exactly the YCC888 / RGB888 stream of the same parameters."""
+    import torch
+    fams = set()
+    for (W, H), f, ab, order, q, inf in itertools.product(
+            [(128, 16), (256, 9), (64, 64), (40, 12), (33, 7), (2048, 6)], (1, 2, 4, 8), ALL_AB,
+            ("CSQ", "QCS", "SQC"), [(8, 8, 8), (5, 4, 3)], (0, 1)):
+        if order == "SQC" and f > 1:
+            with pytest.raises(csic.IllegalArgumentException):
+                both_params(csic, W, H, ab[0], ab[1], q, f, order, 0, 0, 4, inf)
+            continue
+        ch = 3 if inf == 0 else 4
+        rgb = np.random.default_rng(W + 7 * f).integers(0, 256, size=(3, H, W, ch), dtype=np.uint8)
+        p, po = both_params(csic, W, H, ab[0], ab[1], q, f, order, 0, 0, 4, inf)
+        out, fam = run_both_kernels(ctx, p, rgb)
+        fams.add(fam)
+        assert np.array_equal(out, oracle.process(po, rgb)), (W, H, f, ab, order, q, inf, fam)
+        for to_rgb in (False, True):
+            pe, _ = both_params(csic, W, H, ab[0], ab[1], q, f, order, 0, 0, 1 if to_rgb else 0, inf)
+            want = ctx.process_host(pe, rgb)
+            got = ctx.expand_planar_torch(p, torch.from_numpy(out).cuda(), to_rgb)
+            ctx.synchronize(); torch.cuda.synchronize()
+            assert np.array_equal(got.cpu().numpy().reshape(3, -1), want), (W, H, f, ab, order, to_rgb)
+    assert fams == {1, 2}
+    cw, chh, ob, orr = csic.planar_shape(both_params(csic, 1920, 1080, 2, 0, (8, 8, 8), 1, "CSQ", 0, 0, 4)[0])
+    assert (cw, chh, ob, orr) == (960, 540, 1920 * 1080, 1920 * 1080 + 960 * 540)
