@@ -44,6 +44,8 @@ WORKLOADS = {
              "BASELINE configs[1] batched: 512x512 x4096 frames, 4:2:2 + f=2, YCC888"),
     "cfg2x1": (512, 512, 1, 2, 2, (8, 8, 8), 2, "CSQ", 0,
                "BASELINE configs[1]: ONE 512x512 frame, 4:2:2 + f=2, YCC888 (launch-latency bound)"),
+    "cfg3b": (1920, 1080, 256, 2, 0, (4, 4, 4), 1, "CSQ", 3,
+              "BASELINE configs[2] with 16-bit bundle slots (Y4Cb4Cr4 -> 2 B/px out, 5 B/px total)"),
     "cfg3p": (1920, 1080, 256, 2, 0, (4, 4, 4), 1, "CSQ", 4,
               "cfg3 geometry with PLANAR 4:2:0 output (Y plane + quarter-size Cb/Cr planes, 1.5 B/px out)"),
     "cfg4avg": (3840, 2160, 1024, 2, 0, (8, 8, 8), 2, "CSQ", 3,
