@@ -59,15 +59,16 @@ __device__ __forceinline__ void chroma_src_case_b(const KPlan& P, int ro, int co
 }
 
 
-template <bool TRUNC>
+// IdxT: uint32_t whenever the launch has fewer than 2^32 output slots (three 32-bit divisions per slot instead
+// of three 64-bit ones).
+template <bool TRUNC, typename IdxT>
 __global__ void __launch_bounds__(256) csic_generic_kernel(const __grid_constant__ KPlan P) {
-  const uint64_t total = (uint64_t)P.n_frames * (uint64_t)P.band_rows * (uint64_t)P.slots_per_row;
-  for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (uint64_t)gridDim.x * blockDim.x) {
+  const IdxT total = (IdxT)((uint64_t)P.n_frames * (uint64_t)P.band_rows * (uint64_t)P.slots_per_row);
+  for (IdxT idx = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (IdxT)gridDim.x * blockDim.x) {
     const int co = (int)(idx % (uint32_t)P.slots_per_row);
-    const uint64_t t = idx / (uint32_t)P.slots_per_row;
+    const IdxT t = idx / (uint32_t)P.slots_per_row;
     const int ro = P.row0 + (int)(t % (uint32_t)P.band_rows);
-    const uint64_t k = t / (uint32_t)P.band_rows;
+    const uint64_t k = (uint64_t)(t / (uint32_t)P.band_rows);
     uint8_t* orow = P.out + k * P.out_frame_bytes + (size_t)ro * P.out_row_bytes;
     if (co >= P.Wo) {   // BUNDLE row padding: zero slots
       if (P.slot_bytes == 1) orow[co] = 0;
@@ -199,8 +200,14 @@ int launch_generic(const KPlan& k, void* stream) {
   const uint64_t total = (uint64_t)k.n_frames * (uint64_t)k.band_rows * (uint64_t)k.slots_per_row;
   if (total == 0) return (int)cudaSuccess;
   const uint64_t blocks = std::min<uint64_t>((total + 255) / 256, (uint64_t)148 * 64);
-  if (k.trunc) csic_generic_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(k);
-  else csic_generic_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(k);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (total + blocks * 256 < (1ull << 32)) {
+    if (k.trunc) csic_generic_kernel<true, uint32_t><<<(unsigned)blocks, 256, 0, st>>>(k);
+    else csic_generic_kernel<false, uint32_t><<<(unsigned)blocks, 256, 0, st>>>(k);
+  } else {
+    if (k.trunc) csic_generic_kernel<true, uint64_t><<<(unsigned)blocks, 256, 0, st>>>(k);
+    else csic_generic_kernel<false, uint64_t><<<(unsigned)blocks, 256, 0, st>>>(k);
+  }
   return (int)cudaGetLastError();
 }
 

@@ -452,3 +452,25 @@ def test_planar_output_and_decoder(csic, ctx):
     assert fams == {1, 2}
     cw, chh, ob, orr = csic.planar_shape(both_params(csic, 1920, 1080, 2, 0, (8, 8, 8), 1, "CSQ", 0, 0, 4)[0])
     assert (cw, chh, ob, orr) == (960, 540, 1920 * 1080, 1920 * 1080 + 960 * 540)
+
+
+def test_row_segments_and_ring_depths(csic, ctx):
+    """Force rows to be split into several tiles (CSIC_OPT_TILE_BYTES small -> nsplit > 1: held chroma comes from
+    TMA-fetched aux windows, per-segment stores) and vary ring depth / block size / CTAs per SM: results never change."""
+    rng = np.random.default_rng(5)
+    try:
+        for tile_bytes, stages, threads, ctas in [(1024, 2, 128, 1), (3072, 3, 256, 3), (6144, 4, 64, 2), (16384, 2, 512, 1)]:
+            ctx.set_option(4, tile_bytes); ctx.set_option(3, stages); ctx.set_option(5, threads); ctx.set_option(2, ctas)
+            for (W, H), f, ab, order, (fmt, q), inf in itertools.product(
+                    [(1024, 10), (2048, 7), (512, 33)], (1, 2, 4, 8), [(2, 0), (1, 0), (4, 4)], ("CSQ", "SQC"),
+                    [(0, (8, 8, 8)), (1, (6, 5, 5)), (3, (8, 8, 8)), (2, (3, 3, 2)), (4, (7, 6, 5))], (0, 1)):
+                if fmt == 4 and order == "SQC" and f > 1:
+                    continue
+                rgb = rng.integers(0, 256, size=(2, H, W, 3 if inf == 0 else 4), dtype=np.uint8)
+                p, po = both_params(csic, W, H, ab[0], ab[1], q, f, order, 0, 0, fmt, inf)
+                got = ctx.process_host(p, rgb)
+                assert ctx.last_kernel()[0] == 2
+                assert np.array_equal(got, oracle.process(po, rgb)), (tile_bytes, stages, threads, W, H, f, ab, order, fmt, inf)
+    finally:
+        for opt in (2, 3, 4, 5):
+            ctx.set_option(opt, 0)
