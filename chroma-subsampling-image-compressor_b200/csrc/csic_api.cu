@@ -465,6 +465,10 @@ static int host_pipeline(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb
   if (rc != CSIC_OK) return rc;
 
   const size_t n_chunks = (n_frames + per - 1) / per;
+  // One chunk (small batches, single images): nothing to overlap, so issue copy-in, kernel and copy-out on ONE
+  // stream and synchronise once -- no cross-stream events on the latency path.
+  const bool single = n_chunks == 1;
+  cudaStream_t s_in = single ? ctx->stream : ctx->s_h2d, s_out = single ? ctx->stream : ctx->s_d2h;
   for (size_t c = 0; c < n_chunks; ++c) {
     const int b = (int)(c % kPipe);
     const size_t f0 = c * per, nf = std::min(per, n_frames - f0);
@@ -480,36 +484,44 @@ static int host_pipeline(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb
       for (size_t k = 0; k < nf; ++k)
         CSIC_CUDA(cudaMemcpy2DAsync(d_in + k * dev_frame_bytes, in_pitch,
                                     rgb + (f0 + k) * g.in_frame_bytes + first_stored * host_row_step, host_row_step,
-                                    g.in_row_bytes, rows_stored, cudaMemcpyHostToDevice, ctx->s_h2d));
+                                    g.in_row_bytes, rows_stored, cudaMemcpyHostToDevice, s_in));
     } else if (compact || lay.in_pitch) {
       CSIC_CUDA(cudaMemcpy2DAsync(d_in, in_pitch, rgb + f0 * g.in_frame_bytes, host_row_step, g.in_row_bytes,
-                                  nf * rows_stored, cudaMemcpyHostToDevice, ctx->s_h2d));
+                                  nf * rows_stored, cudaMemcpyHostToDevice, s_in));
     } else {
       CSIC_CUDA(cudaMemcpyAsync(d_in, rgb + f0 * g.in_frame_bytes, nf * g.in_frame_bytes, cudaMemcpyHostToDevice,
-                                ctx->s_h2d));
+                                s_in));
     }
     ctx->h2d_bytes += nf * rows_stored * g.in_row_bytes;
-    CSIC_CUDA(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
-    CSIC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
+    if (!single) {
+      CSIC_CUDA(cudaEventRecord(ctx->ev_h2d[b], s_in));
+      CSIC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
+    }
     // virtual frame bases: row r of the frame sits at base + r * pitch; only the band's rows are ever touched
     rc = run(ctx, p, d_in - first_stored * in_pitch, nf, d_out - (size_t)row0 * out_pitch, row0, rows, ctx->stream,
              compact, lay);
     if (rc != CSIC_OK) return rc;
-    CSIC_CUDA(cudaEventRecord(ctx->ev_k[b], ctx->stream));
-    CSIC_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_k[b], 0));
+    if (!single) {
+      CSIC_CUDA(cudaEventRecord(ctx->ev_k[b], ctx->stream));
+      CSIC_CUDA(cudaStreamWaitEvent(s_out, ctx->ev_k[b], 0));
+    }
     if (band) {
       for (size_t k = 0; k < nf; ++k)
         CSIC_CUDA(cudaMemcpy2DAsync(out + (f0 + k) * g.out_frame_bytes + (size_t)row0 * g.out_row_bytes, g.out_row_bytes,
                                     d_out + k * dev_out_frame_bytes, out_pitch, g.out_row_bytes, (size_t)rows,
-                                    cudaMemcpyDeviceToHost, ctx->s_d2h));
+                                    cudaMemcpyDeviceToHost, s_out));
     } else if (lay.out_pitch) {
       CSIC_CUDA(cudaMemcpy2DAsync(out + f0 * g.out_frame_bytes, g.out_row_bytes, d_out, out_pitch, g.out_row_bytes,
-                                  nf * (size_t)g.out_h, cudaMemcpyDeviceToHost, ctx->s_d2h));
+                                  nf * (size_t)g.out_h, cudaMemcpyDeviceToHost, s_out));
     } else {
       CSIC_CUDA(cudaMemcpyAsync(out + f0 * g.out_frame_bytes, d_out, nf * g.out_frame_bytes, cudaMemcpyDeviceToHost,
-                                ctx->s_d2h));
+                                s_out));
     }
-    CSIC_CUDA(cudaEventRecord(ctx->ev_d2h[b], ctx->s_d2h));
+    if (!single) CSIC_CUDA(cudaEventRecord(ctx->ev_d2h[b], s_out));
+  }
+  if (single) {
+    CSIC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CSIC_OK;
   }
   CSIC_CUDA(cudaStreamSynchronize(ctx->s_d2h));
   CSIC_CUDA(cudaStreamSynchronize(ctx->stream));
