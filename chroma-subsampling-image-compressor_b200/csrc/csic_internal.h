@@ -66,11 +66,6 @@ struct KPlan {
   uint32_t qmask;                        // my | mcb<<8 | mcr<<16 (per-channel keep masks)
 };
 
-struct LaunchInfo {
-  int family;      // 1 generic gather kernel, 2 TMA-staged row kernel, 3 TMA-staged pooling kernel
-  int launches;
-};
-
 // Fills the TMA-row-kernel fields of `k`; returns false when the configuration is not eligible
 // (then the generic kernel runs).  `sm_count`/`max_smem` come from the device.
 bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_stages, uint32_t force_tile_bytes);

@@ -1,7 +1,7 @@
 """CPU oracle for the pixel pipeline -- TEST INFRASTRUCTURE ONLY.
 
 Importers allowed: tests/, __graft_entry__.smoke(), bench.py (cpu_baseline / --impl reference).
-The product package never imports this module (tests/test_layout.py greps for it).
+The product package never imports this module (tests/test_host_logic.py::test_product_never_touches_the_oracle).
 
 `lib()` loads oracle/_build/libcsic_oracle.so (built from csic_oracle.c by `make -C oracle`), the
 literal streaming restatement of the reference.  `csic_oracle_np` is an independent closed-form
