@@ -196,6 +196,7 @@ def main():
                     help="capture the K timed launches into one CUDA graph and time its replay (launch-bound workloads)")
     ap.add_argument("--in-format", type=int, default=0, choices=[0, 1, 2], help="0 RGB24, 1 RGBA32, 2 BGRA32")
     ap.add_argument("--generic", action="store_true", help="force the generic gather kernel (family 1)")
+    ap.add_argument("--no-verify", action="store_true", help="skip the full-batch cross-check against the generic kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
@@ -275,6 +276,25 @@ def main():
             ctx.process_torch(p, rgb, out=out)      # one kernel launch on torch's current stream
         else:
             ctx.process_torch(p, rgb, out=out, out_row0=band[0], out_rows=band[1])
+
+    # full-size cross-check (outside the timed region): the whole batch through the independent generic gather
+    # kernel must equal the TMA kernel's output byte for byte
+    full_check = None
+    if rank == 0 and not args.no_verify and not args.generic:
+        try:
+            ctx.process_torch(p, rgb, out=out)
+            fam_fast = ctx.last_kernel()[0]
+            ref = torch.empty_like(out)
+            ctx.set_option(0, 1)
+            ctx.process_torch(p, rgb, out=ref)
+            ctx.set_option(0, 0)
+            torch.cuda.synchronize()
+            full_check = {"frames": frames, "kernels": [fam_fast, 1], "equal": bool(torch.equal(out, ref))}
+            del ref
+            torch.cuda.empty_cache()
+        except torch.cuda.OutOfMemoryError:
+            full_check = {"skipped": "not enough device memory for a second output buffer"}
+            ctx.set_option(0, 0)
 
     def barrier():
         if dist is not None:
@@ -413,7 +433,7 @@ def main():
             "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches1 - launches0) * world,
             "timed_as": "cuda_graph_replay" if args.graph else "stream_launches",
-            "parity_spot_check": parity, "step_ms_min": round(min(step_ms), 4), "step_ms_max": round(max(step_ms), 4),
+            "parity_spot_check": parity, "full_batch_cross_check": full_check, "step_ms_min": round(min(step_ms), 4), "step_ms_max": round(max(step_ms), 4),
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

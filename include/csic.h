@@ -201,7 +201,8 @@ CSIC_API int csic_band_input_rows(const csic_params* p, int32_t out_row0, int32_
 
 /* Host buffers in, host buffers out: H2D + kernel + D2H, chunked and double-buffered on the
  * context's streams, synchronous on return.  This is the call a Scala `processImage` replacement
- * makes (ImageCompressorTopApp.scala:23-145 minus PNG I/O).  rgb/out may be pageable or pinned.
+ * makes (ImageCompressorTopApp.scala:23-145 minus PNG I/O).  rgb/out may be pageable or pinned; pageable
+ * buffers (a JVM heap, malloc) are gathered into / scattered from pinned bounce buffers on several host threads.
  * With DECIMATE and f > 1 (and H % f == 0) only the input rows the pipeline reads -- every f-th -- are
  * copied to the device (strided 2-D copy); the result is identical.  Widths that break the TMA kernels' 16-byte
  * rules are re-pitched in the staging buffers, so they avoid the generic kernel too. */
@@ -235,9 +236,10 @@ CSIC_API int csic_synchronize(csic_ctx* ctx);
  * generic gather kernel.  HOST_CHUNK_BYTES: input bytes per pipelined chunk of csic_process_host.
  * GRID_CTAS_PER_SM / STAGES / TILE_BYTES: overrides for the row kernel's persistent grid, ring depth and
  * input bytes per tile (0 = auto); HOST_FULL_FRAMES: 1 = csic_process_host copies whole frames even when a
- * DECIMATE pipeline reads only every f-th row (default 0: ship only the rows that are read); BLOCK_THREADS: threads per CTA of the row kernel (multiple of 32, <= 512). */
+ * DECIMATE pipeline reads only every f-th row (default 0: ship only the rows that are read); HOST_NO_BOUNCE: 1 =
+ * do not stage pageable caller buffers through the context's pinned bounce buffers; BLOCK_THREADS: threads per CTA of the row kernel (multiple of 32, <= 512). */
 enum csic_option { CSIC_OPT_KERNEL_FAMILY = 0, CSIC_OPT_HOST_CHUNK_BYTES = 1, CSIC_OPT_GRID_CTAS_PER_SM = 2,
-                   CSIC_OPT_STAGES = 3, CSIC_OPT_TILE_BYTES = 4, CSIC_OPT_BLOCK_THREADS = 5, CSIC_OPT_HOST_FULL_FRAMES = 6 };
+                   CSIC_OPT_STAGES = 3, CSIC_OPT_TILE_BYTES = 4, CSIC_OPT_BLOCK_THREADS = 5, CSIC_OPT_HOST_FULL_FRAMES = 6, CSIC_OPT_HOST_NO_BOUNCE = 7 };
 CSIC_API int csic_set_option(csic_ctx* ctx, int option, int64_t value);
 
 /* Diagnostics: total bytes csic_process_host has copied host -> device on this context. */

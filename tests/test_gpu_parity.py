@@ -474,3 +474,30 @@ def test_row_segments_and_ring_depths(csic, ctx):
     finally:
         for opt in (2, 3, 4, 5):
             ctx.set_option(opt, 0)
+
+
+def test_pageable_buffers_use_the_bounce_pipeline(csic, ctx):
+    """Pageable host arrays (what a JVM / malloc caller has) go through the pinned bounce buffers with parallel
+    host copies; pinned arrays go direct; with the bounce path disabled the driver stages.  Same bytes every way --
+    whole frames, compacted rows, re-pitched odd widths, row bands, PLANAR."""
+    rng = np.random.default_rng(8)
+    ctx.set_option(1, 6 << 20)            # 6 MB chunks -> several chunks, ring reuse, deferred drains
+    try:
+        for (W, H, n), f, order, fmt in itertools.product([(1024, 512, 9), (1000, 300, 14)], (1, 2, 4), ("CSQ", "SQC"), (0, 3, 4)):
+            if fmt == 4 and order == "SQC" and f > 1:
+                continue
+            rgb = rng.integers(0, 256, size=(n, H, W, 3), dtype=np.uint8)        # pageable
+            p, po = both_params(csic, W, H, 2, 0, (8, 8, 8), f, order, 0, 0, fmt)
+            want = oracle.process(po, rgb, threads=4)
+            assert np.array_equal(ctx.process_host(p, rgb), want), (W, H, f, order, fmt)
+            ctx.set_option(7, 1)
+            assert np.array_equal(ctx.process_host(p, rgb), want)
+            ctx.set_option(7, 0)
+            if fmt != 4:
+                _, oh, _, fb = csic.out_shape(p)
+                out = np.zeros((n, fb), np.uint8)
+                for r0, r1 in ((0, oh // 3), (oh // 3, oh)):
+                    ctx.process_host_band(p, rgb, out, r0, r1 - r0)
+                assert np.array_equal(out, want)
+    finally:
+        ctx.set_option(1, 0)
