@@ -52,6 +52,10 @@ WORKLOADS = {
                 "AVERAGE-pooling extension on the cfg4 geometry: 4:2:0 + 2x2 mean + BUNDLE128 (reads every row)"),
     "cfg5avg": (7680, 4320, 64, 2, 0, (6, 5, 5), 4, "CSQ", 1,
                 "AVERAGE-pooling extension on the cfg5 geometry: 4:2:0 + 4x4 mean + Q_16BIT + RGB888"),
+    "cfg3odd": (1918, 1078, 256, 2, 0, (4, 4, 4), 1, "CSQ", 0,
+                "cfg3 with a width no 16-byte rule fits (1918x1078, dense): the any-alignment flex kernel"),
+    "cfg4odd": (3838, 2158, 256, 2, 0, (8, 8, 8), 2, "CSQ", 3,
+                "cfg4 with odd dimensions (3838x2158 x256, dense): the any-alignment flex kernel"),
     "cfg5": (7680, 4320, 64, 2, 0, (6, 5, 5), 4, "CSQ", 1,
              "BASELINE configs[4]: 7680x4320 x64 frames, 4:2:0 + f=4 + Q_16BIT + RGB888 reconstruct"),
 }
@@ -196,6 +200,8 @@ def main():
                     help="capture the K timed launches into one CUDA graph and time its replay (launch-bound workloads)")
     ap.add_argument("--in-format", type=int, default=0, choices=[0, 1, 2], help="0 RGB24, 1 RGBA32, 2 BGRA32")
     ap.add_argument("--generic", action="store_true", help="force the generic gather kernel (family 1)")
+    ap.add_argument("--family", type=int, default=0, choices=[0, 1, 2],
+                    help="kernel family option: 0 automatic, 1 generic gather kernel, 2 no TMA kernels (flex kernel)")
     ap.add_argument("--no-verify", action="store_true", help="skip the full-batch cross-check against the generic kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -237,7 +243,9 @@ def main():
     _, out_h, _, out_fb = csic.out_shape(p)
     ctx = csic.Context(local)
     if args.generic:
-        ctx.set_option(0, 1)
+        args.family = 1
+    if args.family:
+        ctx.set_option(0, args.family)
     if args.ctas_per_sm:
         ctx.set_option(2, args.ctas_per_sm)
     if args.stages:
@@ -280,21 +288,21 @@ def main():
     # full-size cross-check (outside the timed region): the whole batch through the independent generic gather
     # kernel must equal the TMA kernel's output byte for byte
     full_check = None
-    if rank == 0 and not args.no_verify and not args.generic:
+    if rank == 0 and not args.no_verify and args.family != 1:
         try:
             ctx.process_torch(p, rgb, out=out)
             fam_fast = ctx.last_kernel()[0]
             ref = torch.empty_like(out)
             ctx.set_option(0, 1)
             ctx.process_torch(p, rgb, out=ref)
-            ctx.set_option(0, 0)
+            ctx.set_option(0, args.family)
             torch.cuda.synchronize()
             full_check = {"frames": frames, "kernels": [fam_fast, 1], "equal": bool(torch.equal(out, ref))}
             del ref
             torch.cuda.empty_cache()
         except torch.cuda.OutOfMemoryError:
             full_check = {"skipped": "not enough device memory for a second output buffer"}
-            ctx.set_option(0, 0)
+            ctx.set_option(0, args.family)
 
     def barrier():
         if dist is not None:
@@ -428,7 +436,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(kernel_ms, 4),
-                         "kernel": {2: "csic_rows_kernel", 3: "csic_pool_kernel"}.get(fam, "csic_generic_kernel"),
+                         "kernel": {2: "csic_rows_kernel", 3: "csic_pool_kernel", 4: "csic_flex_kernel"}.get(fam, "csic_generic_kernel"),
                          "peak_source": peak_src},
             "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches1 - launches0) * world,

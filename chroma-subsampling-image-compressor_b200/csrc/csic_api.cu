@@ -176,12 +176,15 @@ int run(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t n_frames,
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
   k.block_threads = ctx->opt_block_threads;
   int err;
-  if (ctx->opt_family != 1 && csic::plan_rows_kernel(k, ctx->sm_count, ctx->max_smem_optin, ctx->opt_stages, ctx->opt_tile_bytes)) {
+  if (ctx->opt_family == 0 && csic::plan_rows_kernel(k, ctx->sm_count, ctx->max_smem_optin, ctx->opt_stages, ctx->opt_tile_bytes)) {
     err = csic::launch_rows(k, ctx->sm_count, ctx->opt_ctas_per_sm, st);
     ctx->last_family = 2;
-  } else if (ctx->opt_family != 1 && csic::plan_pool_kernel(k, ctx->sm_count, ctx->max_smem_optin)) {
+  } else if (ctx->opt_family == 0 && csic::plan_pool_kernel(k, ctx->sm_count, ctx->max_smem_optin)) {
     err = csic::launch_pool(k, ctx->sm_count, ctx->opt_ctas_per_sm, st);
     ctx->last_family = 3;
+  } else if (ctx->opt_family != 1 && csic::plan_flex_kernel(k, ctx->sm_count, ctx->max_smem_optin)) {
+    err = csic::launch_flex(k, ctx->sm_count, ctx->opt_ctas_per_sm, st);
+    ctx->last_family = 4;
   } else {
     err = csic::launch_generic(k, st);
     ctx->last_family = 1;
@@ -204,8 +207,6 @@ int ensure_staging(csic_ctx* ctx, size_t in_bytes, size_t out_bytes) {
   if (out_bytes > ctx->d_out_cap) {
     for (int i = 0; i < kPipe; ++i) {
       if (ctx->d_out[i]) cudaFree(ctx->d_out[i]);
-    if (ctx->h_in[i]) cudaFreeHost(ctx->h_in[i]);
-    if (ctx->h_out[i]) cudaFreeHost(ctx->h_out[i]);
       ctx->d_out[i] = nullptr;
     }
     ctx->d_out_cap = 0;
@@ -294,7 +295,7 @@ int csic_set_option(csic_ctx* ctx, int option, int64_t value) {
   if (!ctx) return CSIC_EINVAL_ARG;
   switch (option) {
     case CSIC_OPT_KERNEL_FAMILY:
-      if (value != 0 && value != 1) return CSIC_EINVAL_ARG;
+      if (value < 0 || value > 2) return CSIC_EINVAL_ARG;
       ctx->opt_family = (int)value;
       return CSIC_OK;
     case CSIC_OPT_HOST_CHUNK_BYTES:
@@ -497,7 +498,7 @@ static int host_pipeline(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb
   // rows are re-pitched on the way in and out (the copies are 2-D anyway), so odd widths also avoid the
   // generic kernel.
   Layout lay;
-  if (ctx->opt_family != 1) {
+  if (ctx->opt_family == 0) {
     auto eligible = [&](const Layout& l) {
       csic::KPlan probe;
       if (build_plan(*p, reinterpret_cast<const void*>(uintptr_t(4096)), reinterpret_cast<void*>(uintptr_t(4096)), 1, 0,

@@ -84,6 +84,11 @@ int launch_pool(const KPlan& k, int sm_count, int force_ctas_per_sm, void* strea
 template <int F> int launch_pool_factor(const KPlan& k, unsigned grid, void* stream);
 template <int F> int pool_set_attributes_factor(size_t max_smem_optin);
 
+// Any width / pitch / base alignment (csic_flex_kernel.cu): DECIMATE pipelines the TMA kernels' 16-byte rules exclude.
+bool plan_flex_kernel(KPlan& k, int sm_count, size_t max_smem_optin);
+int launch_flex(const KPlan& k, int sm_count, int force_ctas_per_sm, void* stream);
+int flex_set_attributes(size_t max_smem_optin);
+
 // Implemented once per spatial factor in csic_rows_kernel.cu (explicit specialisations for F = 1, 2, 4, 8).
 template <int F> int launch_rows_factor(const KPlan& k, unsigned grid, void* stream);
 template <int F> int rows_set_attributes_factor(size_t max_smem_optin);

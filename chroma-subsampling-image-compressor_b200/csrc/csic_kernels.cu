@@ -59,6 +59,18 @@ __device__ __forceinline__ void chroma_src_case_b(const KPlan& P, int ro, int co
 }
 
 
+// One bundle slot; rows of a caller's sub-buffer need not be slot aligned.
+__device__ __forceinline__ void store_slot(uint8_t* orow, int co, uint32_t v, int slot_bytes) {
+  uint8_t* o = orow + (size_t)co * (size_t)slot_bytes;
+  if ((reinterpret_cast<uintptr_t>(o) & (uintptr_t)(slot_bytes - 1)) == 0) {
+    if (slot_bytes == 1) *o = (uint8_t)v;
+    else if (slot_bytes == 2) *reinterpret_cast<uint16_t*>(o) = (uint16_t)v;
+    else *reinterpret_cast<uint32_t*>(o) = v;
+  } else {
+    for (int i = 0; i < slot_bytes; ++i) o[i] = (uint8_t)(v >> (8 * i));
+  }
+}
+
 // IdxT: uint32_t whenever the launch has fewer than 2^32 output slots (three 32-bit divisions per slot instead
 // of three 64-bit ones).
 template <bool TRUNC, typename IdxT>
@@ -71,9 +83,7 @@ __global__ void __launch_bounds__(256) csic_generic_kernel(const __grid_constant
     const uint64_t k = (uint64_t)(t / (uint32_t)P.band_rows);
     uint8_t* orow = P.out + k * P.out_frame_bytes + (size_t)ro * P.out_row_bytes;
     if (co >= P.Wo) {   // BUNDLE row padding: zero slots
-      if (P.slot_bytes == 1) orow[co] = 0;
-      else if (P.slot_bytes == 2) reinterpret_cast<uint16_t*>(orow)[co] = 0;
-      else reinterpret_cast<uint32_t*>(orow)[co] = 0;
+      store_slot(orow, co, 0u, P.slot_bytes);
       continue;
     }
     const uint8_t* frame = P.in + k * P.in_frame_bytes;
@@ -154,9 +164,7 @@ __global__ void __launch_bounds__(256) csic_generic_kernel(const __grid_constant
     } else {
       const uint32_t v = ((uint32_t)(y >> P.sy) << (P.cb_bits + P.cr_bits)) |
                          ((uint32_t)(cb >> P.scb) << P.cr_bits) | (uint32_t)(cr >> P.scr);
-      if (P.slot_bytes == 1) orow[co] = (uint8_t)v;
-      else if (P.slot_bytes == 2) reinterpret_cast<uint16_t*>(orow)[co] = (uint16_t)v;
-      else reinterpret_cast<uint32_t*>(orow)[co] = v;
+      store_slot(orow, co, v, P.slot_bytes);
     }
   }
 }
@@ -317,6 +325,7 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
 
 int rows_kernel_set_attributes(size_t max_smem_optin) {
   int e;
+  if ((e = flex_set_attributes(max_smem_optin)) != 0) return e;
   if ((e = pool_set_attributes_factor<2>(max_smem_optin)) != 0) return e;
   if ((e = pool_set_attributes_factor<4>(max_smem_optin)) != 0) return e;
   if ((e = pool_set_attributes_factor<8>(max_smem_optin)) != 0) return e;

@@ -37,15 +37,26 @@ def both_params(csic, W, H, a, b, q, f, order, round_mode=0, pool_mode=0, out_fo
 
 
 def run_both_kernels(ctx, p, rgb):
-    """The TMA row kernel (when eligible) and the generic gather kernel must agree with each other."""
+    """Every kernel family that can run the parameter set must produce the same bytes: the automatic choice (TMA
+    row / pooling kernel when eligible), the generic gather kernel (family option 1), and the any-alignment flex
+    kernel (family option 2: no TMA kernels, no re-pitching in the host path -> dense odd rows reach it as they are)."""
     ctx.set_option(0, 0)
     out_auto = ctx.process_host(p, rgb)
     fam_auto = ctx.last_kernel()[0]
     ctx.set_option(0, 1)
     out_gen = ctx.process_host(p, rgb)
     assert ctx.last_kernel()[0] == 1
+    ctx.set_option(0, 2)
+    out_flex = ctx.process_host(p, rgb)
+    fam_flex = ctx.last_kernel()[0]
     ctx.set_option(0, 0)
-    assert np.array_equal(out_auto, out_gen), "row kernel and generic kernel disagree"
+    assert fam_flex in (1, 4)
+    if p.pool_mode == 0 or p.factor == 1:
+        case_b = p.factor > 1 and [p.op[0], p.op[1], p.op[2]].index(1) < [p.op[0], p.op[1], p.op[2]].index(3)
+        if not case_b:
+            assert fam_flex == 4, "every chroma-first DECIMATE pipeline must be eligible for the flex kernel"
+    assert np.array_equal(out_auto, out_gen), "automatic kernel and generic kernel disagree"
+    assert np.array_equal(out_flex, out_gen), "flex kernel and generic kernel disagree"
     return out_auto, fam_auto
 
 
@@ -185,6 +196,11 @@ def test_baseline_geometry(csic, ctx, name):
     out_gen = ctx.process_torch(p, rgb)
     ctx.synchronize(); ctx.set_option(0, 0)
     assert torch.equal(out, out_gen)
+    ctx.set_option(0, 2)      # ... and the any-alignment flex kernel
+    out_flex = ctx.process_torch(p, rgb)
+    ctx.synchronize(); assert ctx.last_kernel()[0] == 4
+    ctx.set_option(0, 0)
+    assert torch.equal(out, out_flex)
     # (3) frames are independent: permuting the batch permutes the output
     perm = torch.tensor([2, 0, 1], device="cuda")
     out_perm = ctx.process_torch(p, rgb[perm].contiguous())
@@ -283,7 +299,7 @@ def test_randomised_parameter_space(csic, ctx):
     (a,b), order, factor, format, rounding, bit depth, pooling mode), both kernels vs the oracle."""
     rng = np.random.default_rng(20261018)
     widths = [1, 2, 3, 5, 16, 17, 31, 32, 48, 64, 96, 100, 128, 160, 256, 272, 320]
-    seen = {1: 0, 2: 0, 3: 0}
+    seen = {1: 0, 2: 0, 3: 0, 4: 0}
     for it in range(400):
         f = int(rng.choice([1, 2, 4, 8]))
         pool = int(rng.random() < 0.15)
@@ -300,7 +316,7 @@ def test_randomised_parameter_space(csic, ctx):
         out, fam = run_both_kernels(ctx, p, rgb)
         seen[fam] += 1
         assert np.array_equal(out, oracle.process(po, rgb)), (it, W, H, a, b, order, q, f, fmt, rm, pool, fam)
-    assert seen[1] > 50 and seen[2] > 50, seen        # both kernel families were exercised
+    assert seen[2] > 50 and seen[1] + seen[4] > 20, seen        # TMA and non-TMA families were exercised
 
 
 def test_writes_stay_inside_the_output_buffer(csic, ctx):
@@ -316,7 +332,7 @@ def test_writes_stay_inside_the_output_buffer(csic, ctx):
         n = 3
         rgb = torch.randint(0, 256, (n, H, W, 3), dtype=torch.uint8, device="cuda")
         want = torch.from_numpy(oracle.process(po, rgb.cpu().numpy())).cuda()
-        for fam in (0, 1):
+        for fam in (0, 1, 2):
             ctx.set_option(0, fam)
             buf = torch.full((G + n * fb + G,), 0xA5, dtype=torch.uint8, device="cuda")
             out = buf[G:G + n * fb].view(n, fb)
@@ -351,7 +367,7 @@ def test_four_byte_input_formats(csic, ctx, in_format):
         seen.add(fam)
         assert np.array_equal(out4, oracle.process(po4, rgba)), (W, H, f, ab, order, fmt)
         assert np.array_equal(out4, ctx.process_host(p3, np.ascontiguousarray(rgba[..., sel])))
-    assert seen == {1, 2}
+    assert 2 in seen and seen <= {1, 2, 4}
 
 
 def test_pitched_layout_any_width(csic, ctx):
@@ -449,7 +465,7 @@ def test_planar_output_and_decoder(csic, ctx):
             got = ctx.expand_planar_torch(p, torch.from_numpy(out).cuda(), to_rgb)
             ctx.synchronize(); torch.cuda.synchronize()
             assert np.array_equal(got.cpu().numpy().reshape(3, -1), want), (W, H, f, ab, order, to_rgb)
-    assert fams == {1, 2}
+    assert 2 in fams and fams <= {1, 2, 4}
     cw, chh, ob, orr = csic.planar_shape(both_params(csic, 1920, 1080, 2, 0, (8, 8, 8), 1, "CSQ", 0, 0, 4)[0])
     assert (cw, chh, ob, orr) == (960, 540, 1920 * 1080, 1920 * 1080 + 960 * 540)
 
@@ -499,5 +515,89 @@ def test_pageable_buffers_use_the_bounce_pipeline(csic, ctx):
                 for r0, r1 in ((0, oh // 3), (oh // 3, oh)):
                     ctx.process_host_band(p, rgb, out, r0, r1 - r0)
                 assert np.array_equal(out, want)
+    finally:
+        ctx.set_option(1, 0)
+
+
+def test_flex_kernel_any_alignment_pitch_and_band(csic, ctx):
+    """The flex kernel (family 4) is what dense odd-width device buffers get automatically.  It must be exact for any
+    base-pointer misalignment of input and output (sub-views of a larger buffer), odd pitches, row bands, every
+    format -- and touch nothing outside its output rows (canaries all around, pitch padding included)."""
+    import torch
+    rng = np.random.default_rng(99)
+    S = torch.cuda.current_stream().cuda_stream or 1
+    seen_auto = set()
+    for (W, H), f, ab, order, (fmt, q), inf in itertools.product(
+            [(1000, 12), (37, 9), (5, 3), (1, 4), (130, 20), (2050, 5), (4099, 3), (96, 33)], (1, 2, 4, 8),
+            [(4, 4), (2, 0), (1, 0), (2, 2)], ("CSQ", "SQC"),
+            [(0, (8, 8, 8)), (1, (6, 5, 5)), (2, (3, 3, 2)), (3, (6, 5, 5)), (3, (8, 8, 8)), (2, (8, 8, 8)), (4, (7, 6, 5))], (0, 2)):
+        if fmt == 4 and order == "SQC" and f > 1:
+            continue
+        ipb = 3 if inf == 0 else 4
+        n = 2
+        rgb = rng.integers(0, 256, size=(n, H, W, ipb), dtype=np.uint8)
+        p, po = both_params(csic, W, H, ab[0], ab[1], q, f, order, 0, 0, fmt, inf)
+        want = oracle.process(po, rgb)
+        ow, oh, orb, ofb = csic.out_shape(p)
+        case_b = order == "SQC" and f > 1
+        eligible = (not case_b) or (W % f == 0 and ow % (4 // ab[0]) == 0)
+        # (1) dense buffers at odd byte offsets inside larger allocations
+        oi, oo = int(rng.integers(0, 16)), int(rng.integers(0, 16))
+        G = 256
+        d_in = torch.empty(oi + rgb.size + 64, dtype=torch.uint8, device="cuda")
+        d_in[oi:oi + rgb.size] = torch.from_numpy(rgb.reshape(-1)).cuda()
+        buf = torch.full((G + oo + n * ofb + G,), 0xA5, dtype=torch.uint8, device="cuda")
+        ctx.set_option(0, 0)
+        ctx.process_device(p, d_in.data_ptr() + oi, n, buf.data_ptr() + G + oo, S)
+        torch.cuda.synchronize()
+        fam = ctx.last_kernel()[0]
+        seen_auto.add(fam)
+        if (oi or oo) and fmt != 4:
+            assert fam == (4 if eligible else 1), (W, H, f, ab, order, fmt, inf, fam)
+        got = buf[G + oo:G + oo + n * ofb].cpu().numpy().reshape(n, ofb)
+        assert np.array_equal(got, want), (W, H, f, ab, order, fmt, q, inf, oi, oo, fam)
+        assert bool((buf[:G + oo] == 0xA5).all()) and bool((buf[G + oo + n * ofb:] == 0xA5).all())
+        if fmt == 4:
+            continue
+        # (2) odd pitches + frame strides, flex forced; pitch padding and the bytes between frames stay untouched
+        ctx.set_option(0, 2)
+        in_pitch, out_pitch = W * ipb + int(rng.integers(0, 40)), orb + int(rng.integers(0, 40))
+        in_fs, out_fs = in_pitch * H + int(rng.integers(0, 100)), out_pitch * oh + int(rng.integers(0, 100))
+        pin = torch.full((n * in_fs,), 0x5A, dtype=torch.uint8, device="cuda")
+        pin_v = pin.view(n, in_fs)[:, :in_pitch * H].view(n, H, in_pitch)
+        pin_v[:, :, :W * ipb] = torch.from_numpy(rgb.reshape(n, H, W * ipb)).cuda()
+        pout = torch.full((n * out_fs + 64,), 0xA5, dtype=torch.uint8, device="cuda")
+        ctx.process_device_pitched(p, pin.data_ptr(), in_pitch, in_fs, n, pout.data_ptr(), out_pitch, out_fs, S)
+        torch.cuda.synchronize()
+        assert ctx.last_kernel()[0] == (4 if eligible else 1)
+        po_v = pout[:n * out_fs].view(n, out_fs)
+        rows_v = po_v[:, :out_pitch * oh].view(n, oh, out_pitch)
+        assert np.array_equal(rows_v[:, :, :orb].contiguous().view(n, ofb).cpu().numpy(), want), (W, H, f, ab, order, fmt, inf)
+        assert bool((rows_v[:, :, orb:] == 0xA5).all()) and bool((po_v[:, out_pitch * oh:] == 0xA5).all())
+        assert bool((pout[n * out_fs:] == 0xA5).all())
+        # (3) a middle band writes only its rows
+        if oh >= 3:
+            buf.fill_(0xA5)
+            ctx.process_band(p, d_in.data_ptr() + oi, n, buf.data_ptr() + G + oo, 1, oh - 2, S)
+            torch.cuda.synchronize()
+            o3 = buf[G + oo:G + oo + n * ofb].view(n, oh, orb)
+            assert np.array_equal(o3[:, 1:oh - 1].cpu().numpy(), want.reshape(n, oh, orb)[:, 1:oh - 1])
+            assert bool((o3[:, 0] == 0xA5).all()) and bool((o3[:, oh - 1] == 0xA5).all())
+        ctx.set_option(0, 0)
+    assert 4 in seen_auto
+
+
+def test_bounce_buffers_survive_staging_growth(csic, ctx):
+    """Regression: growing the device staging buffers (a larger batch after a smaller one) must not disturb the
+    pinned bounce buffers of the pageable path."""
+    rng = np.random.default_rng(3)
+    ctx.set_option(1, 8 << 20)
+    try:
+        for n in (6, 3, 24, 12, 40):
+            for (W, H, f, fmt) in ((1024, 512, 2, 3), (1024, 512, 1, 0)):
+                rgb = rng.integers(0, 256, size=(n, H, W, 3), dtype=np.uint8)
+                p, po = both_params(csic, W, H, 2, 0, (8, 8, 8), f, "CSQ", 0, 0, fmt)
+                assert np.array_equal(ctx.process_host(p, rgb), oracle.process(po, rgb, threads=4)), (n, W, H, f, fmt)
+            ctx.set_option(1, (8 << 20) * (1 + n % 3))
     finally:
         ctx.set_option(1, 0)
