@@ -3,17 +3,21 @@
 // larger buffer, bundle rows with pad slots).  Same arithmetic and the same closed-form source maps as
 // csic_rows_kernel; what differs is how bytes move:
 //
-//   load     a tile = up to 16 whole output rows (or one row segment).  Every input row span is copied into shared
-//            memory at the SAME offset modulo 16 it has in global memory, as whole 16-byte chunks through cp.async
-//            (LDGSTS.128, L2 evict-first).  The chunks that straddle a span's ends bring along a few bytes of the
-//            neighbouring pixels / rows of the same buffer; only at the two ends of the byte range the launch may touch
-//            are the < 16 edge bytes copied one by one, so the kernel is exact on sub-buffers.
-//            Two input stages per CTA: the next tile's copies are in flight while the current one is converted.
-//   compute  one thread per granule of 4 output pixels; a pixel at an arbitrary byte address is two aligned LDS.32
-//            and one funnel shift.  dp4a colour matrix, in-granule chroma hold, held rows from one pixel per row
-//            fetched with the tile (ChromaSubsampler.scala:52-65), quantise, pack -- into an aligned staging area.
-//   store    the staging area leaves as 16-byte st.global.cs words aligned on the GLOBAL address (shared-memory side
-//            re-aligned with funnel shifts), head / tail bytes with byte stores: coalesced whatever the row size.
+//   load     a tile = up to 16 whole output rows (or one row segment).  Every input row span lands in shared memory
+//            at the SAME offset modulo 16 it has in global memory, so its 16-byte-aligned hull can be fetched by the
+//            TMA engine (one cp.async.bulk per span, mbarrier complete_tx) although neither the span's start nor its
+//            length is aligned.  The hull brings along < 16 bytes of the neighbouring pixels / rows of the same
+//            buffer on each side; only at the two ends of the byte range the launch may touch is the hull clipped and
+//            the edge bytes copied one by one, so the kernel is exact on sub-buffers.  Thread 0 is the producer: it
+//            walks the CTA's tiles one ahead of the consumers (two input stages), and publishes a small descriptor
+//            per tile so that nobody else does geometry arithmetic.
+//   compute  one thread per granule of 4 output pixels; pixels at arbitrary byte addresses are aligned LDS.32 words
+//            re-aligned with funnel shifts.  dp4a colour matrix, in-granule chroma hold, held rows from one pixel per
+//            row prefetched a tile ahead (ChromaSubsampler.scala:52-65), quantise, pack -- into a staging area whose
+//            rows sit at the output's own offset modulo 16 (to the word).
+//   store    the staging area leaves as 16-byte st.global.cs words aligned on the GLOBAL address (LDS.128 plus at
+//            most one extra word and four funnel shifts), head / tail bytes with byte stores: coalesced whatever the
+//            row size.
 //
 // Reference semantics as in csic_kernels.cu's header (RGB2YCbCr.scala:33-76, ChromaSubsampler.scala:26-65,
 // SpatialDownsampler.scala:17-55, ColorQuantizer.scala:29-44, RGB2YCbCr.scala:123-132, ImageCompressorTop.scala:43-58).
@@ -32,15 +36,17 @@ namespace {
 
 constexpr int kFlexThreads = 256;
 constexpr uint32_t kFlexTileBytes = 12u * 1024u;     // input bytes of one tile
-constexpr uint32_t kCtaWideSpan = 2048u;             // row spans at least this long are copied by the whole CTA
+constexpr uint32_t kCtaWideSpan = 2048u;             // row spans at least this long are stored by the whole CTA
+constexpr uint32_t kDescBytes = 48u;
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint64_t pol) {
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) {
   asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 // issued where it is written (never sunk towards its use): the value is consumed a whole tile later
 __device__ __forceinline__ uint32_t ldg8_now(const uint8_t* p) {
@@ -48,34 +54,36 @@ __device__ __forceinline__ uint32_t ldg8_now(const uint8_t* p) {
   asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
+__device__ __forceinline__ void mbar_expect_tx_only(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
 
-// global [g, g+len) -> shared, byte i at  slot + (g & 15) + i  (slot is 16-byte aligned).  Whole 16-byte chunks go
-// through cp.async; the chunks that straddle the ends of the span are fetched whole too -- the extra bytes belong to
-// the neighbouring pixels / rows / pitch padding of the same buffer -- unless that would leave [lo, hi), the byte range
-// this launch may touch: only there (first and last span of a launch) the < 16 edge bytes are copied one by one.
-__device__ __forceinline__ void span_load(uint32_t slot, const uint8_t* __restrict__ g, uint32_t len, uint32_t t, uint32_t nthr,
-                                          uint64_t pol, uintptr_t lo, uintptr_t hi) {
+// Producer side (one thread).  global [g, g+len) -> shared, byte i at  slot + (g & 15) + i  (slot 16-byte aligned):
+// the 16-byte hull of the span goes to the TMA engine; where the hull would leave [lo, hi) -- the byte range this
+// launch may touch -- it is clipped and the < 16 edge bytes are copied by hand (first / last span of a launch only).
+__device__ __forceinline__ void span_fetch(uint32_t slot, const uint8_t* __restrict__ g, uint32_t len, uint32_t bar, uint64_t pol,
+                                           uintptr_t lo, uintptr_t hi) {
   const uintptr_t A = reinterpret_cast<uintptr_t>(g), B = A + len, base = A & ~(uintptr_t)15;
   uintptr_t start = base, end = (B + 15) & ~(uintptr_t)15;
-  if (start < lo) start += 16;                   // start > A: head bytes [A, min(start, B)) by hand
-  if (end > hi) end -= 16;                       // end < B: tail bytes by hand
-  const uint8_t* gb = reinterpret_cast<const uint8_t*>(base);
+  if (start < lo) start += 16;                   // then start > A: head bytes [A, min(start, B)) by hand
+  if (end > hi) end -= 16;                       // then end < B: tail bytes by hand
   if (end > start) {
-    const uint32_t o = (uint32_t)(start - base), nchunk = (uint32_t)(end - start) >> 4;
-    for (uint32_t c = t; c < nchunk; c += nthr) cp_async16(slot + o + (c << 4), gb + o + (c << 4), pol);
+    const uint32_t n = (uint32_t)(end - start);
+    mbar_expect_tx_only(bar, n);
+    tma_load_1d(slot + (uint32_t)(start - base), reinterpret_cast<const void*>(start), n, bar, pol);
   }
   if (start > A || end < B) {
+    const uint8_t* gb = reinterpret_cast<const uint8_t*>(base);
     const uintptr_t h1 = start > A ? (start < B ? start : B) : A;          // head is [A, h1)
     const uintptr_t t0 = end < B ? (end > h1 ? end : h1) : B;              // tail is [t0, B)
-    const uint32_t nh = (uint32_t)(h1 - A), nt = (uint32_t)(B - t0);
-    for (uint32_t i = t; i < nh + nt; i += nthr) {
-      const uint32_t off = (uint32_t)(A - base) + (i < nh ? i : (uint32_t)(t0 - A) + (i - nh));
-      sts8(slot + off, __ldg(gb + off));
-    }
+    for (uintptr_t x = A; x < h1; ++x) sts8(slot + (uint32_t)(x - base), __ldg(gb + (x - base)));
+    for (uintptr_t x = t0; x < B; ++x) sts8(slot + (uint32_t)(x - base), __ldg(gb + (x - base)));
   }
 }
 
-// shared [ssrc, ssrc+len) -> global [g, g+len): 16-byte stores aligned on the global address.
+// shared [ssrc, ssrc+len) -> global [g, g+len): 16-byte stores aligned on the global address.  The staging rows are
+// laid out so that (ssrc & 12) == (g & 12): the shared side of a chunk is then one LDS.128, plus one word when the
+// low two address bits differ.
 __device__ __forceinline__ void span_store(uint8_t* __restrict__ g, uint32_t ssrc, uint32_t len, uint32_t t,
                                            uint32_t nthr) {
   const uint32_t head = min(len, (16u - ((uint32_t)reinterpret_cast<uintptr_t>(g) & 15u)) & 15u);
@@ -84,6 +92,15 @@ __device__ __forceinline__ void span_store(uint8_t* __restrict__ g, uint32_t ssr
   const uint32_t s0 = ssrc + head, sa = s0 & ~3u, sh = (s0 & 3u) * 8u;
   if (sh == 0 && (sa & 15u) == 0) {
     for (uint32_t c = t; c < nchunk; c += nthr) __stcs(reinterpret_cast<uint4*>(g + head + (c << 4)), lds128(sa + (c << 4)));
+  } else if ((sa & 15u) == 12u) {
+    for (uint32_t c = t; c < nchunk; c += nthr) {
+      const uint32_t a = sa + (c << 4);
+      const uint32_t w0 = lds32(a);
+      const uint4 v = lds128(a + 4);
+      __stcs(reinterpret_cast<uint4*>(g + head + (c << 4)),
+             make_uint4(__funnelshift_r(w0, v.x, sh), __funnelshift_r(v.x, v.y, sh), __funnelshift_r(v.y, v.z, sh),
+                        __funnelshift_r(v.z, v.w, sh)));
+    }
   } else {
     for (uint32_t c = t; c < nchunk; c += nthr) {
       const uint32_t a = sa + (c << 4);
@@ -116,141 +133,195 @@ __device__ __forceinline__ uint32_t lds_px(uint32_t a) {
   return __funnelshift_r(lds32(b), lds32(b + 4), (a & 3u) * 8u);
 }
 
+// The four sampled pixels of a whole granule: input pixels at a, a + pxb, a + 2 pxb, a + 3 pxb (pxb = bytes between
+// sampled pixels: 3, 6, 12, 24 for RGB24 at f = 1, 2, 4, 8; 4, 8, 16, 32 for the 4-byte formats).
+__device__ __forceinline__ void load_granule_any(uint32_t a, uint32_t pxb, uint32_t (&p)[4]) {
+  const uint32_t b = a & ~3u, sh = (a & 3u) * 8u;
+  if (pxb == 3u) {             // 12 consecutive bytes: word stride 3 across lanes, conflict free
+    const uint32_t w0 = lds32(b), w1 = lds32(b + 4), w2 = lds32(b + 8), w3 = lds32(b + 12);
+    const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
+    p[0] = v0;
+    p[1] = __funnelshift_r(v0, v1, 24);
+    p[2] = __funnelshift_r(v1, v2, 16);
+    p[3] = v2 >> 8;
+  } else if (pxb == 6u) {      // 21 bytes inside six words
+    const uint32_t w0 = lds32(b), w1 = lds32(b + 4), w2 = lds32(b + 8), w3 = lds32(b + 12), w4 = lds32(b + 16), w5 = lds32(b + 20);
+    p[0] = __funnelshift_r(w0, w1, sh);                                                          // bytes 0..2
+    p[1] = __funnelshift_r(__funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), 16);        // bytes 6..8
+    p[2] = __funnelshift_r(w3, w4, sh);                                                          // bytes 12..14
+    p[3] = __funnelshift_r(__funnelshift_r(w4, w5, sh), w5 >> sh, 16);                           // bytes 18..20
+  } else {                     // pxb % 4 == 0: every pixel has the same byte phase
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[j] = __funnelshift_r(lds32(b + j * pxb), lds32(b + j * pxb + 4), sh);
+  }
+}
+
 template <int FMT> struct FlexFmt {
   // staging bytes per granule of four slots
   static constexpr uint32_t kUnit = (FMT == KF_YCC888 || FMT == KF_RGB888) ? 12u : (FMT == KF_SLOT32 ? 16u : (FMT == KF_SLOT16 ? 8u : 4u));
 };
 
-// Where a tile sits: everything the three phases need, derived from the tile index.
-struct FlexTile {
-  const uint8_t* frame;      // input frame
-  const uint8_t* src0;       // first input byte of the tile's first row span
+// Where a tile sits.  Written to shared memory by the producer before it arms the stage's mbarrier, read by every
+// thread after the barrier's phase flips.
+struct FlexDesc {
   uint32_t k, ro0, nrows;    // frame, first output row, rows
   uint32_t col0, ncols, npx; // first slot, slots (pad slots included), pixels (>= 1)
-  uint32_t len_in;           // bytes from the first sampled pixel's first byte to the last one's last byte
+  uint32_t a0;               // (address of the tile's first input byte) & 15
+  uint32_t pad[5];
 };
-__device__ __forceinline__ FlexTile flex_tile(const KPlan& P, uint32_t tile) {
-  FlexTile T;
-  const uint32_t nsplit = (uint32_t)P.nsplit, tile_px = (uint32_t)P.tile_px;
-  const uint32_t t2 = tile / nsplit, seg = tile - t2 * nsplit;
-  T.k = t2 / P.tiles_per_band;
-  const uint32_t tb = t2 - T.k * P.tiles_per_band;
-  T.ro0 = (uint32_t)P.row0 + tb * (uint32_t)P.tile_rows;
-  T.nrows = min((uint32_t)P.tile_rows, (uint32_t)(P.row0 + P.band_rows) - T.ro0);
-  T.col0 = seg * tile_px;
-  T.ncols = min(tile_px, (uint32_t)P.slots_per_row - T.col0);
-  T.npx = min((uint32_t)P.Wo, T.col0 + T.ncols) - T.col0;
-  const uint32_t pxb = (uint32_t)P.f * (uint32_t)P.in_px_bytes;
-  T.len_in = (T.npx - 1u) * pxb + (uint32_t)P.in_px_bytes;
-  T.frame = P.in + (uint64_t)T.k * P.in_frame_bytes;
-  T.src0 = T.frame + (uint64_t)(T.ro0 * (uint32_t)P.row_step) * P.in_row_bytes + (uint64_t)T.col0 * pxb;
-  return T;
-}
+static_assert(sizeof(FlexDesc) == kDescBytes, "kDescBytes out of sync");
 
 }  // namespace
 
 template <int FMT, bool TRUNC>
 __global__ void __launch_bounds__(kFlexThreads) csic_flex_kernel(const __grid_constant__ KPlan P) {
-  extern __shared__ __align__(16) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   constexpr uint32_t kUnit = FlexFmt<FMT>::kUnit, kOpx = kUnit / 4u;
   const uint32_t tid = threadIdx.x, NT = blockDim.x;
   const uint32_t sbase = smem_u32(smem), out_s = sbase + P.out_buf_off, held_base = sbase + P.meta_off;
+  const uint32_t bar0 = sbase + P.bar_off;
+  const FlexDesc* descs = reinterpret_cast<const FlexDesc*>(smem + P.bar_off + 16u);
   const uint32_t in_stage = P.stage_stride * (uint32_t)P.tile_rows + 32u;     // bytes of one input stage
-  const uint64_t pol = policy_evict_first();
   const uint32_t ipb = (uint32_t)P.in_px_bytes, f = (uint32_t)P.f, pxb = f * ipb;
   const uint32_t nsplit = (uint32_t)P.nsplit;
   const uint32_t hfe = (uint32_t)P.hfe;
   const bool vhold = P.vf == 2;
   const uint64_t rstep = (uint64_t)(uint32_t)P.row_step * P.in_row_bytes;
-  // the byte range of the input this launch may touch (see span_load)
-  const uintptr_t lim_lo = reinterpret_cast<uintptr_t>(P.in) + (uint64_t)((uint32_t)P.row0 * (uint32_t)P.row_step) * P.in_row_bytes;
-  const uintptr_t lim_hi = reinterpret_cast<uintptr_t>(P.in) + (uint64_t)(P.n_frames - 1u) * P.in_frame_bytes +
-                           (uint64_t)((uint32_t)(P.row0 + P.band_rows - 1) * (uint32_t)P.row_step) * P.in_row_bytes +
-                           ((uint32_t)P.Wo - 1u) * pxb + ipb;
+  const uint32_t n_my = (P.n_tiles > blockIdx.x) ? (P.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (n_my == 0) return;
   // quantiser masks / shifts
   const uint32_t my = P.qmask & 0xFFu, mcb = (P.qmask >> 8) & 0xFFu, mcr = (P.qmask >> 16) & 0xFFu;
   const uint32_t qm0 = my | (mcb << 8) | (mcr << 16) | (my << 24);
   const uint32_t qm1 = mcb | (mcr << 8) | (my << 16) | (mcb << 24);
   const uint32_t qm2 = mcr | (my << 8) | (mcb << 16) | (mcr << 24);
   const int shy = 8 + P.sy, shb = 8 + P.scb, shr = 8 + P.scr, ly = P.cb_bits + P.cr_bits, lb = P.cr_bits;
+  const bool q8 = FMT == KF_SLOT32 && P.sy == 0 && P.scb == 0 && P.scr == 0;
   const uint32_t vs_sh = P.planar_vs == 2 ? 1u : 0u, hs_sh = P.planar_hs == 4 ? 2u : (P.planar_hs == 2 ? 1u : 0u);
 
   // Input rows of a tile land in stage s at  in(s) + j * rs_mul + ((a0 + j * rs_add) & 15),  a0 = src0 & 15.
   const uint32_t rs_mul = P.in_dense ? P.in_row_bytes : P.stage_stride;
   const uint32_t rs_add = P.in_dense ? 0u : ((uint32_t)rstep & 15u);
 
-  // Hands the tile's input to the copy engine (cp.async) and fetches the pixel a held row replays into registers;
-  // nothing here waits for memory.
-  uint32_t h0 = 0, h1 = 0, h2 = 0, hvalid = 0;
-  auto issue = [&](const FlexTile& T, uint32_t s) {
-    const uint32_t in_s = sbase + s * in_stage;
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8u, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+
+  // ---- producer (thread 0): tile (pk, ptb, pseg) is the next one to hand to the TMA engine -----------------------
+  uint32_t pk = 0, ptb = 0, pseg = 0, dk = 0, dtb = 0, dseg = 0;
+  uintptr_t lim_lo = 0, lim_hi = 0;
+  uint64_t pol = 0;
+  if (tid == 0) {
+    pol = policy_evict_first();
+    const uint32_t t2 = blockIdx.x / nsplit, g2 = gridDim.x / nsplit;
+    pseg = blockIdx.x - t2 * nsplit; pk = t2 / P.tiles_per_band; ptb = t2 - pk * P.tiles_per_band;
+    dseg = gridDim.x - g2 * nsplit; dk = g2 / P.tiles_per_band; dtb = g2 - dk * P.tiles_per_band;
+    // the byte range of the input this launch may touch (see span_fetch)
+    lim_lo = reinterpret_cast<uintptr_t>(P.in) + (uint64_t)((uint32_t)P.row0 * (uint32_t)P.row_step) * P.in_row_bytes;
+    lim_hi = reinterpret_cast<uintptr_t>(P.in) + (uint64_t)(P.n_frames - 1u) * P.in_frame_bytes +
+             (uint64_t)((uint32_t)(P.row0 + P.band_rows - 1) * (uint32_t)P.row_step) * P.in_row_bytes + ((uint32_t)P.Wo - 1u) * pxb + ipb;
+  }
+  auto produce = [&](uint32_t j) {       // thread 0 only
+    const uint32_t s = j & 1u, bar = bar0 + s * 8u, in_s = sbase + s * in_stage;
+    FlexDesc* d = reinterpret_cast<FlexDesc*>(smem + P.bar_off + 16u) + s;
+    const uint32_t ro0 = (uint32_t)P.row0 + ptb * (uint32_t)P.tile_rows;
+    const uint32_t nrows = min((uint32_t)P.tile_rows, (uint32_t)(P.row0 + P.band_rows) - ro0);
+    const uint32_t col0 = pseg * (uint32_t)P.tile_px;
+    const uint32_t ncols = min((uint32_t)P.tile_px, (uint32_t)P.slots_per_row - col0);
+    const uint32_t npx = min((uint32_t)P.Wo, col0 + ncols) - col0;
+    const uint32_t len_in = (npx - 1u) * pxb + ipb;    // first byte of the first .. last byte of the last sampled pixel
+    const uint8_t* src0 = P.in + (uint64_t)pk * P.in_frame_bytes + (uint64_t)(ro0 * (uint32_t)P.row_step) * P.in_row_bytes + (uint64_t)col0 * pxb;
+    d->k = pk; d->ro0 = ro0; d->nrows = nrows; d->col0 = col0; d->ncols = ncols; d->npx = npx;
+    d->a0 = (uint32_t)reinterpret_cast<uintptr_t>(src0) & 15u;
     if (P.in_dense) {          // consecutive rows are contiguous in memory: one span
-      span_load(in_s, T.src0, (T.nrows - 1u) * P.in_row_bytes + T.len_in, tid, NT, pol, lim_lo, lim_hi);
+      span_fetch(in_s, src0, (nrows - 1u) * P.in_row_bytes + len_in, bar, pol, lim_lo, lim_hi);
     } else {
-      for_each_span(T.nrows, T.len_in, [&](uint32_t j, uint32_t t, uint32_t n) {
-        span_load(in_s + j * rs_mul, T.src0 + (uint64_t)j * rstep, T.len_in, t, n, pol, lim_lo, lim_hi);
-      });
+      for (uint32_t r = 0; r < nrows; ++r) span_fetch(in_s + r * rs_mul, src0 + (uint64_t)r * rstep, len_in, bar, pol, lim_lo, lim_hi);
     }
+    mbar_arrive(bar);          // releases the descriptor and the hand-copied edge bytes; the phase completes with the last byte
+    // advance by gridDim.x tiles in (frame, row tile, segment) coordinates
+    pseg += dseg;
+    uint32_t c = pseg >= nsplit ? 1u : 0u;
+    pseg -= c * nsplit;
+    ptb += dtb + c;
+    c = ptb >= P.tiles_per_band ? 1u : 0u;
+    ptb -= c * P.tiles_per_band;
+    pk += dk + c;
+  };
+
+  // The pixel whose chroma a held row replays (ChromaSubsampler.scala:62-65), fetched into registers one tile ahead.
+  uint32_t h0 = 0, h1 = 0, h2 = 0, hvalid = 0;
+  auto prefetch_held = [&](const FlexDesc& D) {
     hvalid = 0;
-    if (vhold && tid < T.nrows) {   // the pixel whose chroma a held row replays (ChromaSubsampler.scala:62-65)
-      const uint32_t ro = T.ro0 + tid;
+    if (vhold && tid < D.nrows) {
+      const uint32_t ro = D.ro0 + tid;
+      const uint8_t* frame = P.in + (uint64_t)D.k * P.in_frame_bytes;
       const uint8_t* hp = nullptr;
       if (!P.case_b) {
-        if (f == 1 && (ro & 1u)) hp = T.frame + (uint64_t)(ro - 1u) * P.in_row_bytes + (uint32_t)P.last_sample_col * ipb;
+        if (f == 1 && (ro & 1u)) hp = frame + (uint64_t)(ro - 1u) * P.in_row_bytes + (uint32_t)P.last_sample_col * ipb;
       } else {
         const uint32_t line = ro / f;        // W == f * Wo: one counter line spans f output rows
         if (line & 1u) {
           const uint32_t srow = (line - 1u) * f + P.caseb_row_add;
-          hp = T.frame + (uint64_t)(srow * (uint32_t)P.row_step) * P.in_row_bytes + P.caseb_col_bytes;
+          hp = frame + (uint64_t)(srow * (uint32_t)P.row_step) * P.in_row_bytes + P.caseb_col_bytes;
         }
       }
       if (hp) { h0 = ldg8_now(hp); h1 = ldg8_now(hp + 1); h2 = ldg8_now(hp + 2); hvalid = 0x80000000u; }
     }
-    cp_async_commit();
   };
-  auto publish_held = [&](uint32_t s) {      // first use of the registers `issue` filled
-    if (vhold && tid < (uint32_t)P.tile_rows) sts32(held_base + (s * (uint32_t)kMaxTileRows + tid) * 4u, hvalid ? (hvalid | h0 | (h1 << 8) | (h2 << 16)) : 0u);
+  auto publish_held = [&](uint32_t s) {      // first use of the registers prefetch_held filled
+    if (vhold && tid < (uint32_t)P.tile_rows)
+      sts32(held_base + (s * (uint32_t)kMaxTileRows + tid) * 4u, hvalid ? (hvalid | h0 | (h1 << 8) | (h2 << 16)) : 0u);
   };
 
-  uint32_t tile = blockIdx.x;
-  if (tile >= P.n_tiles) return;
-  FlexTile T = flex_tile(P, tile);
-  issue(T, 0);
+  __syncthreads();                 // mbarriers initialised
+  if (tid == 0) produce(0);
+  mbar_wait(bar0, 0);              // also makes descriptor 0 visible
+  prefetch_held(descs[0]);
   publish_held(0);
-  for (uint32_t it = 0;; ++it) {
+
+  for (uint32_t it = 0; it < n_my; ++it) {
     const uint32_t s = it & 1u;
-    const uint32_t next = tile + gridDim.x;
-    const bool has_next = next < P.n_tiles;
-    FlexTile Tn;
-    if (has_next) {
-      Tn = flex_tile(P, next);
-      issue(Tn, s ^ 1u);       // stage s^1 was last read two barriers ago
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
+    const bool has_next = it + 1u < n_my;
+    // stage s^1 and its descriptor were last read before the previous iteration's middle barrier
+    if (tid == 0 && has_next) produce(it + 1u);
+    mbar_wait(bar0 + s * 8u, (it >> 1) & 1u);
+    const FlexDesc D = descs[s];
+    __syncthreads();               // the previous tile has left the staging area; descriptor s^1 is visible
+    if (has_next) prefetch_held(descs[s ^ 1u]);
 
     // ---- compute -------------------------------------------------------------------------------------------
     const uint32_t in_s = sbase + s * in_stage, held_s = held_base + s * (uint32_t)kMaxTileRows * 4u;
-    const uint32_t a0 = (uint32_t)reinterpret_cast<uintptr_t>(T.src0) & 15u;
-    const uint32_t gpr = (T.ncols + 3u) >> 2;                  // granules per row
-    const uint32_t n_gran = T.nrows * gpr, srow = gpr * kUnit;
+    const uint32_t gpr = (D.ncols + 3u) >> 2;                  // granules per row
+    const uint32_t n_gran = D.nrows * gpr, srow = gpr * kUnit;
     const uint32_t gpr_magic = gpr > 1u ? 0xFFFFFFFFu / gpr + 1u : 0u;   // q / gpr == umulhi(q, magic) for q < 65536
+    const uint32_t row_out = D.ncols * kOpx;
+    uint8_t* fout = P.out + (uint64_t)D.k * P.out_frame_bytes;
+    uint8_t* obase = fout + (uint64_t)D.ro0 * P.out_row_bytes + (uint64_t)D.col0 * kOpx;
+    // staging row j sits at  out_s + j * st_mul + ((oa0 + j * st_add) & 12):  the output row's own offset modulo 16,
+    // rounded down to a word
+    const bool out_one = P.out_dense && nsplit == 1 && row_out == srow;   // whole dense rows: one packed span
+    const uint32_t oa0 = (uint32_t)reinterpret_cast<uintptr_t>(obase);
+    const uint32_t st_mul = out_one ? srow : srow + 16u, st_add = out_one ? 0u : P.out_row_bytes;
     // PLANAR: chroma rows of the tile are the output rows with ro % vs == 0
-    const uint32_t c_first = (T.ro0 + (1u << vs_sh) - 1u) >> vs_sh;
-    const uint32_t c_last1 = ((T.ro0 + T.nrows - 1u) >> vs_sh) + 1u;
+    const uint32_t c_first = (D.ro0 + (1u << vs_sh) - 1u) >> vs_sh;
+    const uint32_t c_last1 = ((D.ro0 + D.nrows - 1u) >> vs_sh) + 1u;
     const uint32_t nrc = (FMT == KF_PLANAR && c_last1 > c_first) ? c_last1 - c_first : 0u;
-    const uint32_t ccols = (T.npx + (1u << hs_sh) - 1u) >> hs_sh;
-    const uint32_t cb_s = out_s + T.nrows * srow, cr_s = cb_s + nrc * ccols;
-    const uint32_t last_px = T.npx - 1u;
+    const uint32_t ccols = (D.npx + (1u << hs_sh) - 1u) >> hs_sh;
+    const uint32_t cb_s = out_s + D.nrows * st_mul + 16u, cr_s = cb_s + nrc * ccols;
+    const uint32_t last_px = D.npx - 1u;
     for (uint32_t q = tid; q < n_gran; q += NT) {
       const uint32_t row = gpr > 1u ? __umulhi(q, gpr_magic) : q, g = q - row * gpr;
-      const uint32_t rs = in_s + row * rs_mul + ((a0 + row * rs_add) & 15u);
+      const uint32_t rs = in_s + row * rs_mul + ((D.a0 + row * rs_add) & 15u);
       const uint32_t c = g * 4u;
       uint32_t p[4], dy[4], xb[4], xr[4];
+      if (c + 3u <= last_px) {
+        load_granule_any(rs + c * pxb, pxb, p);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) p[j] = lds_px(rs + min(c + j, last_px) * pxb);
+        for (int j = 0; j < 4; ++j) p[j] = lds_px(rs + min(c + j, last_px) * pxb);
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) dy[j] = fwd_y16(p[j], P.coef_y);
       const uint32_t hv = vhold ? lds32(held_s + row * 4u) : 0u;
@@ -268,7 +339,7 @@ __global__ void __launch_bounds__(kFlexThreads) csic_flex_kernel(const __grid_co
         if (hfe == 1) { xb[3] = fwd_nc16<TRUNC>(p[3], P.coef_ncb); xr[3] = fwd_nc16<TRUNC>(p[3], P.coef_ncr); }
         else { xb[3] = xb[2]; xr[3] = xr[2]; }
       }
-      const uint32_t so = out_s + row * srow + g * kUnit;
+      const uint32_t so = out_s + row * st_mul + ((oa0 + row * st_add) & 12u) + g * kUnit;
       if (FMT == KF_YCC888) {
         // byte 1 of dy is Y, byte 1 of xb/xr is ~Cb/~Cr: gather with PRMT, flip and quantise per word
         uint32_t t, u;
@@ -290,7 +361,7 @@ __global__ void __launch_bounds__(kFlexThreads) csic_flex_kernel(const __grid_co
         const uint32_t my4 = my * 0x01010101u;
         sts32(so, __byte_perm(__byte_perm(dy[0], dy[1], 0x0051), __byte_perm(dy[2], dy[3], 0x0051), 0x5410) & my4);
         if (!hv) {               // a sampled line: its sample points go to the chroma planes (hs == hfe here)
-          const uint32_t crow = (((T.ro0 + row) >> vs_sh) - c_first) * ccols + (c >> hs_sh);
+          const uint32_t crow = (((D.ro0 + row) >> vs_sh) - c_first) * ccols + (c >> hs_sh);
           if (hfe == 1) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -304,31 +375,43 @@ __global__ void __launch_bounds__(kFlexThreads) csic_flex_kernel(const __grid_co
         }
       } else {
         uint32_t v[4];
+        if (q8) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          v[j] = ((dy[j] >> shy) << ly) | (((xb[j] ^ 0xFFFFu) >> shb) << lb) | ((xr[j] ^ 0xFFFFu) >> shr);
-          if (c + j > last_px) v[j] = 0u;       // the row's zero pad slots
+          for (int j = 0; j < 4; ++j)   // (Cr, Cb, Y, 0): dy < 65536 so its byte 3 is the zero pad
+            v[j] = __byte_perm(__byte_perm(xr[j], xb[j], 0x0051), dy[j], 0x7510) ^ 0x0000FFFFu;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            v[j] = ((dy[j] >> shy) << ly) | (((xb[j] ^ 0xFFFFu) >> shb) << lb) | ((xr[j] ^ 0xFFFFu) >> shr);
         }
-        if (FMT == KF_SLOT32) { sts32(so, v[0]); sts32(so + 4, v[1]); sts32(so + 8, v[2]); sts32(so + 12, v[3]); }
-        else if (FMT == KF_SLOT16) { sts32(so, v[0] | (v[1] << 16)); sts32(so + 4, v[2] | (v[3] << 16)); }
-        else sts32(so, v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
+        if (c + 3u > last_px) {        // the row's zero pad slots
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (c + j > last_px) v[j] = 0u;
+        }
+        if (FMT == KF_SLOT32) {
+          if ((so & 15u) == 0) sts128(so, v[0], v[1], v[2], v[3]);
+          else if ((so & 7u) == 0) { sts64(so, v[0], v[1]); sts64(so + 8, v[2], v[3]); }
+          else { sts32(so, v[0]); sts32(so + 4, v[1]); sts32(so + 8, v[2]); sts32(so + 12, v[3]); }
+        } else if (FMT == KF_SLOT16) {
+          if ((so & 7u) == 0) sts64(so, v[0] | (v[1] << 16), v[2] | (v[3] << 16));
+          else { sts32(so, v[0] | (v[1] << 16)); sts32(so + 4, v[2] | (v[3] << 16)); }
+        } else {
+          sts32(so, v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
+        }
       }
     }
-    __syncthreads();
+    __syncthreads();               // staging complete; every read of input stage s and its held words is done
 
     // ---- store ---------------------------------------------------------------------------------------------
-    uint8_t* fout = P.out + (uint64_t)T.k * P.out_frame_bytes;
-    uint8_t* obase = fout + (uint64_t)T.ro0 * P.out_row_bytes + (uint64_t)T.col0 * kOpx;
-    const uint32_t row_out = T.ncols * kOpx;
-    if (P.out_dense && nsplit == 1 && row_out == srow) {      // whole dense rows, packed in the staging area: one span
-      span_store(obase, out_s, T.nrows * row_out, tid, NT);
+    if (out_one) {
+      span_store(obase, out_s + (oa0 & 12u), D.nrows * row_out, tid, NT);
     } else {
-      for_each_span(T.nrows, row_out, [&](uint32_t j, uint32_t t, uint32_t n) {
-        span_store(obase + (uint64_t)j * P.out_row_bytes, out_s + j * srow, row_out, t, n);
+      for_each_span(D.nrows, row_out, [&](uint32_t j, uint32_t t, uint32_t n) {
+        span_store(obase + (uint64_t)j * P.out_row_bytes, out_s + j * st_mul + ((oa0 + j * st_add) & 12u), row_out, t, n);
       });
     }
     if (FMT == KF_PLANAR && nrc) {
-      const uint64_t coff = (uint64_t)c_first * (uint32_t)P.planar_cw + (T.col0 >> hs_sh);
+      const uint64_t coff = (uint64_t)c_first * (uint32_t)P.planar_cw + (D.col0 >> hs_sh);
       uint8_t* cb_g = fout + P.planar_cb_off + coff;
       uint8_t* cr_g = fout + P.planar_cr_off + coff;
       if (nsplit == 1) {                                       // ccols == planar_cw: chroma rows are contiguous
@@ -341,12 +424,8 @@ __global__ void __launch_bounds__(kFlexThreads) csic_flex_kernel(const __grid_co
         });
       }
     }
-    if (!has_next) break;
-    // The held words of the next tile: stage s^1's were last read in the compute phase two barriers back; the next
-    // compute phase starts behind the next barrier.  The staging area is rewritten only behind that barrier too.
-    publish_held(s ^ 1u);
-    T = Tn;
-    tile = next;
+    // held words of the next tile: stage s^1's were last read before the previous iteration's middle barrier
+    if (has_next) publish_held(s ^ 1u);
   }
 }
 
@@ -391,16 +470,19 @@ bool plan_flex_kernel(KPlan& k, int sm_count, size_t max_smem_optin) {
   k.out_dense = k.out_row_bytes == dense_out_row ? 1 : 0;
 
   auto up16 = [](uint32_t v) { return (v + 15u) & ~15u; };
+  auto up128 = [](uint32_t v) { return (v + 127u) & ~127u; };
   k.stage_stride = up16((k.in_dense ? std::max(len_in_max, k.in_row_bytes) : len_in_max) + 15u) + 16u;
-  const uint32_t in_bytes = 2u * ((uint32_t)rows * k.stage_stride + 32u);   // two stages; + slack: lds_px reads one word ahead
-  uint32_t stage_bytes = (uint32_t)rows * ((uint32_t)k.tile_px / 4u) * unit;
+  const uint32_t in_bytes = 2u * ((uint32_t)rows * k.stage_stride + 32u);   // two stages; + slack: pixel loads read one word ahead
+  uint32_t stage_bytes = (uint32_t)rows * (((uint32_t)k.tile_px / 4u) * unit + 16u) + 16u;   // rows at their own offset mod 16
   if (planar) stage_bytes += 2u * (uint32_t)(rows / std::max(1, k.planar_vs) + 1) * (uint32_t)k.tile_px;
-  k.out_buf_off = in_bytes;
+  k.out_buf_off = up128(in_bytes);
   k.out_buf_stride = up16(stage_bytes + 32u);                               // + slack: span_store reads one word ahead
-  k.meta_off = k.out_buf_off + k.out_buf_stride;
-  k.smem_bytes = k.meta_off + 2u * (uint32_t)kMaxTileRows * 4u;           // held words of both stages
+  k.meta_off = k.out_buf_off + k.out_buf_stride;                            // held words of both stages
+  k.bar_off = up128(k.meta_off + 2u * (uint32_t)kMaxTileRows * 4u);         // two mbarriers, then two descriptors
+  k.smem_bytes = k.bar_off + 16u + 2u * kDescBytes;
   if (k.smem_bytes > max_smem_optin) return false;
   k.block_threads = kFlexThreads;
+  k.stages = 2;
   k.ctas_per_sm = (int32_t)std::max<uint32_t>(1u, std::min<uint32_t>(std::min<uint32_t>(8u, 2048u / kFlexThreads),
                                                                       227u * 1024u / (k.smem_bytes + 1024u)));
   return true;
