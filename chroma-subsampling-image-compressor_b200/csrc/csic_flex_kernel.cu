@@ -8,13 +8,14 @@
 //            TMA engine (one cp.async.bulk per span, mbarrier complete_tx) although neither the span's start nor its
 //            length is aligned.  The hull brings along < 16 bytes of the neighbouring pixels / rows of the same
 //            buffer on each side; only at the two ends of the byte range the launch may touch is the hull clipped and
-//            the edge bytes copied one by one, so the kernel is exact on sub-buffers.  Thread 0 is the producer: it
-//            walks the CTA's tiles one ahead of the consumers (two input stages), and publishes a small descriptor
-//            per tile so that nobody else does geometry arithmetic.
+//            the edge bytes copied one by one, so the kernel is exact on sub-buffers.  A dedicated producer warp walks
+//            the CTA's tiles ahead of the consumer warps (two input stages, full / empty mbarriers), fetches the
+//            pixel a held row replays, and publishes a small descriptor per tile so that nobody else does geometry
+//            arithmetic.
 //   compute  one thread per granule of 4 output pixels; pixels at arbitrary byte addresses are aligned LDS.32 words
 //            re-aligned with funnel shifts.  dp4a colour matrix, in-granule chroma hold, held rows from one pixel per
-//            row prefetched a tile ahead (ChromaSubsampler.scala:52-65), quantise, pack -- into a staging area whose
-//            rows sit at the output's own offset modulo 16 (to the word).
+//            row (ChromaSubsampler.scala:52-65), quantise, pack -- into a staging area whose rows sit at the output's
+//            own offset modulo 16 (to the word).
 //   store    the staging area leaves as 16-byte st.global.cs words aligned on the GLOBAL address (LDS.128 plus at
 //            most one extra word and four funnel shifts), head / tail bytes with byte stores: coalesced whatever the
 //            row size.
@@ -34,7 +35,7 @@ namespace csic {
 
 namespace {
 
-constexpr int kFlexThreads = 256;
+constexpr int kFlexThreads = 256;                    // 7 consumer warps + 1 producer warp
 constexpr uint32_t kFlexTileBytes = 12u * 1024u;     // input bytes of one tile
 constexpr uint32_t kCtaWideSpan = 2048u;             // row spans at least this long are stored by the whole CTA
 constexpr uint32_t kDescBytes = 48u;
@@ -118,12 +119,12 @@ __device__ __forceinline__ void span_store(uint8_t* __restrict__ g, uint32_t ssr
 
 // `n` row spans of `len` bytes: one after the other with the whole CTA when they are long, one warp per span when short.
 template <typename F>
-__device__ __forceinline__ void for_each_span(uint32_t n, uint32_t len, F&& fn) {
-  const uint32_t tid = threadIdx.x, NT = blockDim.x;
+__device__ __forceinline__ void for_each_span(uint32_t n, uint32_t len, uint32_t NC, F&& fn) {
+  const uint32_t tid = threadIdx.x;
   if (len >= kCtaWideSpan || n == 1) {
-    for (uint32_t j = 0; j < n; ++j) fn(j, tid, NT);
+    for (uint32_t j = 0; j < n; ++j) fn(j, tid, NC);
   } else {
-    for (uint32_t j = tid >> 5; j < n; j += NT >> 5) fn(j, tid & 31u, 32u);
+    for (uint32_t j = tid >> 5; j < n; j += NC >> 5) fn(j, tid & 31u, 32u);
   }
 }
 
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(kFlexThreads) csic_flex_kernel(const __grid_co
   const uint32_t tid = threadIdx.x, NT = blockDim.x;
   const uint32_t sbase = smem_u32(smem), out_s = sbase + P.out_buf_off, held_base = sbase + P.meta_off;
   const uint32_t bar0 = sbase + P.bar_off;
-  const FlexDesc* descs = reinterpret_cast<const FlexDesc*>(smem + P.bar_off + 16u);
+  const FlexDesc* descs = reinterpret_cast<const FlexDesc*>(smem + P.bar_off + 32u);
   const uint32_t in_stage = P.stage_stride * (uint32_t)P.tile_rows + 32u;     // bytes of one input stage
   const uint32_t ipb = (uint32_t)P.in_px_bytes, f = (uint32_t)P.f, pxb = f * ipb;
   const uint32_t nsplit = (uint32_t)P.nsplit;
@@ -202,94 +203,90 @@ __global__ void __launch_bounds__(kFlexThreads) csic_flex_kernel(const __grid_co
   const uint32_t rs_mul = P.in_dense ? P.in_row_bytes : P.stage_stride;
   const uint32_t rs_add = P.in_dense ? 0u : ((uint32_t)rstep & 15u);
 
+  const uint32_t NC = NT - 32u;    // consumer threads; the last warp is the producer
+  const uint32_t full0 = bar0, empty0 = bar0 + 16u;
   if (tid == 0) {
-    mbar_init(bar0, 1);
-    mbar_init(bar0 + 8u, 1);
+    mbar_init(full0, 1); mbar_init(full0 + 8u, 1);       // the producer's arrive (+ the TMA byte count)
+    mbar_init(empty0, 1); mbar_init(empty0 + 8u, 1);     // one consumer's arrive, behind the consumers' barrier
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncthreads();
 
-  // ---- producer (thread 0): tile (pk, ptb, pseg) is the next one to hand to the TMA engine -----------------------
-  uint32_t pk = 0, ptb = 0, pseg = 0, dk = 0, dtb = 0, dseg = 0;
-  uintptr_t lim_lo = 0, lim_hi = 0;
-  uint64_t pol = 0;
-  if (tid == 0) {
-    pol = policy_evict_first();
+  // ============================== producer warp ==============================================================
+  // Walks this CTA's tiles two stages ahead of the consumers.  All lanes track the geometry; lane 0 describes the
+  // tile and hands its row spans to the TMA engine, lanes 0..nrows-1 fetch the pixel a held row replays.
+  if (tid >= NC) {
+    const uint32_t lane = tid - NC;
+    const uint64_t pol = policy_evict_first();
     const uint32_t t2 = blockIdx.x / nsplit, g2 = gridDim.x / nsplit;
-    pseg = blockIdx.x - t2 * nsplit; pk = t2 / P.tiles_per_band; ptb = t2 - pk * P.tiles_per_band;
-    dseg = gridDim.x - g2 * nsplit; dk = g2 / P.tiles_per_band; dtb = g2 - dk * P.tiles_per_band;
+    uint32_t pseg = blockIdx.x - t2 * nsplit, pk = t2 / P.tiles_per_band, ptb = t2 - pk * P.tiles_per_band;
+    const uint32_t dseg = gridDim.x - g2 * nsplit, dk = g2 / P.tiles_per_band, dtb = g2 - dk * P.tiles_per_band;
     // the byte range of the input this launch may touch (see span_fetch)
-    lim_lo = reinterpret_cast<uintptr_t>(P.in) + (uint64_t)((uint32_t)P.row0 * (uint32_t)P.row_step) * P.in_row_bytes;
-    lim_hi = reinterpret_cast<uintptr_t>(P.in) + (uint64_t)(P.n_frames - 1u) * P.in_frame_bytes +
-             (uint64_t)((uint32_t)(P.row0 + P.band_rows - 1) * (uint32_t)P.row_step) * P.in_row_bytes + ((uint32_t)P.Wo - 1u) * pxb + ipb;
-  }
-  auto produce = [&](uint32_t j) {       // thread 0 only
-    const uint32_t s = j & 1u, bar = bar0 + s * 8u, in_s = sbase + s * in_stage;
-    FlexDesc* d = reinterpret_cast<FlexDesc*>(smem + P.bar_off + 16u) + s;
-    const uint32_t ro0 = (uint32_t)P.row0 + ptb * (uint32_t)P.tile_rows;
-    const uint32_t nrows = min((uint32_t)P.tile_rows, (uint32_t)(P.row0 + P.band_rows) - ro0);
-    const uint32_t col0 = pseg * (uint32_t)P.tile_px;
-    const uint32_t ncols = min((uint32_t)P.tile_px, (uint32_t)P.slots_per_row - col0);
-    const uint32_t npx = min((uint32_t)P.Wo, col0 + ncols) - col0;
-    const uint32_t len_in = (npx - 1u) * pxb + ipb;    // first byte of the first .. last byte of the last sampled pixel
-    const uint8_t* src0 = P.in + (uint64_t)pk * P.in_frame_bytes + (uint64_t)(ro0 * (uint32_t)P.row_step) * P.in_row_bytes + (uint64_t)col0 * pxb;
-    d->k = pk; d->ro0 = ro0; d->nrows = nrows; d->col0 = col0; d->ncols = ncols; d->npx = npx;
-    d->a0 = (uint32_t)reinterpret_cast<uintptr_t>(src0) & 15u;
-    if (P.in_dense) {          // consecutive rows are contiguous in memory: one span
-      span_fetch(in_s, src0, (nrows - 1u) * P.in_row_bytes + len_in, bar, pol, lim_lo, lim_hi);
-    } else {
-      for (uint32_t r = 0; r < nrows; ++r) span_fetch(in_s + r * rs_mul, src0 + (uint64_t)r * rstep, len_in, bar, pol, lim_lo, lim_hi);
-    }
-    mbar_arrive(bar);          // releases the descriptor and the hand-copied edge bytes; the phase completes with the last byte
-    // advance by gridDim.x tiles in (frame, row tile, segment) coordinates
-    pseg += dseg;
-    uint32_t c = pseg >= nsplit ? 1u : 0u;
-    pseg -= c * nsplit;
-    ptb += dtb + c;
-    c = ptb >= P.tiles_per_band ? 1u : 0u;
-    ptb -= c * P.tiles_per_band;
-    pk += dk + c;
-  };
-
-  // The pixel whose chroma a held row replays (ChromaSubsampler.scala:62-65), fetched into registers one tile ahead.
-  uint32_t h0 = 0, h1 = 0, h2 = 0, hvalid = 0;
-  auto prefetch_held = [&](const FlexDesc& D) {
-    hvalid = 0;
-    if (vhold && tid < D.nrows) {
-      const uint32_t ro = D.ro0 + tid;
-      const uint8_t* frame = P.in + (uint64_t)D.k * P.in_frame_bytes;
-      const uint8_t* hp = nullptr;
-      if (!P.case_b) {
-        if (f == 1 && (ro & 1u)) hp = frame + (uint64_t)(ro - 1u) * P.in_row_bytes + (uint32_t)P.last_sample_col * ipb;
-      } else {
-        const uint32_t line = ro / f;        // W == f * Wo: one counter line spans f output rows
-        if (line & 1u) {
-          const uint32_t srow = (line - 1u) * f + P.caseb_row_add;
-          hp = frame + (uint64_t)(srow * (uint32_t)P.row_step) * P.in_row_bytes + P.caseb_col_bytes;
+    const uintptr_t lim_lo = reinterpret_cast<uintptr_t>(P.in) + (uint64_t)((uint32_t)P.row0 * (uint32_t)P.row_step) * P.in_row_bytes;
+    const uintptr_t lim_hi = reinterpret_cast<uintptr_t>(P.in) + (uint64_t)(P.n_frames - 1u) * P.in_frame_bytes +
+                             (uint64_t)((uint32_t)(P.row0 + P.band_rows - 1) * (uint32_t)P.row_step) * P.in_row_bytes +
+                             ((uint32_t)P.Wo - 1u) * pxb + ipb;
+    for (uint32_t j = 0; j < n_my; ++j) {
+      const uint32_t s = j & 1u, bar = full0 + s * 8u, in_s = sbase + s * in_stage;
+      if (j >= 2u) mbar_wait(empty0 + s * 8u, ((j >> 1) - 1u) & 1u);       // the consumers drained the previous use
+      FlexDesc* d = reinterpret_cast<FlexDesc*>(smem + P.bar_off + 32u) + s;
+      const uint32_t ro0 = (uint32_t)P.row0 + ptb * (uint32_t)P.tile_rows;
+      const uint32_t nrows = min((uint32_t)P.tile_rows, (uint32_t)(P.row0 + P.band_rows) - ro0);
+      const uint32_t col0 = pseg * (uint32_t)P.tile_px;
+      const uint32_t ncols = min((uint32_t)P.tile_px, (uint32_t)P.slots_per_row - col0);
+      const uint32_t npx = min((uint32_t)P.Wo, col0 + ncols) - col0;
+      const uint32_t len_in = (npx - 1u) * pxb + ipb;  // first byte of the first .. last byte of the last sampled pixel
+      const uint8_t* frame = P.in + (uint64_t)pk * P.in_frame_bytes;
+      const uint8_t* src0 = frame + (uint64_t)(ro0 * (uint32_t)P.row_step) * P.in_row_bytes + (uint64_t)col0 * pxb;
+      // the pixel whose chroma a held row replays (ChromaSubsampler.scala:62-65): loads first, used after the TMA issue
+      uint32_t h0 = 0, h1 = 0, h2 = 0, hvalid = 0;
+      if (vhold && lane < nrows) {
+        const uint32_t ro = ro0 + lane;
+        const uint8_t* hp = nullptr;
+        if (!P.case_b) {
+          if (f == 1 && (ro & 1u)) hp = frame + (uint64_t)(ro - 1u) * P.in_row_bytes + (uint32_t)P.last_sample_col * ipb;
+        } else {
+          const uint32_t line = ro / f;        // W == f * Wo: one counter line spans f output rows
+          if (line & 1u) {
+            const uint32_t srow = (line - 1u) * f + P.caseb_row_add;
+            hp = frame + (uint64_t)(srow * (uint32_t)P.row_step) * P.in_row_bytes + P.caseb_col_bytes;
+          }
+        }
+        if (hp) { h0 = ldg8_now(hp); h1 = ldg8_now(hp + 1); h2 = ldg8_now(hp + 2); hvalid = 0x80000000u; }
+      }
+      if (lane == 0) {
+        d->k = pk; d->ro0 = ro0; d->nrows = nrows; d->col0 = col0; d->ncols = ncols; d->npx = npx;
+        d->a0 = (uint32_t)reinterpret_cast<uintptr_t>(src0) & 15u;
+        if (P.in_dense) {          // consecutive rows are contiguous in memory: one span
+          span_fetch(in_s, src0, (nrows - 1u) * P.in_row_bytes + len_in, bar, pol, lim_lo, lim_hi);
+        } else {
+          for (uint32_t r = 0; r < nrows; ++r)
+            span_fetch(in_s + r * rs_mul, src0 + (uint64_t)r * rstep, len_in, bar, pol, lim_lo, lim_hi);
         }
       }
-      if (hp) { h0 = ldg8_now(hp); h1 = ldg8_now(hp + 1); h2 = ldg8_now(hp + 2); hvalid = 0x80000000u; }
+      if (vhold && lane < (uint32_t)kMaxTileRows)
+        sts32(held_base + (s * (uint32_t)kMaxTileRows + lane) * 4u, hvalid ? (hvalid | h0 | (h1 << 8) | (h2 << 16)) : 0u);
+      __syncwarp();
+      // releases the descriptor, the held words and the hand-copied edge bytes; the phase completes with the last TMA byte
+      if (lane == 0) mbar_arrive(bar);
+      // advance by gridDim.x tiles in (frame, row tile, segment) coordinates
+      pseg += dseg;
+      uint32_t c = pseg >= nsplit ? 1u : 0u;
+      pseg -= c * nsplit;
+      ptb += dtb + c;
+      c = ptb >= P.tiles_per_band ? 1u : 0u;
+      ptb -= c * P.tiles_per_band;
+      pk += dk + c;
     }
-  };
-  auto publish_held = [&](uint32_t s) {      // first use of the registers prefetch_held filled
-    if (vhold && tid < (uint32_t)P.tile_rows)
-      sts32(held_base + (s * (uint32_t)kMaxTileRows + tid) * 4u, hvalid ? (hvalid | h0 | (h1 << 8) | (h2 << 16)) : 0u);
-  };
+    return;
+  }
 
-  __syncthreads();                 // mbarriers initialised
-  if (tid == 0) produce(0);
-  mbar_wait(bar0, 0);              // also makes descriptor 0 visible
-  prefetch_held(descs[0]);
-  publish_held(0);
-
+  // ============================== consumer warps =============================================================
   for (uint32_t it = 0; it < n_my; ++it) {
     const uint32_t s = it & 1u;
-    const bool has_next = it + 1u < n_my;
-    // stage s^1 and its descriptor were last read before the previous iteration's middle barrier
-    if (tid == 0 && has_next) produce(it + 1u);
-    mbar_wait(bar0 + s * 8u, (it >> 1) & 1u);
+    mbar_wait(full0 + s * 8u, (it >> 1) & 1u);
     const FlexDesc D = descs[s];
-    __syncthreads();               // the previous tile has left the staging area; descriptor s^1 is visible
-    if (has_next) prefetch_held(descs[s ^ 1u]);
+    consumer_barrier(NC);          // the previous tile has left the staging area
 
     // ---- compute -------------------------------------------------------------------------------------------
     const uint32_t in_s = sbase + s * in_stage, held_s = held_base + s * (uint32_t)kMaxTileRows * 4u;
@@ -311,7 +308,7 @@ __global__ void __launch_bounds__(kFlexThreads) csic_flex_kernel(const __grid_co
     const uint32_t ccols = (D.npx + (1u << hs_sh) - 1u) >> hs_sh;
     const uint32_t cb_s = out_s + D.nrows * st_mul + 16u, cr_s = cb_s + nrc * ccols;
     const uint32_t last_px = D.npx - 1u;
-    for (uint32_t q = tid; q < n_gran; q += NT) {
+    for (uint32_t q = tid; q < n_gran; q += NC) {
       const uint32_t row = gpr > 1u ? __umulhi(q, gpr_magic) : q, g = q - row * gpr;
       const uint32_t rs = in_s + row * rs_mul + ((D.a0 + row * rs_add) & 15u);
       const uint32_t c = g * 4u;
@@ -400,13 +397,14 @@ __global__ void __launch_bounds__(kFlexThreads) csic_flex_kernel(const __grid_co
         }
       }
     }
-    __syncthreads();               // staging complete; every read of input stage s and its held words is done
+    consumer_barrier(NC);          // staging complete; every read of input stage s, its held words and descriptor is done
+    if (tid == 0) mbar_arrive(empty0 + s * 8u);
 
     // ---- store ---------------------------------------------------------------------------------------------
     if (out_one) {
-      span_store(obase, out_s + (oa0 & 12u), D.nrows * row_out, tid, NT);
+      span_store(obase, out_s + (oa0 & 12u), D.nrows * row_out, tid, NC);
     } else {
-      for_each_span(D.nrows, row_out, [&](uint32_t j, uint32_t t, uint32_t n) {
+      for_each_span(D.nrows, row_out, NC, [&](uint32_t j, uint32_t t, uint32_t n) {
         span_store(obase + (uint64_t)j * P.out_row_bytes, out_s + j * st_mul + ((oa0 + j * st_add) & 12u), row_out, t, n);
       });
     }
@@ -415,17 +413,15 @@ __global__ void __launch_bounds__(kFlexThreads) csic_flex_kernel(const __grid_co
       uint8_t* cb_g = fout + P.planar_cb_off + coff;
       uint8_t* cr_g = fout + P.planar_cr_off + coff;
       if (nsplit == 1) {                                       // ccols == planar_cw: chroma rows are contiguous
-        span_store(cb_g, cb_s, nrc * ccols, tid, NT);
-        span_store(cr_g, cr_s, nrc * ccols, tid, NT);
+        span_store(cb_g, cb_s, nrc * ccols, tid, NC);
+        span_store(cr_g, cr_s, nrc * ccols, tid, NC);
       } else {
-        for_each_span(nrc, ccols, [&](uint32_t j, uint32_t t, uint32_t n) {
+        for_each_span(nrc, ccols, NC, [&](uint32_t j, uint32_t t, uint32_t n) {
           span_store(cb_g + (uint64_t)j * (uint32_t)P.planar_cw, cb_s + j * ccols, ccols, t, n);
           span_store(cr_g + (uint64_t)j * (uint32_t)P.planar_cw, cr_s + j * ccols, ccols, t, n);
         });
       }
     }
-    // held words of the next tile: stage s^1's were last read before the previous iteration's middle barrier
-    if (has_next) publish_held(s ^ 1u);
   }
 }
 
@@ -478,8 +474,8 @@ bool plan_flex_kernel(KPlan& k, int sm_count, size_t max_smem_optin) {
   k.out_buf_off = up128(in_bytes);
   k.out_buf_stride = up16(stage_bytes + 32u);                               // + slack: span_store reads one word ahead
   k.meta_off = k.out_buf_off + k.out_buf_stride;                            // held words of both stages
-  k.bar_off = up128(k.meta_off + 2u * (uint32_t)kMaxTileRows * 4u);         // two mbarriers, then two descriptors
-  k.smem_bytes = k.bar_off + 16u + 2u * kDescBytes;
+  k.bar_off = up128(k.meta_off + 2u * (uint32_t)kMaxTileRows * 4u);         // full[2], empty[2] mbarriers, then two descriptors
+  k.smem_bytes = k.bar_off + 32u + 2u * kDescBytes;
   if (k.smem_bytes > max_smem_optin) return false;
   k.block_threads = kFlexThreads;
   k.stages = 2;
