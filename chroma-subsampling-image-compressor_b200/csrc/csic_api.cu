@@ -182,7 +182,7 @@ int run(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t n_frames,
   } else if (ctx->opt_family == 0 && csic::plan_pool_kernel(k, ctx->sm_count, ctx->max_smem_optin)) {
     err = csic::launch_pool(k, ctx->sm_count, ctx->opt_ctas_per_sm, st);
     ctx->last_family = 3;
-  } else if (ctx->opt_family != 1 && csic::plan_flex_kernel(k, ctx->sm_count, ctx->max_smem_optin)) {
+  } else if (ctx->opt_family != 1 && csic::plan_flex_kernel(k, ctx->sm_count, ctx->max_smem_optin, ctx->opt_stages, ctx->opt_tile_bytes)) {
     err = csic::launch_flex(k, ctx->sm_count, ctx->opt_ctas_per_sm, st);
     ctx->last_family = 4;
   } else {

@@ -26,6 +26,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <type_traits>
 
 #include "csic_internal.h"
 #include "csic_device_math.cuh"
@@ -35,8 +36,9 @@ namespace csic {
 
 namespace {
 
-constexpr int kFlexThreads = 256;                    // 7 consumer warps + 1 producer warp
-constexpr uint32_t kFlexTileBytes = 12u * 1024u;     // input bytes of one tile
+constexpr int kFlexConsumers = 256;                  // default: 8 consumer warps (+ 1 producer warp)
+constexpr int kFlexMaxThreads = 288;                 // 8 consumer warps + the producer warp
+constexpr uint32_t kFlexTileBytes = 24u * 1024u;     // input bytes of one tile (B200 sweep: profiles/r1/sweep_flex.txt)
 constexpr uint32_t kCtaWideSpan = 2048u;             // row spans at least this long are stored by the whole CTA
 constexpr uint32_t kDescBytes = 48u;
 
@@ -175,13 +177,14 @@ static_assert(sizeof(FlexDesc) == kDescBytes, "kDescBytes out of sync");
 }  // namespace
 
 template <int FMT, bool TRUNC>
-__global__ void __launch_bounds__(kFlexThreads) csic_flex_kernel(const __grid_constant__ KPlan P) {
+__global__ void __launch_bounds__(kFlexMaxThreads) csic_flex_kernel(const __grid_constant__ KPlan P) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr uint32_t kUnit = FlexFmt<FMT>::kUnit, kOpx = kUnit / 4u;
   const uint32_t tid = threadIdx.x, NT = blockDim.x;
   const uint32_t sbase = smem_u32(smem), out_s = sbase + P.out_buf_off, held_base = sbase + P.meta_off;
   const uint32_t bar0 = sbase + P.bar_off;
-  const FlexDesc* descs = reinterpret_cast<const FlexDesc*>(smem + P.bar_off + 32u);
+  const uint32_t S = (uint32_t)P.stages;
+  const FlexDesc* descs = reinterpret_cast<const FlexDesc*>(smem + P.bar_off + 16u * S);
   const uint32_t in_stage = P.stage_stride * (uint32_t)P.tile_rows + 32u;     // bytes of one input stage
   const uint32_t ipb = (uint32_t)P.in_px_bytes, f = (uint32_t)P.f, pxb = f * ipb;
   const uint32_t nsplit = (uint32_t)P.nsplit;
@@ -204,16 +207,18 @@ __global__ void __launch_bounds__(kFlexThreads) csic_flex_kernel(const __grid_co
   const uint32_t rs_add = P.in_dense ? 0u : ((uint32_t)rstep & 15u);
 
   const uint32_t NC = NT - 32u;    // consumer threads; the last warp is the producer
-  const uint32_t full0 = bar0, empty0 = bar0 + 16u;
+  const uint32_t full0 = bar0, empty0 = bar0 + 8u * S;
   if (tid == 0) {
-    mbar_init(full0, 1); mbar_init(full0 + 8u, 1);       // the producer's arrive (+ the TMA byte count)
-    mbar_init(empty0, 1); mbar_init(empty0 + 8u, 1);     // one consumer's arrive, behind the consumers' barrier
+    for (uint32_t s = 0; s < S; ++s) {
+      mbar_init(full0 + s * 8u, 1);        // the producer's arrive (+ the TMA byte count)
+      mbar_init(empty0 + s * 8u, 1);       // one consumer's arrive, behind the consumers' barrier
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
   // ============================== producer warp ==============================================================
-  // Walks this CTA's tiles two stages ahead of the consumers.  All lanes track the geometry; lane 0 describes the
+  // Walks this CTA's tiles up to S stages ahead of the consumers.  All lanes track the geometry; lane 0 describes the
   // tile and hands its row spans to the TMA engine, lanes 0..nrows-1 fetch the pixel a held row replays.
   if (tid >= NC) {
     const uint32_t lane = tid - NC;
@@ -227,9 +232,9 @@ __global__ void __launch_bounds__(kFlexThreads) csic_flex_kernel(const __grid_co
                              (uint64_t)((uint32_t)(P.row0 + P.band_rows - 1) * (uint32_t)P.row_step) * P.in_row_bytes +
                              ((uint32_t)P.Wo - 1u) * pxb + ipb;
     for (uint32_t j = 0; j < n_my; ++j) {
-      const uint32_t s = j & 1u, bar = full0 + s * 8u, in_s = sbase + s * in_stage;
-      if (j >= 2u) mbar_wait(empty0 + s * 8u, ((j >> 1) - 1u) & 1u);       // the consumers drained the previous use
-      FlexDesc* d = reinterpret_cast<FlexDesc*>(smem + P.bar_off + 32u) + s;
+      const uint32_t s = j % S, bar = full0 + s * 8u, in_s = sbase + s * in_stage;
+      if (j >= S) mbar_wait(empty0 + s * 8u, ((j / S) - 1u) & 1u);         // the consumers drained the previous use
+      FlexDesc* d = reinterpret_cast<FlexDesc*>(smem + P.bar_off + 16u * S) + s;
       const uint32_t ro0 = (uint32_t)P.row0 + ptb * (uint32_t)P.tile_rows;
       const uint32_t nrows = min((uint32_t)P.tile_rows, (uint32_t)(P.row0 + P.band_rows) - ro0);
       const uint32_t col0 = pseg * (uint32_t)P.tile_px;
@@ -283,8 +288,8 @@ __global__ void __launch_bounds__(kFlexThreads) csic_flex_kernel(const __grid_co
 
   // ============================== consumer warps =============================================================
   for (uint32_t it = 0; it < n_my; ++it) {
-    const uint32_t s = it & 1u;
-    mbar_wait(full0 + s * 8u, (it >> 1) & 1u);
+    const uint32_t s = it % S;
+    mbar_wait(full0 + s * 8u, (it / S) & 1u);
     const FlexDesc D = descs[s];
     consumer_barrier(NC);          // the previous tile has left the staging area
 
@@ -308,95 +313,102 @@ __global__ void __launch_bounds__(kFlexThreads) csic_flex_kernel(const __grid_co
     const uint32_t ccols = (D.npx + (1u << hs_sh) - 1u) >> hs_sh;
     const uint32_t cb_s = out_s + D.nrows * st_mul + 16u, cr_s = cb_s + nrc * ccols;
     const uint32_t last_px = D.npx - 1u;
-    for (uint32_t q = tid; q < n_gran; q += NC) {
-      const uint32_t row = gpr > 1u ? __umulhi(q, gpr_magic) : q, g = q - row * gpr;
-      const uint32_t rs = in_s + row * rs_mul + ((D.a0 + row * rs_add) & 15u);
-      const uint32_t c = g * 4u;
-      uint32_t p[4], dy[4], xb[4], xr[4];
-      if (c + 3u <= last_px) {
-        load_granule_any(rs + c * pxb, pxb, p);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) p[j] = lds_px(rs + min(c + j, last_px) * pxb);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dy[j] = fwd_y16(p[j], P.coef_y);
-      const uint32_t hv = vhold ? lds32(held_s + row * 4u) : 0u;
-      if (hv) {
-        const uint32_t hb = fwd_nc16<TRUNC>(hv & 0x00FFFFFFu, P.coef_ncb), hr = fwd_nc16<TRUNC>(hv & 0x00FFFFFFu, P.coef_ncr);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { xb[j] = hb; xr[j] = hr; }
-      } else {
-        // sample where j % hfe == 0, hold in between (ChromaSubsampler.scala:57-65)
-        xb[0] = fwd_nc16<TRUNC>(p[0], P.coef_ncb); xr[0] = fwd_nc16<TRUNC>(p[0], P.coef_ncr);
-        if (hfe == 1) { xb[1] = fwd_nc16<TRUNC>(p[1], P.coef_ncb); xr[1] = fwd_nc16<TRUNC>(p[1], P.coef_ncr); }
-        else { xb[1] = xb[0]; xr[1] = xr[0]; }
-        if (hfe <= 2) { xb[2] = fwd_nc16<TRUNC>(p[2], P.coef_ncb); xr[2] = fwd_nc16<TRUNC>(p[2], P.coef_ncr); }
-        else { xb[2] = xb[0]; xr[2] = xr[0]; }
-        if (hfe == 1) { xb[3] = fwd_nc16<TRUNC>(p[3], P.coef_ncb); xr[3] = fwd_nc16<TRUNC>(p[3], P.coef_ncr); }
-        else { xb[3] = xb[2]; xr[3] = xr[2]; }
-      }
-      const uint32_t so = out_s + row * st_mul + ((oa0 + row * st_add) & 12u) + g * kUnit;
-      if (FMT == KF_YCC888) {
-        // byte 1 of dy is Y, byte 1 of xb/xr is ~Cb/~Cr: gather with PRMT, flip and quantise per word
-        uint32_t t, u;
-        t = __byte_perm(dy[0], xb[0], 0x0051); u = __byte_perm(xr[0], dy[1], 0x0051);
-        sts32(so, (__byte_perm(t, u, 0x5410) ^ 0x00FFFF00u) & qm0);
-        t = __byte_perm(xb[1], xr[1], 0x0051); u = __byte_perm(dy[2], xb[2], 0x0051);
-        sts32(so + 4, (__byte_perm(t, u, 0x5410) ^ 0xFF00FFFFu) & qm1);
-        t = __byte_perm(xr[2], dy[3], 0x0051); u = __byte_perm(xb[3], xr[3], 0x0051);
-        sts32(so + 8, (__byte_perm(t, u, 0x5410) ^ 0xFFFF00FFu) & qm2);
-      } else if (FMT == KF_RGB888) {
-        uint32_t v[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          v[j] = inverse_rgb((int)((dy[j] >> 8) & my), (int)((255u - (xb[j] >> 8)) & mcb), (int)((255u - (xr[j] >> 8)) & mcr));
-        sts32(so, v[0] | (v[1] << 24));
-        sts32(so + 4, (v[1] >> 8) | (v[2] << 16));
-        sts32(so + 8, (v[2] >> 16) | (v[3] << 8));
-      } else if (FMT == KF_PLANAR) {
-        const uint32_t my4 = my * 0x01010101u;
-        sts32(so, __byte_perm(__byte_perm(dy[0], dy[1], 0x0051), __byte_perm(dy[2], dy[3], 0x0051), 0x5410) & my4);
-        if (!hv) {               // a sampled line: its sample points go to the chroma planes (hs == hfe here)
-          const uint32_t crow = (((D.ro0 + row) >> vs_sh) - c_first) * ccols + (c >> hs_sh);
-          if (hfe == 1) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (c + j <= last_px) { sts8(cb_s + crow + j, (~(xb[j] >> 8)) & mcb); sts8(cr_s + crow + j, (~(xr[j] >> 8)) & mcr); }
-          } else if (hfe == 2) {
-            sts8(cb_s + crow, (~(xb[0] >> 8)) & mcb); sts8(cr_s + crow, (~(xr[0] >> 8)) & mcr);
-            if (c + 2 <= last_px) { sts8(cb_s + crow + 1, (~(xb[2] >> 8)) & mcb); sts8(cr_s + crow + 1, (~(xr[2] >> 8)) & mcr); }
+    // the loop is instantiated per chroma hold width (1, 2 or 4 output pixels): no per-granule branches or moves
+    auto compute = [&](auto hfe_tag) {
+      constexpr uint32_t HFE = decltype(hfe_tag)::value;
+      for (uint32_t q = tid; q < n_gran; q += NC) {
+        const uint32_t row = gpr > 1u ? __umulhi(q, gpr_magic) : q, g = q - row * gpr;
+        const uint32_t rs = in_s + row * rs_mul + ((D.a0 + row * rs_add) & 15u);
+        const uint32_t c = g * 4u;
+        uint32_t p[4], dy[4], xb[4], xr[4];
+        if (c + 3u <= last_px) {
+          load_granule_any(rs + c * pxb, pxb, p);
+        } else {
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) p[j] = lds_px(rs + min(c + j, last_px) * pxb);
+        }
+  #pragma unroll
+        for (int j = 0; j < 4; ++j) dy[j] = fwd_y16(p[j], P.coef_y);
+        const uint32_t hv = vhold ? lds32(held_s + row * 4u) : 0u;
+        if (hv) {
+          const uint32_t hb = fwd_nc16<TRUNC>(hv & 0x00FFFFFFu, P.coef_ncb), hr = fwd_nc16<TRUNC>(hv & 0x00FFFFFFu, P.coef_ncr);
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) { xb[j] = hb; xr[j] = hr; }
+        } else {
+          // sample where j % HFE == 0, hold in between (ChromaSubsampler.scala:57-65)
+          xb[0] = fwd_nc16<TRUNC>(p[0], P.coef_ncb); xr[0] = fwd_nc16<TRUNC>(p[0], P.coef_ncr);
+          if (HFE == 1) { xb[1] = fwd_nc16<TRUNC>(p[1], P.coef_ncb); xr[1] = fwd_nc16<TRUNC>(p[1], P.coef_ncr); }
+          else { xb[1] = xb[0]; xr[1] = xr[0]; }
+          if (HFE <= 2) { xb[2] = fwd_nc16<TRUNC>(p[2], P.coef_ncb); xr[2] = fwd_nc16<TRUNC>(p[2], P.coef_ncr); }
+          else { xb[2] = xb[0]; xr[2] = xr[0]; }
+          if (HFE == 1) { xb[3] = fwd_nc16<TRUNC>(p[3], P.coef_ncb); xr[3] = fwd_nc16<TRUNC>(p[3], P.coef_ncr); }
+          else { xb[3] = xb[2]; xr[3] = xr[2]; }
+        }
+        const uint32_t so = out_s + row * st_mul + ((oa0 + row * st_add) & 12u) + g * kUnit;
+        if (FMT == KF_YCC888) {
+          // byte 1 of dy is Y, byte 1 of xb/xr is ~Cb/~Cr: gather with PRMT, flip and quantise per word
+          uint32_t t, u;
+          t = __byte_perm(dy[0], xb[0], 0x0051); u = __byte_perm(xr[0], dy[1], 0x0051);
+          sts32(so, (__byte_perm(t, u, 0x5410) ^ 0x00FFFF00u) & qm0);
+          t = __byte_perm(xb[1], xr[1], 0x0051); u = __byte_perm(dy[2], xb[2], 0x0051);
+          sts32(so + 4, (__byte_perm(t, u, 0x5410) ^ 0xFF00FFFFu) & qm1);
+          t = __byte_perm(xr[2], dy[3], 0x0051); u = __byte_perm(xb[3], xr[3], 0x0051);
+          sts32(so + 8, (__byte_perm(t, u, 0x5410) ^ 0xFFFF00FFu) & qm2);
+        } else if (FMT == KF_RGB888) {
+          uint32_t v[4];
+  #pragma unroll
+          for (int j = 0; j < 4; ++j)
+            v[j] = inverse_rgb((int)((dy[j] >> 8) & my), (int)((255u - (xb[j] >> 8)) & mcb), (int)((255u - (xr[j] >> 8)) & mcr));
+          sts32(so, v[0] | (v[1] << 24));
+          sts32(so + 4, (v[1] >> 8) | (v[2] << 16));
+          sts32(so + 8, (v[2] >> 16) | (v[3] << 8));
+        } else if (FMT == KF_PLANAR) {
+          const uint32_t my4 = my * 0x01010101u;
+          sts32(so, __byte_perm(__byte_perm(dy[0], dy[1], 0x0051), __byte_perm(dy[2], dy[3], 0x0051), 0x5410) & my4);
+          if (!hv) {               // a sampled line: its sample points go to the chroma planes (hs == HFE here)
+            const uint32_t crow = (((D.ro0 + row) >> vs_sh) - c_first) * ccols + (c >> hs_sh);
+            if (HFE == 1) {
+  #pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (c + j <= last_px) { sts8(cb_s + crow + j, (~(xb[j] >> 8)) & mcb); sts8(cr_s + crow + j, (~(xr[j] >> 8)) & mcr); }
+            } else if (HFE == 2) {
+              sts8(cb_s + crow, (~(xb[0] >> 8)) & mcb); sts8(cr_s + crow, (~(xr[0] >> 8)) & mcr);
+              if (c + 2 <= last_px) { sts8(cb_s + crow + 1, (~(xb[2] >> 8)) & mcb); sts8(cr_s + crow + 1, (~(xr[2] >> 8)) & mcr); }
+            } else {
+              sts8(cb_s + crow, (~(xb[0] >> 8)) & mcb); sts8(cr_s + crow, (~(xr[0] >> 8)) & mcr);
+            }
+          }
+        } else {
+          uint32_t v[4];
+          if (q8) {
+  #pragma unroll
+            for (int j = 0; j < 4; ++j)   // (Cr, Cb, Y, 0): dy < 65536 so its byte 3 is the zero pad
+              v[j] = __byte_perm(__byte_perm(xr[j], xb[j], 0x0051), dy[j], 0x7510) ^ 0x0000FFFFu;
           } else {
-            sts8(cb_s + crow, (~(xb[0] >> 8)) & mcb); sts8(cr_s + crow, (~(xr[0] >> 8)) & mcr);
+  #pragma unroll
+            for (int j = 0; j < 4; ++j)
+              v[j] = ((dy[j] >> shy) << ly) | (((xb[j] ^ 0xFFFFu) >> shb) << lb) | ((xr[j] ^ 0xFFFFu) >> shr);
+          }
+          if (c + 3u > last_px) {        // the row's zero pad slots
+  #pragma unroll
+            for (int j = 0; j < 4; ++j) if (c + j > last_px) v[j] = 0u;
+          }
+          if (FMT == KF_SLOT32) {
+            if ((so & 15u) == 0) sts128(so, v[0], v[1], v[2], v[3]);
+            else if ((so & 7u) == 0) { sts64(so, v[0], v[1]); sts64(so + 8, v[2], v[3]); }
+            else { sts32(so, v[0]); sts32(so + 4, v[1]); sts32(so + 8, v[2]); sts32(so + 12, v[3]); }
+          } else if (FMT == KF_SLOT16) {
+            if ((so & 7u) == 0) sts64(so, v[0] | (v[1] << 16), v[2] | (v[3] << 16));
+            else { sts32(so, v[0] | (v[1] << 16)); sts32(so + 4, v[2] | (v[3] << 16)); }
+          } else {
+            sts32(so, v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
           }
         }
-      } else {
-        uint32_t v[4];
-        if (q8) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)   // (Cr, Cb, Y, 0): dy < 65536 so its byte 3 is the zero pad
-            v[j] = __byte_perm(__byte_perm(xr[j], xb[j], 0x0051), dy[j], 0x7510) ^ 0x0000FFFFu;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            v[j] = ((dy[j] >> shy) << ly) | (((xb[j] ^ 0xFFFFu) >> shb) << lb) | ((xr[j] ^ 0xFFFFu) >> shr);
-        }
-        if (c + 3u > last_px) {        // the row's zero pad slots
-#pragma unroll
-          for (int j = 0; j < 4; ++j) if (c + j > last_px) v[j] = 0u;
-        }
-        if (FMT == KF_SLOT32) {
-          if ((so & 15u) == 0) sts128(so, v[0], v[1], v[2], v[3]);
-          else if ((so & 7u) == 0) { sts64(so, v[0], v[1]); sts64(so + 8, v[2], v[3]); }
-          else { sts32(so, v[0]); sts32(so + 4, v[1]); sts32(so + 8, v[2]); sts32(so + 12, v[3]); }
-        } else if (FMT == KF_SLOT16) {
-          if ((so & 7u) == 0) sts64(so, v[0] | (v[1] << 16), v[2] | (v[3] << 16));
-          else { sts32(so, v[0] | (v[1] << 16)); sts32(so + 4, v[2] | (v[3] << 16)); }
-        } else {
-          sts32(so, v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
-        }
       }
-    }
+    };
+    if (hfe == 1u) compute(std::integral_constant<uint32_t, 1u>{});
+    else if (hfe == 2u) compute(std::integral_constant<uint32_t, 2u>{});
+    else compute(std::integral_constant<uint32_t, 4u>{});
     consumer_barrier(NC);          // staging complete; every read of input stage s, its held words and descriptor is done
     if (tid == 0) mbar_arrive(empty0 + s * 8u);
 
@@ -426,7 +438,7 @@ __global__ void __launch_bounds__(kFlexThreads) csic_flex_kernel(const __grid_co
 }
 
 // ---- planning and dispatch ---------------------------------------------------------------------------------
-bool plan_flex_kernel(KPlan& k, int sm_count, size_t max_smem_optin) {
+bool plan_flex_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_stages, uint32_t force_tile_bytes) {
   if (k.average && k.f > 1) return false;                       // AVERAGE extension: csic_pool_kernel / generic
   if (k.band_rows <= 0 || k.n_frames == 0) return false;
   const uint32_t ipb = (uint32_t)k.in_px_bytes, f = (uint32_t)k.f, pxb = f * ipb;
@@ -442,7 +454,8 @@ bool plan_flex_kernel(KPlan& k, int sm_count, size_t max_smem_optin) {
   const bool planar = k.kformat == KF_PLANAR;
   const uint32_t unit = (k.kformat <= KF_RGB888) ? 12u : (planar ? 4u : 4u * (uint32_t)k.slot_bytes);
   const uint32_t S = (uint32_t)k.slots_per_row, Wo = (uint32_t)k.Wo;
-  const uint32_t tile_px_max = std::max(16u, (kFlexTileBytes / pxb) & ~15u);
+  const uint32_t tile_bytes = force_tile_bytes ? std::max(1024u, force_tile_bytes) : kFlexTileBytes;
+  const uint32_t tile_px_max = std::max(16u, (tile_bytes / pxb) & ~15u);
   k.tile_px = (int32_t)std::min(tile_px_max, (S + 15u) & ~15u);
   k.nsplit = (int32_t)((S + (uint32_t)k.tile_px - 1u) / (uint32_t)k.tile_px);
   const uint32_t len_in_max = ((std::min((uint32_t)k.tile_px, Wo) - 1u) * f + 1u) * ipb;
@@ -451,7 +464,7 @@ bool plan_flex_kernel(KPlan& k, int sm_count, size_t max_smem_optin) {
   int rows = 1;
   if (k.nsplit == 1) {
     const uint32_t per_row = contiguous ? k.in_row_bytes : len_in_max;
-    rows = (int)std::min<uint32_t>((uint32_t)kMaxTileRows, std::max<uint32_t>(1u, kFlexTileBytes / std::max(1u, per_row)));
+    rows = (int)std::min<uint32_t>((uint32_t)kMaxTileRows, std::max<uint32_t>(1u, tile_bytes / std::max(1u, per_row)));
     rows = std::min(rows, k.band_rows);
     auto tiles_for = [&](int r) { return (uint64_t)k.n_frames * (uint64_t)((k.band_rows + r - 1) / r); };
     while (rows > 1 && tiles_for(rows) < (uint64_t)sm_count * 8u) rows = (rows + 1) / 2;
@@ -468,18 +481,20 @@ bool plan_flex_kernel(KPlan& k, int sm_count, size_t max_smem_optin) {
   auto up16 = [](uint32_t v) { return (v + 15u) & ~15u; };
   auto up128 = [](uint32_t v) { return (v + 127u) & ~127u; };
   k.stage_stride = up16((k.in_dense ? std::max(len_in_max, k.in_row_bytes) : len_in_max) + 15u) + 16u;
-  const uint32_t in_bytes = 2u * ((uint32_t)rows * k.stage_stride + 32u);   // two stages; + slack: pixel loads read one word ahead
+  const uint32_t stages = (uint32_t)std::min(std::max(force_stages, 2), 8);
+  const uint32_t in_bytes = stages * ((uint32_t)rows * k.stage_stride + 32u);   // + slack: pixel loads read one word ahead
   uint32_t stage_bytes = (uint32_t)rows * (((uint32_t)k.tile_px / 4u) * unit + 16u) + 16u;   // rows at their own offset mod 16
   if (planar) stage_bytes += 2u * (uint32_t)(rows / std::max(1, k.planar_vs) + 1) * (uint32_t)k.tile_px;
   k.out_buf_off = up128(in_bytes);
   k.out_buf_stride = up16(stage_bytes + 32u);                               // + slack: span_store reads one word ahead
-  k.meta_off = k.out_buf_off + k.out_buf_stride;                            // held words of both stages
-  k.bar_off = up128(k.meta_off + 2u * (uint32_t)kMaxTileRows * 4u);         // full[2], empty[2] mbarriers, then two descriptors
-  k.smem_bytes = k.bar_off + 32u + 2u * kDescBytes;
+  k.meta_off = k.out_buf_off + k.out_buf_stride;                            // held words of every stage
+  k.bar_off = up128(k.meta_off + stages * (uint32_t)kMaxTileRows * 4u);     // full[S], empty[S] mbarriers, then S descriptors
+  k.smem_bytes = k.bar_off + stages * (16u + kDescBytes);
   if (k.smem_bytes > max_smem_optin) return false;
-  k.block_threads = kFlexThreads;
-  k.stages = 2;
-  k.ctas_per_sm = (int32_t)std::max<uint32_t>(1u, std::min<uint32_t>(std::min<uint32_t>(8u, 2048u / kFlexThreads),
+  if (k.block_threads <= 0) k.block_threads = kFlexConsumers;
+  k.block_threads = std::min(k.block_threads, kFlexMaxThreads - 32);
+  k.stages = (int32_t)stages;
+  k.ctas_per_sm = (int32_t)std::max<uint32_t>(1u, std::min<uint32_t>(std::min<uint32_t>(8u, 2048u / ((uint32_t)k.block_threads + 32u)),
                                                                       227u * 1024u / (k.smem_bytes + 1024u)));
   return true;
 }
@@ -487,8 +502,9 @@ bool plan_flex_kernel(KPlan& k, int sm_count, size_t max_smem_optin) {
 namespace {
 template <int FMT>
 int launch_flex_fmt(const KPlan& k, unsigned grid, cudaStream_t st) {
-  if (k.trunc) csic_flex_kernel<FMT, true><<<grid, kFlexThreads, k.smem_bytes, st>>>(k);
-  else csic_flex_kernel<FMT, false><<<grid, kFlexThreads, k.smem_bytes, st>>>(k);
+  const unsigned threads = (unsigned)k.block_threads + 32u;   // + producer warp
+  if (k.trunc) csic_flex_kernel<FMT, true><<<grid, threads, k.smem_bytes, st>>>(k);
+  else csic_flex_kernel<FMT, false><<<grid, threads, k.smem_bytes, st>>>(k);
   return (int)cudaGetLastError();
 }
 template <int FMT>

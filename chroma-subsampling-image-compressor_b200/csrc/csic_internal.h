@@ -85,7 +85,7 @@ template <int F> int launch_pool_factor(const KPlan& k, unsigned grid, void* str
 template <int F> int pool_set_attributes_factor(size_t max_smem_optin);
 
 // Any width / pitch / base alignment (csic_flex_kernel.cu): DECIMATE pipelines the TMA kernels' 16-byte rules exclude.
-bool plan_flex_kernel(KPlan& k, int sm_count, size_t max_smem_optin);
+bool plan_flex_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_stages, uint32_t force_tile_bytes);
 int launch_flex(const KPlan& k, int sm_count, int force_ctas_per_sm, void* stream);
 int flex_set_attributes(size_t max_smem_optin);
 
