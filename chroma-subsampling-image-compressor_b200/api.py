@@ -172,7 +172,7 @@ class PinnedBuffer:
 
 class Context:
     """`csic_ctx`: one per (host thread, GPU)."""
-    KERNEL_AUTO, KERNEL_GENERIC = 0, 1
+    KERNEL_AUTO, KERNEL_GENERIC, KERNEL_NO_ALIGNED_TMA = 0, 1, 2
 
     def __init__(self, device=0):
         self._h = ctypes.c_void_p()

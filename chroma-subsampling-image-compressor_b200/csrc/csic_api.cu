@@ -477,8 +477,8 @@ void parallel_rows_copy(uint8_t* dst, size_t dst_step, const uint8_t* src, size_
 // row band).  Frames are cut into chunks that flow through a kPipe-deep ring of device buffers on three streams.
 // Only what the band needs crosses PCIe: its input rows (every f-th one under DECIMATE) and its output rows; the
 // device buffers hold just those rows and the kernel is handed *virtual* frame bases (buffer - first_row * pitch).
-static int host_pipeline(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, size_t n_frames, uint8_t* out,
-                         int32_t row0, int32_t rows) {
+static int host_pipeline_run(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, size_t n_frames, uint8_t* out,
+                             int32_t row0, int32_t rows) {
   const csic::Geometry g = csic::geometry(*p);
   DeviceGuard guard(ctx->device);
   const bool band = !(row0 == 0 && rows == g.out_h);
@@ -657,6 +657,23 @@ static int host_pipeline(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb
   CSIC_CUDA(cudaStreamSynchronize(ctx->stream));
   CSIC_CUDA(cudaStreamSynchronize(ctx->s_h2d));
   return CSIC_OK;
+}
+
+// An error in the middle of the pipeline must not leave copies in flight on the caller's buffers or on the staging
+// ring: drain the three streams before reporting it.
+static int host_pipeline(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, size_t n_frames, uint8_t* out,
+                         int32_t row0, int32_t rows) {
+  const int rc = host_pipeline_run(ctx, p, rgb, n_frames, out, row0, rows);
+  if (rc != CSIC_OK) {
+    const std::string keep = g_last_error;
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->s_h2d);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->s_d2h);
+    cudaGetLastError();
+    g_last_error = keep;
+  }
+  return rc;
 }
 
 int csic_process_host(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, size_t n_frames, uint8_t* out) {

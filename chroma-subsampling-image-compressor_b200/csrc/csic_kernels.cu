@@ -196,9 +196,73 @@ __global__ void __launch_bounds__(256) csic_expand_planar_kernel(const __grid_co
   }
 }
 
+// Same decoder, four output pixels per thread (needs Wo % 4 == 0 and a 16-byte-aligned output).  The Y bytes arrive
+// as one word when aligned and the chroma samples of the granule are fetched once.  The output is one contiguous
+// array of 12 bytes per granule, so a warp's 32 granules are 384 consecutive bytes: the lanes park their three words
+// in shared memory and lanes 0..23 write them back out as coalesced 16-byte words.
+template <typename IdxT>   // uint32_t whenever the launch has fewer than 2^32 granules: 32-bit divisions
+__global__ void __launch_bounds__(256) csic_expand_planar4_kernel(const __grid_constant__ KPlan P, const uint8_t* __restrict__ planar,
+                                                                  uint8_t* __restrict__ out, int to_rgb) {
+  __shared__ __align__(16) uint32_t stage[8][96];
+  const uint32_t gpr = (uint32_t)P.Wo >> 2, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const IdxT total = (IdxT)((uint64_t)P.n_frames * (uint64_t)P.Ho * gpr);
+  const int last_c = (P.last_sample_col / P.f) / P.planar_hs;       // plane column of a line's last sample point
+  const int hs = P.planar_hs;
+  // every warp walks whole groups of 32 granules (the loop bound is warp uniform)
+  for (IdxT base = ((IdxT)blockIdx.x * blockDim.x + threadIdx.x) & ~(IdxT)31; base < total;
+       base += (IdxT)gridDim.x * blockDim.x) {
+    const IdxT idx = base + lane;
+    uint32_t w0 = 0, w1 = 0, w2 = 0;
+    if (idx < total) {
+      const IdxT t = idx / gpr;
+      const uint32_t g = (uint32_t)(idx - t * gpr);
+      const IdxT k = t / (uint32_t)P.Ho;
+      const int ro = (int)(t - k * (uint32_t)P.Ho);
+      const uint8_t* fr = planar + (uint64_t)k * P.out_frame_bytes;
+      const uint8_t* yp = fr + (size_t)ro * P.Wo + 4u * g;
+      uint32_t yw;
+      if ((reinterpret_cast<uintptr_t>(yp) & 3u) == 0) yw = __ldg(reinterpret_cast<const uint32_t*>(yp));
+      else yw = (uint32_t)__ldg(yp) | ((uint32_t)__ldg(yp + 1) << 8) | ((uint32_t)__ldg(yp + 2) << 16) | ((uint32_t)__ldg(yp + 3) << 24);
+      const bool held = P.vf == 2 && ((ro * P.f) & 1);   // only possible for f == 1
+      const size_t crow = (size_t)((held ? ro - 1 : ro) / P.planar_vs) * (size_t)P.planar_cw;
+      const uint8_t* cbp = fr + P.planar_cb_off + crow;
+      const uint8_t* crp = fr + P.planar_cr_off + crow;
+      uint32_t v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int sc = held ? last_c : (int)(4u * g + j) / hs;
+        // consecutive j share a sample when hs > 1: the loads hit the same byte and are served by L1
+        const int y = (int)((yw >> (8 * j)) & 0xFFu), cb = __ldg(cbp + sc), cr = __ldg(crp + sc);
+        v[j] = to_rgb ? inverse_rgb(y, cb, cr) : ((uint32_t)y | ((uint32_t)cb << 8) | ((uint32_t)cr << 16));
+      }
+      w0 = v[0] | (v[1] << 24); w1 = (v[1] >> 8) | (v[2] << 16); w2 = (v[2] >> 16) | (v[3] << 8);
+    }
+    uint32_t* st = stage[warp];
+    st[3 * lane] = w0; st[3 * lane + 1] = w1; st[3 * lane + 2] = w2;
+    __syncwarp();
+    uint8_t* o = out + (uint64_t)base * 12u;             // granule `base` starts here; 384-byte aligned relative to out
+    const uint64_t valid = (uint64_t)(total - base < 32u ? total - base : 32u) * 12u;   // bytes of this group that exist
+    if (lane < 24u) {
+      if ((uint64_t)(lane + 1u) * 16u <= valid) {
+        __stcs(reinterpret_cast<uint4*>(o) + lane, reinterpret_cast<const uint4*>(st)[lane]);
+      } else {
+        for (uint32_t wd = lane * 4u; wd < lane * 4u + 4u; ++wd)
+          if ((uint64_t)(wd + 1u) * 4u <= valid) __stcs(reinterpret_cast<uint32_t*>(o) + wd, st[wd]);
+      }
+    }
+    __syncwarp();
+  }
+}
+
 int launch_expand_planar(const KPlan& k, const uint8_t* planar, uint8_t* out, int to_rgb, void* stream) {
   const uint64_t total = (uint64_t)k.n_frames * (uint64_t)k.Ho * (uint64_t)k.Wo;
   if (total == 0) return (int)cudaSuccess;
+  if (k.Wo % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+    const uint64_t blocks = std::min<uint64_t>((total / 4 + 255) / 256, (uint64_t)148 * 32);
+    if (total / 4 + blocks * 256 < (1ull << 32)) csic_expand_planar4_kernel<uint32_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(k, planar, out, to_rgb);
+    else csic_expand_planar4_kernel<uint64_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(k, planar, out, to_rgb);
+    return (int)cudaGetLastError();
+  }
   const uint64_t blocks = std::min<uint64_t>((total + 255) / 256, (uint64_t)148 * 64);
   csic_expand_planar_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(k, planar, out, to_rgb);
   return (int)cudaGetLastError();

@@ -179,7 +179,10 @@ CSIC_API int csic_process_device(csic_ctx* ctx, const csic_params* p, const void
  * bytes (0 = dense).  When both pitches are multiples of 16 and cover the width rounded up to 16 output pixels
  * (in: that many x factor x bytes-per-pixel; out: that many x 3 or slot bytes) ANY frame width takes the TMA row
  * kernel; columns beyond the frame are read from / written into the row padding.  Dense buffers take it when
- * ceil(W/f) % 16 == 0 and the input row size is a multiple of 16 bytes; everything else runs the generic kernel. */
+ * ceil(W/f) % 16 == 0 and the input row size is a multiple of 16 bytes.  Every other DECIMATE layout -- any width,
+ * pitch or base-pointer alignment -- runs the flex kernel (TMA hull fetch + shifted 16-byte stores); only AVERAGE with
+ * pooling before chroma and spatial-before-chroma shapes whose counter lines are not whole output rows use the
+ * generic gather kernel. */
 CSIC_API int csic_process_device_pitched(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t in_pitch_bytes,
                                          size_t in_frame_stride, size_t n_frames, void* d_out, size_t out_pitch_bytes,
                                          size_t out_frame_stride, void* cuda_stream);
@@ -205,7 +208,7 @@ CSIC_API int csic_band_input_rows(const csic_params* p, int32_t out_row0, int32_
  * buffers (a JVM heap, malloc) are gathered into / scattered from pinned bounce buffers on several host threads.
  * With DECIMATE and f > 1 (and H % f == 0) only the input rows the pipeline reads -- every f-th -- are
  * copied to the device (strided 2-D copy); the result is identical.  Widths that break the TMA kernels' 16-byte
- * rules are re-pitched in the staging buffers, so they avoid the generic kernel too. */
+ * rules are re-pitched in the staging buffers, so they take the TMA row kernel too. */
 CSIC_API int csic_process_host(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, size_t n_frames,
                       uint8_t* out);
 
@@ -231,11 +234,12 @@ CSIC_API int csic_host_free(void* p);
 
 CSIC_API int csic_synchronize(csic_ctx* ctx);
 
-/* Tuning / test knobs (never change results).  KERNEL_FAMILY: 0 = automatic (TMA row kernel whenever
- * the shape satisfies its 16-byte alignment rules, else the generic gather kernel), 1 = always the
- * generic gather kernel.  HOST_CHUNK_BYTES: input bytes per pipelined chunk of csic_process_host.
+/* Tuning / test knobs (never change results).  KERNEL_FAMILY: 0 = automatic (TMA row / pooling kernel whenever
+ * the shape satisfies its 16-byte alignment rules, else the flex kernel, else the generic gather kernel), 1 = always
+ * the generic gather kernel, 2 = never the aligned TMA kernels and no re-pitching in the host path (flex kernel
+ * whenever it is eligible).  HOST_CHUNK_BYTES: input bytes per pipelined chunk of csic_process_host.
  * GRID_CTAS_PER_SM / STAGES / TILE_BYTES: overrides for the row kernel's persistent grid, ring depth and
- * input bytes per tile (0 = auto); HOST_FULL_FRAMES: 1 = csic_process_host copies whole frames even when a
+ * input bytes per tile (0 = auto; STAGES / TILE_BYTES / BLOCK_THREADS also steer the flex kernel); HOST_FULL_FRAMES: 1 = csic_process_host copies whole frames even when a
  * DECIMATE pipeline reads only every f-th row (default 0: ship only the rows that are read); HOST_NO_BOUNCE: 1 =
  * do not stage pageable caller buffers through the context's pinned bounce buffers; BLOCK_THREADS: threads per CTA of the row kernel (multiple of 32, <= 512). */
 enum csic_option { CSIC_OPT_KERNEL_FAMILY = 0, CSIC_OPT_HOST_CHUNK_BYTES = 1, CSIC_OPT_GRID_CTAS_PER_SM = 2,
@@ -246,7 +250,8 @@ CSIC_API int csic_set_option(csic_ctx* ctx, int option, int64_t value);
 CSIC_API int csic_host_bytes(const csic_ctx* ctx, uint64_t* h2d_total);
 
 /* Diagnostics: which kernel family the last process call on this ctx used (0 none, 1 generic gather
- * kernel, 2 TMA-staged row kernel, 3 TMA-staged pooling kernel of the AVERAGE extension) and how many kernels it launched. */
+ * kernel, 2 TMA-staged row kernel, 3 TMA-staged pooling kernel of the AVERAGE extension, 4 any-alignment flex
+ * kernel) and how many kernels it launched. */
 CSIC_API int csic_last_kernel(const csic_ctx* ctx, int32_t* family, int64_t* launches_total);
 
 #ifdef __cplusplus

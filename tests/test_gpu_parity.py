@@ -601,3 +601,47 @@ def test_bounce_buffers_survive_staging_growth(csic, ctx):
             ctx.set_option(1, (8 << 20) * (1 + n % 3))
     finally:
         ctx.set_option(1, 0)
+
+
+def test_full_batch_size_independent_properties(csic, ctx):
+    """BASELINE configs[3] at its FULL size (1024 4K frames, 25.5 GB in / 8.5 GB out on the device), checked through
+    properties that do not need the oracle to replay 8.5 G pixels: (1) three independent kernels (TMA row kernel,
+    flex kernel, generic gather kernel) agree byte for byte on the whole batch; (2) splitting the batch anywhere gives
+    the same bytes (frames are independent: ImageCompressorTopApp.scala:53 builds a fresh DUT per image); (3) duplicated
+    frames give duplicated outputs; (4) the oracle on two frames picked from the ends."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    W, H, a, b, q, f, order, fmt = BASELINE_CFGS["cfg4_4k_420_sf2_bundle128"]
+    n = 1024
+    p, po = both_params(csic, W, H, a, b, q, f, order, 0, 0, fmt)
+    fb = csic.out_shape(p)[3]
+    need = n * (W * H * 3 + 2 * fb) + (2 << 30)
+    if free < need:
+        n = max(16, int((free - (2 << 30)) // (W * H * 3 + 2 * fb)) // 16 * 16)
+    g = torch.Generator(device="cuda").manual_seed(99)
+    rgb = torch.empty((n, H, W, 3), dtype=torch.uint8, device="cuda")
+    for i in range(0, n, 32):
+        rgb[i:i + 32] = torch.randint(0, 256, rgb[i:i + 32].shape, dtype=torch.uint8, device="cuda", generator=g)
+    rgb[n - 1] = rgb[0]                                   # (3) a duplicated frame
+    ctx.set_option(0, 0)
+    out = ctx.process_torch(p, rgb)
+    torch.cuda.synchronize(); ctx.synchronize()
+    assert ctx.last_kernel()[0] == 2
+    other = torch.empty_like(out)
+    for fam, want_fam in ((2, 4), (1, 1)):                # (1)
+        ctx.set_option(0, fam)
+        ctx.process_torch(p, rgb, out=other)
+        torch.cuda.synchronize(); ctx.synchronize()
+        assert ctx.last_kernel()[0] == want_fam
+        assert torch.equal(out, other), f"kernel family {want_fam} disagrees with the row kernel on the full batch"
+    ctx.set_option(0, 0)
+    cut = n // 3 + 1                                      # (2)
+    other.zero_()
+    ctx.process_torch(p, rgb[:cut], out=other[:cut])
+    ctx.process_torch(p, rgb[cut:], out=other[cut:])
+    torch.cuda.synchronize(); ctx.synchronize()
+    assert torch.equal(out, other)
+    assert torch.equal(out[0], out[n - 1])                # (3)
+    for k in (0, n - 2):                                  # (4)
+        want = oracle.process(po, rgb[k].cpu().numpy(), threads=8)[0]
+        assert np.array_equal(out[k].cpu().numpy(), want)
