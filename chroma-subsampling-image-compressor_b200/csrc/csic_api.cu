@@ -560,6 +560,29 @@ static int host_pipeline_run(csic_ctx* ctx, const csic_params* p, const uint8_t*
     }
     return CSIC_OK;
   };
+  // The scatter of chunk j runs on its own host thread, so that it overlaps the gather of chunk j + kPipe - 1 on this
+  // one (each side fans out over parallel_rows_copy's workers).  Joined before its bounce buffer is refilled.
+  struct AsyncDrain {
+    std::thread th;
+    int rc = CSIC_OK;
+    std::string err;
+    int join() {
+      if (th.joinable()) th.join();
+      if (rc != CSIC_OK) g_last_error = err;
+      const int r = rc;
+      rc = CSIC_OK;
+      return r;
+    }
+    ~AsyncDrain() { if (th.joinable()) th.join(); }
+  } adrain;
+  const int device = ctx->device;
+  auto start_drain = [&](size_t j) {
+    adrain.th = std::thread([&adrain, &drain, device, j] {
+      cudaSetDevice(device);
+      adrain.rc = drain(j);
+      if (adrain.rc != CSIC_OK) adrain.err = g_last_error;
+    });
+  };
   // One chunk (small batches, single images): nothing to overlap, so issue copy-in, kernel and copy-out on ONE
   // stream and synchronise once -- no cross-stream events on the latency path.
   const bool single = n_chunks == 1 && !bounce;
@@ -618,6 +641,8 @@ static int host_pipeline_run(csic_ctx* ctx, const csic_params* p, const uint8_t*
       CSIC_CUDA(cudaStreamWaitEvent(s_out, ctx->ev_k[b], 0));
     }
     if (bounce) {
+      rc = adrain.join();                  // chunk c - kPipe has left h_out[b]
+      if (rc != CSIC_OK) return rc;
       uint8_t* hb = static_cast<uint8_t*>(ctx->h_out[b]);
       if (band || lay.out_pitch) {
         CSIC_CUDA(cudaMemcpy2DAsync(hb, g.out_row_bytes, d_out, out_pitch, g.out_row_bytes, nf * (size_t)rows,
@@ -638,12 +663,11 @@ static int host_pipeline_run(csic_ctx* ctx, const csic_params* p, const uint8_t*
                                 s_out));
     }
     if (!single) CSIC_CUDA(cudaEventRecord(ctx->ev_d2h[b], s_out));
-    if (bounce && c + 1 >= (size_t)kPipe) {          // overlap: scatter the chunk issued kPipe-1 iterations ago
-      rc = drain(c + 1 - (size_t)kPipe);
-      if (rc != CSIC_OK) return rc;
-    }
+    if (bounce && c + 1 >= (size_t)kPipe) start_drain(c + 1 - (size_t)kPipe);   // the chunk issued kPipe-1 iterations ago
   }
   if (bounce) {
+    rc = adrain.join();
+    if (rc != CSIC_OK) return rc;
     for (size_t j = n_chunks >= (size_t)kPipe ? n_chunks - ((size_t)kPipe - 1) : 0; j < n_chunks; ++j) {
       rc = drain(j);
       if (rc != CSIC_OK) return rc;
