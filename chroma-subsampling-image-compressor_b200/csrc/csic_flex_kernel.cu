@@ -138,16 +138,17 @@ __device__ __forceinline__ uint32_t lds_px(uint32_t a) {
 
 // The four sampled pixels of a whole granule: input pixels at a, a + pxb, a + 2 pxb, a + 3 pxb (pxb = bytes between
 // sampled pixels: 3, 6, 12, 24 for RGB24 at f = 1, 2, 4, 8; 4, 8, 16, 32 for the 4-byte formats).
+template <uint32_t PXB>   // 3, 6, or 0 = any multiple of four (passed at run time)
 __device__ __forceinline__ void load_granule_any(uint32_t a, uint32_t pxb, uint32_t (&p)[4]) {
   const uint32_t b = a & ~3u, sh = (a & 3u) * 8u;
-  if (pxb == 3u) {             // 12 consecutive bytes: word stride 3 across lanes, conflict free
+  if (PXB == 3u) {             // 12 consecutive bytes: word stride 3 across lanes, conflict free
     const uint32_t w0 = lds32(b), w1 = lds32(b + 4), w2 = lds32(b + 8), w3 = lds32(b + 12);
     const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
     p[0] = v0;
     p[1] = __funnelshift_r(v0, v1, 24);
     p[2] = __funnelshift_r(v1, v2, 16);
     p[3] = v2 >> 8;
-  } else if (pxb == 6u) {      // 21 bytes inside six words
+  } else if (PXB == 6u) {      // 21 bytes inside six words
     const uint32_t w0 = lds32(b), w1 = lds32(b + 4), w2 = lds32(b + 8), w3 = lds32(b + 12), w4 = lds32(b + 16), w5 = lds32(b + 20);
     p[0] = __funnelshift_r(w0, w1, sh);                                                          // bytes 0..2
     p[1] = __funnelshift_r(__funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), 16);        // bytes 6..8
@@ -313,23 +314,23 @@ __global__ void __launch_bounds__(kFlexMaxThreads) csic_flex_kernel(const __grid
     const uint32_t ccols = (D.npx + (1u << hs_sh) - 1u) >> hs_sh;
     const uint32_t cb_s = out_s + D.nrows * st_mul + 16u, cr_s = cb_s + nrc * ccols;
     const uint32_t last_px = D.npx - 1u;
-    // the loop is instantiated per chroma hold width (1, 2 or 4 output pixels): no per-granule branches or moves
-    auto compute = [&](auto hfe_tag) {
-      constexpr uint32_t HFE = decltype(hfe_tag)::value;
-      for (uint32_t q = tid; q < n_gran; q += NC) {
-        const uint32_t row = gpr > 1u ? __umulhi(q, gpr_magic) : q, g = q - row * gpr;
-        const uint32_t rs = in_s + row * rs_mul + ((D.a0 + row * rs_add) & 15u);
+    // the loop is instantiated per chroma hold width (1, 2 or 4 output pixels) and per pixel stride class: no
+    // per-granule branches or moves
+    auto compute = [&](auto hfe_tag, auto pxb_tag) {
+      constexpr uint32_t HFE = decltype(hfe_tag)::value, PXB = decltype(pxb_tag)::value;
+      // one granule: (row, g) of the tile; rs = shared address of the row's first input byte, so_row = of its staging
+      // row, hv = the row's held pixel (0: the row samples its own chroma)
+      auto granule = [&](uint32_t row, uint32_t g, uint32_t rs, uint32_t so_row, uint32_t hv) {
         const uint32_t c = g * 4u;
         uint32_t p[4], dy[4], xb[4], xr[4];
         if (c + 3u <= last_px) {
-          load_granule_any(rs + c * pxb, pxb, p);
+          load_granule_any<PXB>(rs + c * pxb, pxb, p);
         } else {
   #pragma unroll
           for (int j = 0; j < 4; ++j) p[j] = lds_px(rs + min(c + j, last_px) * pxb);
         }
   #pragma unroll
         for (int j = 0; j < 4; ++j) dy[j] = fwd_y16(p[j], P.coef_y);
-        const uint32_t hv = vhold ? lds32(held_s + row * 4u) : 0u;
         if (hv) {
           const uint32_t hb = fwd_nc16<TRUNC>(hv & 0x00FFFFFFu, P.coef_ncb), hr = fwd_nc16<TRUNC>(hv & 0x00FFFFFFu, P.coef_ncr);
   #pragma unroll
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(kFlexMaxThreads) csic_flex_kernel(const __grid
           if (HFE == 1) { xb[3] = fwd_nc16<TRUNC>(p[3], P.coef_ncb); xr[3] = fwd_nc16<TRUNC>(p[3], P.coef_ncr); }
           else { xb[3] = xb[2]; xr[3] = xr[2]; }
         }
-        const uint32_t so = out_s + row * st_mul + ((oa0 + row * st_add) & 12u) + g * kUnit;
+        const uint32_t so = so_row + g * kUnit;
         if (FMT == KF_YCC888) {
           // byte 1 of dy is Y, byte 1 of xb/xr is ~Cb/~Cr: gather with PRMT, flip and quantise per word
           uint32_t t, u;
@@ -404,11 +405,29 @@ __global__ void __launch_bounds__(kFlexMaxThreads) csic_flex_kernel(const __grid
             sts32(so, v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
           }
         }
+      };
+      auto row_in = [&](uint32_t row) { return in_s + row * rs_mul + ((D.a0 + row * rs_add) & 15u); };
+      auto row_st = [&](uint32_t row) { return out_s + row * st_mul + ((oa0 + row * st_add) & 12u); };
+      if (gpr >= NC) {             // wide rows: row by row, nothing row-dependent inside the loop
+        for (uint32_t row = 0; row < D.nrows; ++row) {
+          const uint32_t rs = row_in(row), so_row = row_st(row), hv = vhold ? lds32(held_s + row * 4u) : 0u;
+          for (uint32_t g = tid; g < gpr; g += NC) granule(row, g, rs, so_row, hv);
+        }
+      } else {                     // narrow rows: one flat loop over the tile's granules
+        for (uint32_t q = tid; q < n_gran; q += NC) {
+          const uint32_t row = gpr > 1u ? __umulhi(q, gpr_magic) : q, g = q - row * gpr;
+          granule(row, g, row_in(row), row_st(row), vhold ? lds32(held_s + row * 4u) : 0u);
+        }
       }
     };
-    if (hfe == 1u) compute(std::integral_constant<uint32_t, 1u>{});
-    else if (hfe == 2u) compute(std::integral_constant<uint32_t, 2u>{});
-    else compute(std::integral_constant<uint32_t, 4u>{});
+    auto compute_hfe = [&](auto pxb_tag) {
+      if (hfe == 1u) compute(std::integral_constant<uint32_t, 1u>{}, pxb_tag);
+      else if (hfe == 2u) compute(std::integral_constant<uint32_t, 2u>{}, pxb_tag);
+      else compute(std::integral_constant<uint32_t, 4u>{}, pxb_tag);
+    };
+    if (pxb == 3u) compute_hfe(std::integral_constant<uint32_t, 3u>{});         // RGB24, f = 1
+    else if (pxb == 6u) compute_hfe(std::integral_constant<uint32_t, 6u>{});    // RGB24, f = 2
+    else compute_hfe(std::integral_constant<uint32_t, 0u>{});                   // sampled pixels on a common byte phase
     consumer_barrier(NC);          // staging complete; every read of input stage s, its held words and descriptor is done
     if (tid == 0) mbar_arrive(empty0 + s * 8u);
 
