@@ -50,6 +50,10 @@ WORKLOADS = {
               "cfg3 geometry with PLANAR 4:2:0 output (Y plane + quarter-size Cb/Cr planes, 1.5 B/px out)"),
     "cfg4avg": (3840, 2160, 1024, 2, 0, (8, 8, 8), 2, "CSQ", 3,
                 "AVERAGE-pooling extension on the cfg4 geometry: 4:2:0 + 2x2 mean + BUNDLE128 (reads every row)"),
+    "cfg4savg": (3840, 2160, 1024, 2, 0, (8, 8, 8), 2, "SQC", 3,
+                 "AVERAGE-pooling extension, pooling BEFORE chroma (the app's default order) on the cfg4 geometry"),
+    "cfg5savg": (7680, 4320, 64, 2, 0, (6, 5, 5), 4, "SQC", 1,
+                 "AVERAGE-pooling extension, pooling BEFORE chroma on the cfg5 geometry: 4x4 mean + Q_16BIT + RGB888"),
     "cfg5avg": (7680, 4320, 64, 2, 0, (6, 5, 5), 4, "CSQ", 1,
                 "AVERAGE-pooling extension on the cfg5 geometry: 4:2:0 + 4x4 mean + Q_16BIT + RGB888"),
     "cfg3odd": (1918, 1078, 256, 2, 0, (4, 4, 4), 1, "CSQ", 0,

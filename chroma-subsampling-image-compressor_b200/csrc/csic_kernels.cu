@@ -403,7 +403,13 @@ int rows_kernel_set_attributes(size_t max_smem_optin) {
 // ---- AVERAGE extension: planning and dispatch of csic_pool_kernel --------------------------------
 bool plan_pool_kernel(KPlan& k, int sm_count, size_t max_smem_optin) {
   if (!(k.average && k.f > 1)) return false;
-  if (k.case_b) return false;                                   // pooling before chroma: generic kernel
+  if (k.case_b) {
+    // pooling before chroma: a counter line (W == f * Wo stream elements) must be whole output rows that start on a
+    // sample column; the held block of an odd line is the stream element (line-1) * W + lastSampleCol
+    if (k.W % k.f != 0 || k.Wo % k.hf != 0) return false;
+    k.caseb_row_add = (uint32_t)k.last_sample_col / (uint32_t)k.Wo;
+    k.caseb_col_bytes = ((uint32_t)k.last_sample_col % (uint32_t)k.Wo) * (uint32_t)k.in_px_bytes * (uint32_t)k.f;
+  }
   if (k.Wo % 16 != 0 || k.in_row_bytes % 16 != 0) return false;
   if ((reinterpret_cast<uintptr_t>(k.in) | reinterpret_cast<uintptr_t>(k.out)) & 15u) return false;
   if ((k.in_frame_bytes | k.out_frame_bytes | k.out_row_bytes) & 15u) return false;

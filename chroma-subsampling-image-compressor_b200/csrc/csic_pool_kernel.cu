@@ -10,6 +10,11 @@
 //   chroma hold    in-row: sample at i % hf == 0 inside the 4F-pixel span; odd lines of 4:2:0 / 4:1:0 replay the
 //                  last sample of the line above, which is the previous row part of the same block
 //                  (ChromaSubsampler.scala:52-65); when rows are split into segments it is TMA-fetched instead.
+// Pooling BEFORE the chroma stage (SQC / SCQ / QSC: the application's default order, ImageCompressorTopApp.scala:170-173)
+// runs here too when a counter line is whole output rows starting on a sample column (ceil(W/f) % hf == 0): every
+// channel is pooled first, the chroma stage then samples the pooled stream with the full-size counters
+// (ImageCompressorTop.scala:52-58) -- in-row hold between output pixels, and on odd counter lines every pixel replays
+// the pooled chroma of ONE block of the line above, which the producer warp reduces itself (f x f pixels, lanes = pixels).
 // Compiled once per F = CSIC_POOL_F (2, 4, 8).
 #include <cuda_runtime.h>
 
@@ -43,6 +48,7 @@ struct PoolConst {
   uint32_t gran_per_row, nthreads, row0_of_thread, rem0_of_thread, drow, drem;
   uint32_t seg_row_bytes;
   bool trunc, vhold;
+  bool pool_first;                    // pooling precedes the chroma stage: held_addr[] holds pooled pairs, not addresses
 };
 
 // 4F consecutive input pixels of one row part, each as a word whose low three bytes are the colour bytes.
@@ -85,6 +91,7 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
   for (uint32_t q = threadIdx.x; q < n; q += C.nthreads) {
     int ay[4] = {0, 0, 0, 0}, ab[4] = {0, 0, 0, 0}, ar[4] = {0, 0, 0, 0};
     const uint32_t base = in_s + row * (F * C.seg_row_bytes) + rem * kGranBytes;
+    const uint32_t held_pair = C.pool_first ? meta->held_addr[row] : 0u;   // bit 31 | pooled Cb << 8 | pooled Cr
 #pragma unroll 1
     for (int dr = 0; dr < F; ++dr) {
       uint32_t p[4 * F];
@@ -108,7 +115,19 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
           }
         }
       }
-      if (C.vhold && (dr & 1)) {
+      if (C.pool_first) {
+        // every pixel's own chroma is pooled; only output pixels on a sample column are needed (the others replay
+        // them after the pooling), and rows of an odd counter line replay a pooled pair the producer supplies
+        if (!held_pair) {
+#pragma unroll
+          for (int i = 0; i < 4 * F; ++i) {
+            if ((i / F) % HF == 0) {
+              ab[i / F] += (int)(((fwd_nc16<TRUNC>(p[i], C.coef_ncb) ^ 0xFFFFu) >> 8) & C.pre_cb);
+              ar[i / F] += (int)(((fwd_nc16<TRUNC>(p[i], C.coef_ncr) ^ 0xFFFFu) >> 8) & C.pre_cr);
+            }
+          }
+        }
+      } else if (C.vhold && (dr & 1)) {
         // nothing is sampled on an odd line: every pixel replays the last sample of the line above
         const uint32_t ha = meta->held_addr[row * (F / 2) + (uint32_t)(dr >> 1)];
         const uint32_t hp = lds8(ha) | (lds8(ha + 1) << 8) | (lds8(ha + 2) << 16);
@@ -135,6 +154,13 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
       y[o] = (uint32_t)((ay[o] + kHalf) >> kShift) & C.post_y;
       cb[o] = (uint32_t)((ab[o] + kHalf) >> kShift) & C.post_cb;
       cr[o] = (uint32_t)((ar[o] + kHalf) >> kShift) & C.post_cr;
+    }
+    if (C.pool_first) {                // the chroma stage on the pooled stream (ChromaSubsampler.scala:57-65)
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        if (held_pair) { cb[o] = (held_pair >> 8) & 0xFFu & C.post_cb; cr[o] = held_pair & 0xFFu & C.post_cr; }
+        else if (o % HF != 0) { cb[o] = cb[o - o % HF]; cr[o] = cr[o - o % HF]; }
+      }
     }
     if (FMT == KF_YCC888 || FMT == KF_RGB888) {
       uint32_t w0, w1, w2;
@@ -190,8 +216,11 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_pool_kernel(con
 
   // ============================== producer warp ==============================================
   if (tid >= NC) {
-    if (tid != NC) return;
+    const bool pool_first = P.case_b != 0;
+    const uint32_t lane = tid - NC;
+    if (lane != 0 && !pool_first) return;        // chroma-first orders: one lane feeds the TMA engine
     const uint32_t ipb = (uint32_t)P.in_px_bytes;
+    uint32_t cached_line = 0xFFFFFFFFu, cached_pair = 0;
     for (uint32_t i = 0; i < n_my; ++i) {
       const uint32_t s = i % S;
       if (i >= S) mbar_wait(empty_bar + s * 8u, ((i / S) - 1u) & 1u);
@@ -210,7 +239,39 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_pool_kernel(con
 
       uint32_t n_aux = 0;
       const uint8_t* aux_src[kMaxTileRows];
-      if (P.vf == 2) {
+      if (pool_first) {
+        // Rows of an odd counter line (a line = F output rows, W == F * Wo) replay the pooled chroma of the block at
+        // stream element (line-1) * W + lastSampleCol of the pooled stream.  The warp reduces that block itself:
+        // lane l takes pixels l, l + 32 of the F x F block.
+        constexpr int kShift = (CSIC_POOL_F == 2) ? 2 : (CSIC_POOL_F == 4 ? 4 : 6);
+        const uint32_t mcb = P.quant_first ? (P.qmask >> 8) & 0xFFu : 0xFFu, mcr = P.quant_first ? (P.qmask >> 16) & 0xFFu : 0xFFu;
+        for (uint32_t j = 0; j < nrows; ++j) {
+          const uint32_t line = (ro0 + j) / F;
+          uint32_t pair = 0;
+          if (P.vf == 2 && (line & 1u)) {
+            if (line != cached_line) {
+              const uint8_t* blk = frame + (uint64_t)(((line - 1u) * F + P.caseb_row_add) * F) * P.in_row_bytes + P.caseb_col_bytes;
+              int sb = 0, sr = 0;
+              for (uint32_t e = lane; e < F * F; e += 32u) {
+                const uint8_t* px = blk + (uint64_t)(e / F) * P.in_row_bytes + (e % F) * ipb;
+                const uint32_t v = (uint32_t)__ldg(px) | ((uint32_t)__ldg(px + 1) << 8) | ((uint32_t)__ldg(px + 2) << 16);
+                const uint32_t xb = P.trunc ? fwd_nc16<true>(v, P.coef_ncb) : fwd_nc16<false>(v, P.coef_ncb);
+                const uint32_t xr = P.trunc ? fwd_nc16<true>(v, P.coef_ncr) : fwd_nc16<false>(v, P.coef_ncr);
+                sb += (int)(((xb ^ 0xFFFFu) >> 8) & mcb);
+                sr += (int)(((xr ^ 0xFFFFu) >> 8) & mcr);
+              }
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) { sb += __shfl_xor_sync(0xFFFFFFFFu, sb, o); sr += __shfl_xor_sync(0xFFFFFFFFu, sr, o); }
+              cached_pair = 0x80000000u | ((uint32_t)((sb + (F * F) / 2) >> kShift) << 8) | (uint32_t)((sr + (F * F) / 2) >> kShift);
+              cached_line = line;
+            }
+            pair = cached_pair;
+          }
+          if (lane == 0) m->held_addr[j] = pair;
+        }
+        __syncwarp();
+        if (lane != 0) continue;                  // the rest is lane 0's: describe the tile, feed the TMA engine
+      } else if (P.vf == 2) {
         for (uint32_t j = 0; j < nrows; ++j)
           for (uint32_t h = 0; h < F / 2; ++h) {       // odd input line dr = 2h+1 replays (dr-1, lastSampleCol)
             const uint32_t e = j * (F / 2) + h;
@@ -264,6 +325,7 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_pool_kernel(con
     C.seg_row_bytes = seg_row_bytes;
     C.trunc = P.trunc != 0;
     C.vhold = P.vf == 2;
+    C.pool_first = P.case_b != 0;
   }
   const int hf = P.hf;
 

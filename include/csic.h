@@ -180,9 +180,9 @@ CSIC_API int csic_process_device(csic_ctx* ctx, const csic_params* p, const void
  * (in: that many x factor x bytes-per-pixel; out: that many x 3 or slot bytes) ANY frame width takes the TMA row
  * kernel; columns beyond the frame are read from / written into the row padding.  Dense buffers take it when
  * ceil(W/f) % 16 == 0 and the input row size is a multiple of 16 bytes.  Every other DECIMATE layout -- any width,
- * pitch or base-pointer alignment -- runs the flex kernel (TMA hull fetch + shifted 16-byte stores); only AVERAGE with
- * pooling before chroma and spatial-before-chroma shapes whose counter lines are not whole output rows use the
- * generic gather kernel. */
+ * pitch or base-pointer alignment -- runs the flex kernel (TMA hull fetch + shifted 16-byte stores); only AVERAGE on
+ * unaligned shapes and spatial-before-chroma shapes whose counter lines are not whole output rows use the
+ * generic gather kernel (AVERAGE: the TMA pooling kernel on 16-byte-aligned shapes, any stage order). */
 CSIC_API int csic_process_device_pitched(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t in_pitch_bytes,
                                          size_t in_frame_stride, size_t n_frames, void* d_out, size_t out_pitch_bytes,
                                          size_t out_frame_stride, void* cuda_stream);
