@@ -207,7 +207,8 @@ __global__ void __launch_bounds__(256) csic_expand_planar4_kernel(const __grid_c
   const uint32_t gpr = (uint32_t)P.Wo >> 2, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const IdxT total = (IdxT)((uint64_t)P.n_frames * (uint64_t)P.Ho * gpr);
   const int last_c = (P.last_sample_col / P.f) / P.planar_hs;       // plane column of a line's last sample point
-  const int hs = P.planar_hs;
+  const int hs_sh = P.planar_hs == 4 ? 2 : (P.planar_hs == 2 ? 1 : 0), vs_sh = P.planar_vs == 2 ? 1 : 0;   // 1, 2, 4 / 1, 2
+  const bool vhold = P.vf == 2 && P.f == 1;                         // odd lines replay the line above (f == 1 only)
   // every warp walks whole groups of 32 granules (the loop bound is warp uniform)
   for (IdxT base = ((IdxT)blockIdx.x * blockDim.x + threadIdx.x) & ~(IdxT)31; base < total;
        base += (IdxT)gridDim.x * blockDim.x) {
@@ -223,14 +224,14 @@ __global__ void __launch_bounds__(256) csic_expand_planar4_kernel(const __grid_c
       uint32_t yw;
       if ((reinterpret_cast<uintptr_t>(yp) & 3u) == 0) yw = __ldg(reinterpret_cast<const uint32_t*>(yp));
       else yw = (uint32_t)__ldg(yp) | ((uint32_t)__ldg(yp + 1) << 8) | ((uint32_t)__ldg(yp + 2) << 16) | ((uint32_t)__ldg(yp + 3) << 24);
-      const bool held = P.vf == 2 && ((ro * P.f) & 1);   // only possible for f == 1
-      const size_t crow = (size_t)((held ? ro - 1 : ro) / P.planar_vs) * (size_t)P.planar_cw;
+      const bool held = vhold && (ro & 1);
+      const size_t crow = (size_t)((held ? ro - 1 : ro) >> vs_sh) * (size_t)P.planar_cw;
       const uint8_t* cbp = fr + P.planar_cb_off + crow;
       const uint8_t* crp = fr + P.planar_cr_off + crow;
       uint32_t v[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int sc = held ? last_c : (int)(4u * g + j) / hs;
+        const int sc = held ? last_c : (int)((4u * g + j) >> hs_sh);
         // consecutive j share a sample when hs > 1: the loads hit the same byte and are served by L1
         const int y = (int)((yw >> (8 * j)) & 0xFFu), cb = __ldg(cbp + sc), cr = __ldg(crp + sc);
         v[j] = to_rgb ? inverse_rgb(y, cb, cr) : ((uint32_t)y | ((uint32_t)cb << 8) | ((uint32_t)cr << 16));
