@@ -48,6 +48,8 @@ struct PoolConst {
   uint32_t gran_per_row, nthreads, row0_of_thread, rem0_of_thread, drow, drem;
   uint32_t seg_row_bytes;
   bool trunc, vhold;
+  bool linear_y;                      // ... same for Y: byte 1 of each dp4a result is accumulated by a second dp4a
+  bool linear;                        // no quantiser in front of the pooling: chroma sums in the complement domain
   bool pool_first;                    // pooling precedes the chroma stage: held_addr[] holds pooled pairs, not addresses
 };
 
@@ -103,7 +105,10 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
         uint32_t d[F];
 #pragma unroll
         for (int i = 0; i < F; ++i) d[i] = fwd_y16(p[o * F + i], C.coef_y);
-        if (F == 2) {
+        if (C.linear_y) {          // no quantiser in front: byte 1 of every result goes straight into the sum (FMA pipe)
+#pragma unroll
+          for (int i = 0; i < F; ++i) ay[o] = (int)dp4a_uu(d[i], 1u << 8, (uint32_t)ay[o]);
+        } else if (F == 2) {
           const uint32_t w = __byte_perm(d[0], d[1], 0x3351) & C.pre_y4;
           ay[o] = (int)dp4a_uu(w, 0x01010101u, (uint32_t)ay[o]);
         } else {
@@ -115,9 +120,49 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
           }
         }
       }
-      if (C.pool_first) {
-        // every pixel's own chroma is pooled; only output pixels on a sample column are needed (the others replay
-        // them after the pooling), and rows of an odd counter line replay a pooled pair the producer supplies
+      if (C.linear) {
+        // No quantiser in front of the pooling: the chroma value is 255 - byte1(x) (x = fwd_nc16 < 65536), so the sums are
+        // taken in the complement domain -- weight * byte1(x) accumulated by ONE dp4a per sample and channel (coefficient
+        // `weight` on byte 1), on the FMA pipe instead of four ALU-pipe instructions -- and flipped once after the loop.
+        if (C.pool_first) {
+          // every pixel's own chroma is pooled; only output pixels on a sample column are needed (the others replay
+          // them after the pooling), and rows of an odd counter line replay a pooled pair the producer supplies
+          if (!held_pair) {
+#pragma unroll
+            for (int i = 0; i < 4 * F; ++i) {
+              if ((i / F) % HF == 0) {
+                ab[i / F] = (int)dp4a_uu(fwd_nc16<TRUNC>(p[i], C.coef_ncb), 1u << 8, (uint32_t)ab[i / F]);
+                ar[i / F] = (int)dp4a_uu(fwd_nc16<TRUNC>(p[i], C.coef_ncr), 1u << 8, (uint32_t)ar[i / F]);
+              }
+            }
+          }
+        } else if (C.vhold && (dr & 1)) {
+          // nothing is sampled on an odd line: every pixel replays the last sample of the line above
+          const uint32_t ha = meta->held_addr[row * (F / 2) + (uint32_t)(dr >> 1)];
+          const uint32_t hp = lds8(ha) | (lds8(ha + 1) << 8) | (lds8(ha + 2) << 16);
+          const uint32_t xb = fwd_nc16<TRUNC>(hp, C.coef_ncb), xr = fwd_nc16<TRUNC>(hp, C.coef_ncr);
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            ab[o] = (int)dp4a_uu(xb, (uint32_t)F << 8, (uint32_t)ab[o]);
+            ar[o] = (int)dp4a_uu(xr, (uint32_t)F << 8, (uint32_t)ar[o]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4 * F; i += HF) {   // sample points; each is held for HF pixels (ChromaSubsampler.scala:57-65)
+            const uint32_t xb = fwd_nc16<TRUNC>(p[i], C.coef_ncb), xr = fwd_nc16<TRUNC>(p[i], C.coef_ncr);
+            if (HF <= F) {                        // the HF pixels lie inside one output pixel
+              ab[i / F] = (int)dp4a_uu(xb, (uint32_t)HF << 8, (uint32_t)ab[i / F]);
+              ar[i / F] = (int)dp4a_uu(xr, (uint32_t)HF << 8, (uint32_t)ar[i / F]);
+            } else {                              // ... or cover HF / F whole output pixels
+#pragma unroll
+              for (int o = i / F; o < (i + HF) / F; ++o) {
+                ab[o] = (int)dp4a_uu(xb, (uint32_t)F << 8, (uint32_t)ab[o]);
+                ar[o] = (int)dp4a_uu(xr, (uint32_t)F << 8, (uint32_t)ar[o]);
+              }
+            }
+          }
+        }
+      } else if (C.pool_first) {
         if (!held_pair) {
 #pragma unroll
           for (int i = 0; i < 4 * F; ++i) {
@@ -128,7 +173,6 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
           }
         }
       } else if (C.vhold && (dr & 1)) {
-        // nothing is sampled on an odd line: every pixel replays the last sample of the line above
         const uint32_t ha = meta->held_addr[row * (F / 2) + (uint32_t)(dr >> 1)];
         const uint32_t hp = lds8(ha) | (lds8(ha + 1) << 8) | (lds8(ha + 2) << 16);
         const int hb = (int)(((fwd_nc16<TRUNC>(hp, C.coef_ncb) ^ 0xFFFFu) >> 8) & C.pre_cb) * F;
@@ -147,6 +191,10 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
           ar[i / F] += cr;
         }
       }
+    }
+    if (C.linear) {                    // back from the complement domain: F*F samples of weight 1 each
+#pragma unroll
+      for (int o = 0; o < 4; ++o) { ab[o] = 255 * F * F - ab[o]; ar[o] = 255 * F * F - ar[o]; }
     }
     uint32_t y[4], cb[4], cr[4];
 #pragma unroll
@@ -326,6 +374,8 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_pool_kernel(con
     C.trunc = P.trunc != 0;
     C.vhold = P.vf == 2;
     C.pool_first = P.case_b != 0;
+    C.linear = C.pre_cb == 0xFFu && C.pre_cr == 0xFFu;
+    C.linear_y = F == 2 && C.pre_y == 0xFFu;   // B200: pays for 2x2 only (4x4: the PRMT gather + one dp4a is cheaper)
   }
   const int hf = P.hf;
 
