@@ -119,14 +119,24 @@ __device__ __forceinline__ void span_store(uint8_t* __restrict__ g, uint32_t ssr
   }
 }
 
-// `n` row spans of `len` bytes: one after the other with the whole CTA when they are long, one warp per span when short.
+// n and m powers of two, n <= m  (no division: this runs once per tile in every thread)
+__device__ __forceinline__ bool pow2_divides(uint32_t n, uint32_t m) {
+  return n != 0u && (n & (n - 1u)) == 0u && (m & (m - 1u)) == 0u && n <= m;
+}
+
+// `n` row spans of `len` bytes: long ones share the warps (or go one after the other with the whole CTA when their
+// number does not divide the warps), short ones take one warp each.
 template <typename F>
 __device__ __forceinline__ void for_each_span(uint32_t n, uint32_t len, uint32_t NC, F&& fn) {
-  const uint32_t tid = threadIdx.x;
-  if (len >= kCtaWideSpan || n == 1) {
+  const uint32_t tid = threadIdx.x, NW = NC >> 5;
+  if ((len >= kCtaWideSpan || n == 1) && pow2_divides(n, NW)) {      // few long spans: NW / n warps each, set up once per warp
+    const uint32_t sh = 31u - __clz(NW) - (31u - __clz(n));                // log2(NW / n): both powers of two
+    const uint32_t parts = 1u << sh, j = (tid >> 5) >> sh, part = (tid >> 5) & (parts - 1u);
+    fn(j, part * 32u + (tid & 31u), parts * 32u);
+  } else if (len >= kCtaWideSpan || n == 1) {
     for (uint32_t j = 0; j < n; ++j) fn(j, tid, NC);
   } else {
-    for (uint32_t j = tid >> 5; j < n; j += NC >> 5) fn(j, tid & 31u, 32u);
+    for (uint32_t j = tid >> 5; j < n; j += NW) fn(j, tid & 31u, 32u);
   }
 }
 
@@ -178,7 +188,7 @@ static_assert(sizeof(FlexDesc) == kDescBytes, "kDescBytes out of sync");
 }  // namespace
 
 template <int FMT, bool TRUNC>
-__global__ void __launch_bounds__(kFlexMaxThreads) csic_flex_kernel(const __grid_constant__ KPlan P) {
+__global__ void __launch_bounds__(kFlexMaxThreads, 4) csic_flex_kernel(const __grid_constant__ KPlan P) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr uint32_t kUnit = FlexFmt<FMT>::kUnit, kOpx = kUnit / 4u;
   const uint32_t tid = threadIdx.x, NT = blockDim.x;
@@ -252,7 +262,7 @@ __global__ void __launch_bounds__(kFlexMaxThreads) csic_flex_kernel(const __grid
         if (!P.case_b) {
           if (f == 1 && (ro & 1u)) hp = frame + (uint64_t)(ro - 1u) * P.in_row_bytes + (uint32_t)P.last_sample_col * ipb;
         } else {
-          const uint32_t line = ro / f;        // W == f * Wo: one counter line spans f output rows
+          const uint32_t line = ro >> (31u - __clz(f));   // ro / f (f is 1, 2, 4 or 8); W == f * Wo: one counter line spans f output rows
           if (line & 1u) {
             const uint32_t srow = (line - 1u) * f + P.caseb_row_add;
             hp = frame + (uint64_t)(srow * (uint32_t)P.row_step) * P.in_row_bytes + P.caseb_col_bytes;
@@ -298,7 +308,6 @@ __global__ void __launch_bounds__(kFlexMaxThreads) csic_flex_kernel(const __grid
     const uint32_t in_s = sbase + s * in_stage, held_s = held_base + s * (uint32_t)kMaxTileRows * 4u;
     const uint32_t gpr = (D.ncols + 3u) >> 2;                  // granules per row
     const uint32_t n_gran = D.nrows * gpr, srow = gpr * kUnit;
-    const uint32_t gpr_magic = gpr > 1u ? 0xFFFFFFFFu / gpr + 1u : 0u;   // q / gpr == umulhi(q, magic) for q < 65536
     const uint32_t row_out = D.ncols * kOpx;
     uint8_t* fout = P.out + (uint64_t)D.k * P.out_frame_bytes;
     uint8_t* obase = fout + (uint64_t)D.ro0 * P.out_row_bytes + (uint64_t)D.col0 * kOpx;
@@ -408,12 +417,25 @@ __global__ void __launch_bounds__(kFlexMaxThreads) csic_flex_kernel(const __grid
       };
       auto row_in = [&](uint32_t row) { return in_s + row * rs_mul + ((D.a0 + row * rs_add) & 15u); };
       auto row_st = [&](uint32_t row) { return out_s + row * st_mul + ((oa0 + row * st_add) & 12u); };
-      if (gpr >= NC) {             // wide rows: row by row, nothing row-dependent inside the loop
+      const uint32_t NW = NC >> 5;
+      if (gpr >= NC && pow2_divides(D.nrows, NW)) {   // wide rows that divide the warps: NW / nrows warps per row, set up once
+        const uint32_t sh = 31u - __clz(NW) - (31u - __clz(D.nrows));      // log2(NW / nrows): both powers of two
+        const uint32_t parts = 1u << sh, row = (tid >> 5) >> sh, part = (tid >> 5) & (parts - 1u);
+        const uint32_t rs = row_in(row), so_row = row_st(row), hv = vhold ? lds32(held_s + row * 4u) : 0u;
+        for (uint32_t g = part * 32u + (tid & 31u); g < gpr; g += parts * 32u) granule(row, g, rs, so_row, hv);
+      } else if (gpr >= NC) {      // wide rows: row by row, nothing row-dependent inside the loop
         for (uint32_t row = 0; row < D.nrows; ++row) {
           const uint32_t rs = row_in(row), so_row = row_st(row), hv = vhold ? lds32(held_s + row * 4u) : 0u;
           for (uint32_t g = tid; g < gpr; g += NC) granule(row, g, rs, so_row, hv);
         }
+      } else if ((gpr & 31u) == 0u && (NW & (NW - 1u)) == 0u && (D.nrows & (NW - 1u)) == 0u) {
+        // narrow rows that fill whole warps, a whole number of rows per warp: row by row per warp
+        for (uint32_t row = tid >> 5; row < D.nrows; row += NW) {
+          const uint32_t rs = row_in(row), so_row = row_st(row), hv = vhold ? lds32(held_s + row * 4u) : 0u;
+          for (uint32_t g = tid & 31u; g < gpr; g += 32u) granule(row, g, rs, so_row, hv);
+        }
       } else {                     // narrow rows: one flat loop over the tile's granules
+        const uint32_t gpr_magic = gpr > 1u ? 0xFFFFFFFFu / gpr + 1u : 0u;   // q / gpr == umulhi(q, magic) for q < 65536
         for (uint32_t q = tid; q < n_gran; q += NC) {
           const uint32_t row = gpr > 1u ? __umulhi(q, gpr_magic) : q, g = q - row * gpr;
           granule(row, g, row_in(row), row_st(row), vhold ? lds32(held_s + row * 4u) : 0u);
