@@ -1,8 +1,8 @@
 #!/usr/bin/env bash
 # Evidence for the flex kernel (run under gpurun): parity suite, bench lines, launch list, one full ncu capture.
 set -u
-O=gpurun_out/flexfinal; mkdir -p $O
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > $O/pytest.log; cat $O/pytest.log
+O=gpurun_out/flexfinal2; mkdir -p $O
+
 for wl in cfg4odd cfg3odd; do
   python bench.py --workload $wl --steps 50 --warmup 5 --no-e2e --no-cpu > $O/bench_${wl}_flex.json 2> $O/bench_${wl}.err
 done
@@ -17,7 +17,7 @@ $CMD > $O/plain2.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k "regex:csic_flex_kernel" -s 4 -c 1 -f -o $O/prof_cfg4odd_flex $CMD > $O/ncu_f.log 2>&1
 python - <<'PY'
 import json,glob
-for f in sorted(glob.glob('gpurun_out/flexfinal/bench_*.json')):
+for f in sorted(glob.glob('gpurun_out/flexfinal2/bench_*.json')):
     try:
         d=json.loads(open(f).read().strip().splitlines()[-1])
         print(f.split('/')[-1], d['roofline']['kernel'], round(d['value']), 'MP/s frac', d['roofline']['frac'], d.get('full_check'), d.get('parity_spot_check'))
