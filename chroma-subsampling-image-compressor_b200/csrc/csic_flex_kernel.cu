@@ -61,7 +61,7 @@ __device__ __forceinline__ void mbar_expect_tx_only(uint32_t bar, uint32_t bytes
   asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 
-// Producer side (one thread).  global [g, g+len) -> shared, byte i at  slot + (g & 15) + i  (slot 16-byte aligned):
+// Producer side (one thread per span).  global [g, g+len) -> shared, byte i at  slot + (g & 15) + i  (slot 16-byte aligned):
 // the 16-byte hull of the span goes to the TMA engine; where the hull would leave [lo, hi) -- the byte range this
 // launch may touch -- it is clipped and the < 16 edge bytes are copied by hand (first / last span of a launch only).
 __device__ __forceinline__ void span_fetch(uint32_t slot, const uint8_t* __restrict__ g, uint32_t len, uint32_t bar, uint64_t pol,
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(kFlexMaxThreads, 4) csic_flex_kernel(const __g
 
   // ============================== producer warp ==============================================================
   // Walks this CTA's tiles up to S stages ahead of the consumers.  All lanes track the geometry; lane 0 describes the
-  // tile and hands its row spans to the TMA engine, lanes 0..nrows-1 fetch the pixel a held row replays.
+  // tile, lanes 0..nrows-1 hand one row span each to the TMA engine and fetch the pixel a held row replays.
   if (tid >= NC) {
     const uint32_t lane = tid - NC;
     const uint64_t pol = policy_evict_first();
@@ -273,12 +273,11 @@ __global__ void __launch_bounds__(kFlexMaxThreads, 4) csic_flex_kernel(const __g
       if (lane == 0) {
         d->k = pk; d->ro0 = ro0; d->nrows = nrows; d->col0 = col0; d->ncols = ncols; d->npx = npx;
         d->a0 = (uint32_t)reinterpret_cast<uintptr_t>(src0) & 15u;
-        if (P.in_dense) {          // consecutive rows are contiguous in memory: one span
-          span_fetch(in_s, src0, (nrows - 1u) * P.in_row_bytes + len_in, bar, pol, lim_lo, lim_hi);
-        } else {
-          for (uint32_t r = 0; r < nrows; ++r)
-            span_fetch(in_s + r * rs_mul, src0 + (uint64_t)r * rstep, len_in, bar, pol, lim_lo, lim_hi);
-        }
+      }
+      if (P.in_dense) {            // consecutive rows are contiguous in memory: one span
+        if (lane == 0) span_fetch(in_s, src0, (nrows - 1u) * P.in_row_bytes + len_in, bar, pol, lim_lo, lim_hi);
+      } else if (lane < nrows) {   // one lane per row span: 16 short rows do not queue up behind one thread
+        span_fetch(in_s + lane * rs_mul, src0 + (uint64_t)lane * rstep, len_in, bar, pol, lim_lo, lim_hi);
       }
       if (vhold && lane < (uint32_t)kMaxTileRows)
         sts32(held_base + (s * (uint32_t)kMaxTileRows + lane) * 4u, hvalid ? (hvalid | h0 | (h1 << 8) | (h2 << 16)) : 0u);
