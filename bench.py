@@ -56,6 +56,10 @@ WORKLOADS = {
                  "AVERAGE-pooling extension, pooling BEFORE chroma on the cfg5 geometry: 4x4 mean + Q_16BIT + RGB888"),
     "cfg5avg": (7680, 4320, 64, 2, 0, (6, 5, 5), 4, "CSQ", 1,
                 "AVERAGE-pooling extension on the cfg5 geometry: 4:2:0 + 4x4 mean + Q_16BIT + RGB888"),
+    "thumb128": (128, 128, 32768, 2, 0, (8, 8, 8), 1, "CSQ", 0,
+                 "small frames: 128x128 x32768, 4:2:0, f=1, YCC888 (many short rows per tile)"),
+    "thumb256": (256, 256, 16384, 2, 0, (8, 8, 8), 2, "CSQ", 3,
+                 "small frames: 256x256 x16384, 4:2:0 + f=2 + BUNDLE128"),
     "cfg3odd": (1918, 1078, 256, 2, 0, (4, 4, 4), 1, "CSQ", 0,
                 "cfg3 with a width no 16-byte rule fits (1918x1078, dense): the any-alignment flex kernel"),
     "cfg4odd": (3838, 2158, 256, 2, 0, (8, 8, 8), 2, "CSQ", 3,

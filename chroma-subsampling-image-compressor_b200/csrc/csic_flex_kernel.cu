@@ -57,9 +57,6 @@ __device__ __forceinline__ uint32_t ldg8_now(const uint8_t* p) {
   asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
-__device__ __forceinline__ void mbar_expect_tx_only(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
 
 // Producer side (one thread per span).  global [g, g+len) -> shared, byte i at  slot + (g & 15) + i  (slot 16-byte aligned):
 // the 16-byte hull of the span goes to the TMA engine; where the hull would leave [lo, hi) -- the byte range this
@@ -279,8 +276,8 @@ __global__ void __launch_bounds__(kFlexMaxThreads, 4) csic_flex_kernel(const __g
       } else if (lane < nrows) {   // one lane per row span: 16 short rows do not queue up behind one thread
         span_fetch(in_s + lane * rs_mul, src0 + (uint64_t)lane * rstep, len_in, bar, pol, lim_lo, lim_hi);
       }
-      if (vhold && lane < (uint32_t)kMaxTileRows)
-        sts32(held_base + (s * (uint32_t)kMaxTileRows + lane) * 4u, hvalid ? (hvalid | h0 | (h1 << 8) | (h2 << 16)) : 0u);
+      if (vhold && lane < (uint32_t)kFlexMaxRows)
+        sts32(held_base + (s * (uint32_t)kFlexMaxRows + lane) * 4u, hvalid ? (hvalid | h0 | (h1 << 8) | (h2 << 16)) : 0u);
       __syncwarp();
       // releases the descriptor, the held words and the hand-copied edge bytes; the phase completes with the last TMA byte
       if (lane == 0) mbar_arrive(bar);
@@ -304,7 +301,7 @@ __global__ void __launch_bounds__(kFlexMaxThreads, 4) csic_flex_kernel(const __g
     consumer_barrier(NC);          // the previous tile has left the staging area
 
     // ---- compute -------------------------------------------------------------------------------------------
-    const uint32_t in_s = sbase + s * in_stage, held_s = held_base + s * (uint32_t)kMaxTileRows * 4u;
+    const uint32_t in_s = sbase + s * in_stage, held_s = held_base + s * (uint32_t)kFlexMaxRows * 4u;
     const uint32_t gpr = (D.ncols + 3u) >> 2;                  // granules per row
     const uint32_t n_gran = D.nrows * gpr, srow = gpr * kUnit;
     const uint32_t row_out = D.ncols * kOpx;
@@ -504,7 +501,7 @@ bool plan_flex_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
   int rows = 1;
   if (k.nsplit == 1) {
     const uint32_t per_row = contiguous ? k.in_row_bytes : len_in_max;
-    rows = (int)std::min<uint32_t>((uint32_t)kMaxTileRows, std::max<uint32_t>(1u, tile_bytes / std::max(1u, per_row)));
+    rows = (int)std::min<uint32_t>((uint32_t)kFlexMaxRows, std::max<uint32_t>(1u, tile_bytes / std::max(1u, per_row)));
     rows = std::min(rows, k.band_rows);
     auto tiles_for = [&](int r) { return (uint64_t)k.n_frames * (uint64_t)((k.band_rows + r - 1) / r); };
     while (rows > 1 && tiles_for(rows) < (uint64_t)sm_count * 8u) rows = (rows + 1) / 2;
@@ -528,7 +525,7 @@ bool plan_flex_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
   k.out_buf_off = up128(in_bytes);
   k.out_buf_stride = up16(stage_bytes + 32u);                               // + slack: span_store reads one word ahead
   k.meta_off = k.out_buf_off + k.out_buf_stride;                            // held words of every stage
-  k.bar_off = up128(k.meta_off + stages * (uint32_t)kMaxTileRows * 4u);     // full[S], empty[S] mbarriers, then S descriptors
+  k.bar_off = up128(k.meta_off + stages * (uint32_t)kFlexMaxRows * 4u);     // full[S], empty[S] mbarriers, then S descriptors
   k.smem_bytes = k.bar_off + stages * (16u + kDescBytes);
   if (k.smem_bytes > max_smem_optin) return false;
   if (k.block_threads <= 0) k.block_threads = kFlexConsumers;

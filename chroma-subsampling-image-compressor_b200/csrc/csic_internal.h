@@ -92,8 +92,11 @@ int flex_set_attributes(size_t max_smem_optin);
 // Implemented once per spatial factor in csic_rows_kernel.cu (explicit specialisations for F = 1, 2, 4, 8).
 template <int F> int launch_rows_factor(const KPlan& k, unsigned grid, void* stream);
 template <int F> int rows_set_attributes_factor(size_t max_smem_optin);
-constexpr int kMaxTileRows = 16;        // rows per tile of the row kernel
+constexpr int kMaxTileRows = 64;        // rows per tile of the row kernel (small frames: 64 rows x 384 B still make a 24 KB tile)
 constexpr uint32_t kTileMetaBytes = 32 + 4 * kMaxTileRows;   // sizeof(TileMeta) in csic_rows_kernel.cu
+constexpr int kPoolMaxRows = 16;        // output rows per tile of the pooling kernel (each carries f input rows)
+constexpr uint32_t kPoolMetaBytes = 32 + 4 * kPoolMaxRows;   // sizeof(PoolMeta) in csic_pool_kernel.cu
+constexpr int kFlexMaxRows = 32;        // rows per tile of the flex kernel: one producer lane per row
 
 }  // namespace csic
 

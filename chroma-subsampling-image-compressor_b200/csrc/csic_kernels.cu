@@ -435,7 +435,7 @@ bool plan_pool_kernel(KPlan& k, int sm_count, size_t max_smem_optin) {
   int rows = 1;
   if (nsplit == 1) {
     rows = (int)std::max<uint32_t>(1u, budget / k.tile_in_bytes);
-    rows = std::min(rows, (int)(2u * (uint32_t)kMaxTileRows / f));      // held_addr[] holds rows * f/2 entries
+    rows = std::min(rows, (int)(2u * (uint32_t)kPoolMaxRows / f));      // held_addr[] holds rows * f/2 entries
     rows = std::min(rows, k.band_rows);
     auto tiles_for = [&](int r) { return (uint64_t)k.n_frames * (uint64_t)((k.band_rows + r - 1) / r); };
     while (rows > 1 && tiles_for(rows) < (uint64_t)sm_count * 4u) rows = (rows + 1) / 2;
@@ -446,17 +446,17 @@ bool plan_pool_kernel(KPlan& k, int sm_count, size_t max_smem_optin) {
   if (n_tiles >= (1ull << 31)) return false;
   k.n_tiles = (uint32_t)n_tiles;
   auto up128 = [](uint32_t v) { return (v + 127u) & ~127u; };
-  k.stage_stride = up128((uint32_t)rows * k.tile_in_bytes + (uint32_t)kMaxTileRows * 32u);
+  k.stage_stride = up128((uint32_t)rows * k.tile_in_bytes + (uint32_t)kPoolMaxRows * 32u);
   k.out_buf_stride = staged ? up128((uint32_t)rows * k.tile_out_bytes) : 0u;
   k.stages = 2;
-  const uint32_t need = 2u * k.stage_stride + 2u * k.out_buf_stride + 2u * kTileMetaBytes + 32u + 384u;
+  const uint32_t need = 2u * k.stage_stride + 2u * k.out_buf_stride + 2u * kPoolMetaBytes + 32u + 384u;
   if (need > max_smem_optin) return false;
   // pooling converts every input pixel: the kernel is issue-bound, so take all the warps that fit (measured:
   // 4 CTAs 0.79 of the copy peak on the 4K 2x2 case vs 0.73 with 2)
   k.ctas_per_sm = (int32_t)std::max<uint32_t>(1u, std::min<uint32_t>(4u, 227u * 1024u / (need + 1024u)));
   k.out_buf_off = 2u * k.stage_stride;
   k.meta_off = up128(k.out_buf_off + 2u * k.out_buf_stride);
-  k.bar_off = up128(k.meta_off + 2u * kTileMetaBytes);
+  k.bar_off = up128(k.meta_off + 2u * kPoolMetaBytes);
   k.smem_bytes = k.bar_off + 2u * 16u;
   return true;
 }

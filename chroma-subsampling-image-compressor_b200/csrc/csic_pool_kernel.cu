@@ -35,9 +35,9 @@ struct PoolMeta {
   uint64_t out_base;
   uint32_t n_granules;
   uint32_t pad[5];
-  uint32_t held_addr[kMaxTileRows];   // index j * (F/2) + dr/2: shared address of the pixel an odd line replays
+  uint32_t held_addr[kPoolMaxRows];   // index j * (F/2) + dr/2: shared address of the pixel an odd line replays
 };
-static_assert(sizeof(PoolMeta) == kTileMetaBytes, "kTileMetaBytes out of sync");
+static_assert(sizeof(PoolMeta) == kPoolMetaBytes, "kPoolMetaBytes out of sync");
 
 struct PoolConst {
   uint32_t coef_y, coef_ncb, coef_ncr;
@@ -282,11 +282,11 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_pool_kernel(con
       const uint8_t* frame = P.in + (uint64_t)k * P.in_frame_bytes;
       const uint32_t bar = full_bar + s * 8u;
       const uint32_t dst = sbase + s * P.stage_stride;
-      const uint32_t aux = dst + (uint32_t)P.tile_rows * P.tile_in_bytes;    // kMaxTileRows windows of 32 bytes
+      const uint32_t aux = dst + (uint32_t)P.tile_rows * P.tile_in_bytes;    // kPoolMaxRows windows of 32 bytes
       PoolMeta* m = reinterpret_cast<PoolMeta*>(smem + P.meta_off) + s;
 
       uint32_t n_aux = 0;
-      const uint8_t* aux_src[kMaxTileRows];
+      const uint8_t* aux_src[kPoolMaxRows];
       if (pool_first) {
         // Rows of an odd counter line (a line = F output rows, W == F * Wo) replay the pooled chroma of the block at
         // stream element (line-1) * W + lastSampleCol of the pooled stream.  The warp reduces that block itself:

@@ -231,10 +231,14 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(con
   __syncthreads();
 
   // ============================== producer warp ==============================================
-  // One lane walks this CTA's tiles, S deep ahead of the consumers: describe the tile in the stage's
-  // TileMeta, arm the stage's mbarrier with the byte count, and hand the copies to the TMA engine.
+  // Walks this CTA's tiles S deep ahead of the consumers.  All lanes track the geometry; the per-row work of a tile
+  // (where a held row finds its chroma, the row's own bulk copy when rows are not contiguous) is spread over the
+  // lanes -- a tile of small frames has up to 64 rows -- and every lane announces its copies on the stage's mbarrier
+  // (expect_tx); lane 0 describes the tile in TileMeta and arrives once for the warp.
   if (tid >= NC) {
-    if (tid != NC) return;
+    const uint32_t lane = tid - NC;
+    const uint32_t ipb = (uint32_t)P.in_px_bytes;
+    const bool one_copy = P.row_step == 1 && P.nsplit == 1 && P.in_dense;   // consecutive rows are contiguous in memory
     for (uint32_t i = 0; i < n_my; ++i) {
       const uint32_t s = i % S;
       if (i >= S) mbar_wait(empty_bar + s * 8u, ((i / S) - 1u) & 1u);   // consumers drained the previous use
@@ -250,13 +254,12 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(con
       const uint32_t dst = sbase + s * P.stage_stride;
       const uint32_t aux = dst + (uint32_t)P.tile_rows * P.tile_in_bytes;    // 32-byte window per row
       TileMeta* m = reinterpret_cast<TileMeta*>(smem + P.meta_off) + s;
+      const uint8_t* src = frame + (uint64_t)(ro0 * (uint32_t)P.row_step) * P.in_row_bytes + (uint64_t)seg * P.tile_in_bytes;
 
       // Which rows replay a held chroma pair, and from where?  (KPlan::hfe covers the in-row hold.)
-      const uint32_t ipb = (uint32_t)P.in_px_bytes;
-      uint32_t n_aux = 0, any = 0;
-      const uint8_t* aux_src[kMaxTileRows];
-      if (P.vf == 2) {
-        for (uint32_t j = 0; j < nrows; ++j) {
+      uint32_t any = 0;
+      for (uint32_t j = lane; j < nrows; j += 32u) {
+        if (P.vf == 2) {
           const uint32_t ro = ro0 + j;
           uint32_t h = 0;
           const uint8_t* hp = nullptr;
@@ -272,45 +275,45 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(con
               hp = frame + (uint64_t)(srow * (uint32_t)P.row_step) * P.in_row_bytes + P.caseb_col_bytes;
             }
           }
-          if (hp) {
+          if (hp) {                            // a 32-byte TMA-fetched window around the pixel
             const uint64_t a = reinterpret_cast<uint64_t>(hp);
             h = aux + j * 32u + (uint32_t)(a & 15u);
-            aux_src[j] = reinterpret_cast<const uint8_t*>(a & ~(uint64_t)15);
-            ++n_aux;
-          } else {
-            aux_src[j] = nullptr;
+            mbar_expect_tx_only(bar, 32u);
+            tma_load_1d(aux + j * 32u, reinterpret_cast<const uint8_t*>(a & ~(uint64_t)15), 32u, bar, pol);
           }
           m->held_addr[j] = h;
           any |= h;
         }
-      }
-      m->any_held_col0 = (any ? 0x80000000u : 0u) | (seg * (uint32_t)P.tile_px);
-      m->n_granules = nrows * ((uint32_t)P.tile_px >> 2);
-      m->out_base = reinterpret_cast<uint64_t>(P.out) + (uint64_t)k * P.out_frame_bytes + (uint64_t)ro0 * P.out_row_bytes +
-                    (uint64_t)seg * P.tile_out_bytes;
-      if (FMT == KF_PLANAR) {
-        // chroma rows of this tile: output rows with (ro % vs == 0); tiles of more than one row start on one
-        const uint32_t vs = (uint32_t)P.planar_vs, hs = (uint32_t)P.planar_hs;
-        const uint32_t nrc = (ro0 % vs == 0) ? (nrows + vs - 1) / vs : 0u;
-        const uint64_t coff = (uint64_t)(ro0 / vs) * (uint32_t)P.planar_cw + (uint64_t)seg * ((uint32_t)P.tile_px / hs);
-        const uint64_t fbase = reinterpret_cast<uint64_t>(P.out) + (uint64_t)k * P.out_frame_bytes;
-        m->cb_base = fbase + P.planar_cb_off + coff;
-        m->cr_base = fbase + P.planar_cr_off + coff;
-        m->n_granules |= nrc << 24;
-      }
-      // meta is published by the release of this arrive and observed after the consumers' acquire-wait
-      mbar_expect_tx(bar, nrows * P.tile_in_bytes + n_aux * 32u);
-      const uint8_t* src = frame + (uint64_t)(ro0 * (uint32_t)P.row_step) * P.in_row_bytes + (uint64_t)seg * P.tile_in_bytes;
-      if (P.row_step == 1 && P.nsplit == 1 && P.in_dense) {  // consecutive rows are contiguous in memory: one bulk copy
-        tma_load_1d(dst, src, nrows * P.tile_in_bytes, bar, pol);
-      } else {
-        for (uint32_t j = 0; j < nrows; ++j)
+        if (!one_copy) {
+          mbar_expect_tx_only(bar, P.tile_in_bytes);
           tma_load_1d(dst + j * P.tile_in_bytes, src + (uint64_t)j * (uint32_t)P.row_step * P.in_row_bytes, P.tile_in_bytes, bar, pol);
+        }
       }
-      if (n_aux) {
-        for (uint32_t j = 0; j < nrows; ++j)
-          if (aux_src[j]) tma_load_1d(aux + j * 32u, aux_src[j], 32u, bar, pol);
+      any = __reduce_or_sync(0xFFFFFFFFu, any);
+      if (lane == 0) {
+        m->any_held_col0 = (any ? 0x80000000u : 0u) | (seg * (uint32_t)P.tile_px);
+        m->n_granules = nrows * ((uint32_t)P.tile_px >> 2);
+        m->out_base = reinterpret_cast<uint64_t>(P.out) + (uint64_t)k * P.out_frame_bytes + (uint64_t)ro0 * P.out_row_bytes +
+                      (uint64_t)seg * P.tile_out_bytes;
+        if (FMT == KF_PLANAR) {
+          // chroma rows of this tile: output rows with (ro % vs == 0); tiles of more than one row start on one
+          const uint32_t vs = (uint32_t)P.planar_vs, hs = (uint32_t)P.planar_hs;
+          const uint32_t nrc = (ro0 % vs == 0) ? (nrows + vs - 1) / vs : 0u;
+          const uint64_t coff = (uint64_t)(ro0 / vs) * (uint32_t)P.planar_cw + (uint64_t)seg * ((uint32_t)P.tile_px / hs);
+          const uint64_t fbase = reinterpret_cast<uint64_t>(P.out) + (uint64_t)k * P.out_frame_bytes;
+          m->cb_base = fbase + P.planar_cb_off + coff;
+          m->cr_base = fbase + P.planar_cr_off + coff;
+          m->n_granules |= nrc << 24;
+        }
+        if (one_copy) {                        // one bulk copy for the whole tile
+          mbar_expect_tx_only(bar, nrows * P.tile_in_bytes);
+          tma_load_1d(dst, src, nrows * P.tile_in_bytes, bar, pol);
+        }
       }
+      __syncwarp();
+      // meta is published by the release of this arrive and observed after the consumers' acquire-wait; the phase
+      // completes when the last announced byte has landed
+      if (lane == 0) mbar_arrive(bar);
     }
     return;
   }
