@@ -7,7 +7,7 @@ python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | tee $O/smoke
 python bench.py --impl reference 2>&1 | tail -1 > $O/bench_reference_cfg4.json
 python bench.py 2>&1 | tail -1 > $O/bench_cfg4.json; cat $O/bench_cfg4.json
 for w in cfg4s cfg3 cfg2 cfg5; do python bench.py --workload $w --no-cpu 2>&1 | tail -1 > $O/bench_${w}.json; done
-for w in cfg3b cfg3p cfg4avg cfg5avg cfg4savg cfg5savg cfg4odd cfg3odd; do python bench.py --workload $w --no-cpu --no-e2e 2>&1 | tail -1 > $O/bench_${w}.json; done
+for w in cfg3b cfg3p cfg4avg cfg5avg cfg4savg cfg5savg cfg4odd cfg3odd thumb128 thumb256; do python bench.py --workload $w --no-cpu --no-e2e 2>&1 | tail -1 > $O/bench_${w}.json; done
 python bench.py --workload cfg2x1 --steps 200 --no-cpu 2>&1 | tail -1 > $O/bench_cfg2x1_stream.json
 python bench.py --workload cfg2x1 --steps 200 --no-cpu --no-e2e --graph 2>&1 | tail -1 > $O/bench_cfg2x1_graph.json
 python tools/bench_expand.py > $O/expand.txt 2>&1
