@@ -331,14 +331,14 @@ __global__ void __launch_bounds__(kFlexMaxThreads, 4) csic_flex_kernel(const __g
         if (c + 3u <= last_px) {
           load_granule_any<PXB>(rs + c * pxb, pxb, p);
         } else {
-  #pragma unroll
+#pragma unroll
           for (int j = 0; j < 4; ++j) p[j] = lds_px(rs + min(c + j, last_px) * pxb);
         }
-  #pragma unroll
+#pragma unroll
         for (int j = 0; j < 4; ++j) dy[j] = fwd_y16(p[j], P.coef_y);
         if (hv) {
           const uint32_t hb = fwd_nc16<TRUNC>(hv & 0x00FFFFFFu, P.coef_ncb), hr = fwd_nc16<TRUNC>(hv & 0x00FFFFFFu, P.coef_ncr);
-  #pragma unroll
+#pragma unroll
           for (int j = 0; j < 4; ++j) { xb[j] = hb; xr[j] = hr; }
         } else {
           // sample where j % HFE == 0, hold in between (ChromaSubsampler.scala:57-65)
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(kFlexMaxThreads, 4) csic_flex_kernel(const __g
           sts32(so + 8, (__byte_perm(t, u, 0x5410) ^ 0xFFFF00FFu) & qm2);
         } else if (FMT == KF_RGB888) {
           uint32_t v[4];
-  #pragma unroll
+#pragma unroll
           for (int j = 0; j < 4; ++j)
             v[j] = inverse_rgb((int)((dy[j] >> 8) & my), (int)((255u - (xb[j] >> 8)) & mcb), (int)((255u - (xr[j] >> 8)) & mcr));
           sts32(so, v[0] | (v[1] << 24));
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(kFlexMaxThreads, 4) csic_flex_kernel(const __g
           if (!hv) {               // a sampled line: its sample points go to the chroma planes (hs == HFE here)
             const uint32_t crow = (((D.ro0 + row) >> vs_sh) - c_first) * ccols + (c >> hs_sh);
             if (HFE == 1) {
-  #pragma unroll
+#pragma unroll
               for (int j = 0; j < 4; ++j)
                 if (c + j <= last_px) { sts8(cb_s + crow + j, (~(xb[j] >> 8)) & mcb); sts8(cr_s + crow + j, (~(xr[j] >> 8)) & mcr); }
             } else if (HFE == 2) {
@@ -387,16 +387,16 @@ __global__ void __launch_bounds__(kFlexMaxThreads, 4) csic_flex_kernel(const __g
         } else {
           uint32_t v[4];
           if (q8) {
-  #pragma unroll
+#pragma unroll
             for (int j = 0; j < 4; ++j)   // (Cr, Cb, Y, 0): dy < 65536 so its byte 3 is the zero pad
               v[j] = __byte_perm(__byte_perm(xr[j], xb[j], 0x0051), dy[j], 0x7510) ^ 0x0000FFFFu;
           } else {
-  #pragma unroll
+#pragma unroll
             for (int j = 0; j < 4; ++j)
               v[j] = ((dy[j] >> shy) << ly) | (((xb[j] ^ 0xFFFFu) >> shb) << lb) | ((xr[j] ^ 0xFFFFu) >> shr);
           }
           if (c + 3u > last_px) {        // the row's zero pad slots
-  #pragma unroll
+#pragma unroll
             for (int j = 0; j < 4; ++j) if (c + j > last_px) v[j] = 0u;
           }
           if (FMT == KF_SLOT32) {
