@@ -58,6 +58,10 @@ WORKLOADS = {
                 "AVERAGE-pooling extension on the cfg5 geometry: 4:2:0 + 4x4 mean + Q_16BIT + RGB888"),
     "thumb128": (128, 128, 32768, 2, 0, (8, 8, 8), 1, "CSQ", 0,
                  "small frames: 128x128 x32768, 4:2:0, f=1, YCC888 (many short rows per tile)"),
+    "thumb64": (64, 64, 131072, 2, 0, (8, 8, 8), 1, "CSQ", 0,
+                "tiny frames: 64x64 x131072, 4:2:0, f=1, YCC888 (a tile never spans two frames)"),
+    "thumb32": (32, 32, 524288, 2, 0, (8, 8, 8), 1, "CSQ", 0,
+                "tiny frames: 32x32 x524288, 4:2:0, f=1, YCC888"),
     "thumb256": (256, 256, 16384, 2, 0, (8, 8, 8), 2, "CSQ", 3,
                  "small frames: 256x256 x16384, 4:2:0 + f=2 + BUNDLE128"),
     "cfg3odd": (1918, 1078, 256, 2, 0, (4, 4, 4), 1, "CSQ", 0,
