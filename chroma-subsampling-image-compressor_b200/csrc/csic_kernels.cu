@@ -416,7 +416,9 @@ bool plan_pool_kernel(KPlan& k, int sm_count, size_t max_smem_optin) {
   if ((k.in_frame_bytes | k.out_frame_bytes | k.out_row_bytes) & 15u) return false;
   if (k.slots_per_row != k.Wo) return false;
   if (k.band_rows <= 0 || k.n_frames == 0) return false;
-  if (k.block_threads <= 0) k.block_threads = kDefaultBlockThreads;
+  // 4x4 / 8x8 pooling keeps more live registers per thread: 6 consumer warps leave room for one more CTA per SM
+  // (B200 sweep, profiles/r1/sweep_pool_v8.txt: 8K 4x4 0.97 of the copy peak vs 0.92 with 8 warps)
+  if (k.block_threads <= 0) k.block_threads = k.f >= 4 ? 192 : kDefaultBlockThreads;
   if (k.block_threads > kMaxConsumerThreads) return false;
 
   const bool staged = k.kformat <= KF_RGB888;
