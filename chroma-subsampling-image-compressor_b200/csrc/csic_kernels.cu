@@ -290,7 +290,8 @@ int launch_generic(const KPlan& k, void* stream) {
 bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_stages, uint32_t force_tile_bytes) {
   if (k.average && k.f > 1) return false;                       // AVERAGE extension: csic_pool_kernel / generic
   if (k.band_rows <= 0 || k.n_frames == 0) return false;
-  if (k.block_threads <= 0) k.block_threads = kDefaultBlockThreads;
+  const bool auto_threads = k.block_threads <= 0;
+  if (auto_threads) k.block_threads = kDefaultBlockThreads;
   if (k.block_threads > kMaxConsumerThreads) return false;
   // The kernel processes Wp = Wo rounded up to 16 output pixels per row; columns >= Wo are read from / written to
   // the row padding, so both pitches must cover Wp (dense buffers qualify when Wo % 16 == 0).
@@ -356,6 +357,11 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
   const uint64_t n_tiles = (uint64_t)k.n_frames * (uint64_t)k.tiles_per_band * (uint64_t)nsplit;
   if (n_tiles >= (1ull << 31)) return false;
   k.n_tiles = (uint32_t)n_tiles;
+  // Tiny tiles (whole frames of a few KB: a tile never spans two frames): a granule per thread is all there is, so the
+  // per-tile costs dominate -- half-size CTAs, as many as fit (32x32 frames: 0.74 of the copy peak vs 0.51;
+  // profiles/r1/sweep_rows_v8.txt)
+  const bool tiny = (uint32_t)rows * ((uint32_t)k.tile_px >> 2) <= 512u && n_tiles > (uint64_t)sm_count * 8u;
+  if (tiny && auto_threads) k.block_threads = 128;
 
   auto up128 = [](uint32_t v) { return (v + 127u) & ~127u; };
   k.stage_stride = up128((uint32_t)rows * (k.tile_in_bytes + 32u));
@@ -379,7 +385,7 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
   if (need(stages) > max_smem_optin || ctas_for(stages) < 1) return false;
   // f == 1 converts every byte it loads (issue slots 64 % busy with 16 warps): there more resident warps win
   // (PLANAR 1080p: 0.97 of the copy peak with 3 CTAs vs 0.84 with 2; 16-bit bundles: 0.93 with 4).
-  k.ctas_per_sm = (int32_t)std::min<uint32_t>(ctas_for(stages), k.f == 1 ? 4u : 2u);
+  k.ctas_per_sm = (int32_t)std::min<uint32_t>(ctas_for(stages), tiny ? 8u : (k.f == 1 ? 4u : 2u));
   k.stages = stages;
   k.out_buf_off = (uint32_t)stages * k.stage_stride;
   k.meta_off = up128(k.out_buf_off + 2u * k.out_buf_stride);
