@@ -47,7 +47,8 @@ __device__ __forceinline__ uint32_t fwd_nc16(uint32_t p, uint32_t coef) {
   return (uint32_t)x;
 }
 
-__device__ __forceinline__ int clamp255(int v) { return min(max(v, 0), 255); }
+// max(min(v, 255), 0) in one instruction (VIMNMX with the RELU modifier)
+__device__ __forceinline__ int clamp255(int v) { return __vimin_s32_relu(v, 255); }
 
 // YCbCrUtils.ycbcr2rgb with the -128 offsets folded into the constants.  Returns R | G<<8 | B<<16.
 __device__ __forceinline__ uint32_t inverse_rgb(int y, int cb, int cr) {
@@ -55,6 +56,19 @@ __device__ __forceinline__ uint32_t inverse_rgb(int y, int cb, int cr) {
   const int r = clamp255((c + 409 * cr - 52224) >> 8);
   const int g = clamp255((c - 100 * cb - 208 * cr + 39552) >> 8);
   const int b = clamp255((c + 516 * cb - 65920) >> 8);
+  return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
+}
+
+// The same transform applied straight to the forward results: dy = fwd_y16 (byte 1 = Y), xb / xr = fwd_nc16 (byte 1 =
+// ~Cb / ~Cr); my8 / mcb8 / mcr8 are the quantiser keep-masks shifted left by 8.  The channel values stay shifted left
+// by 8 (one LOP3 each instead of shift + subtract + mask), the constants are scaled by 256 and the final shift is 16:
+// floor(256 N / 65536) == floor(N / 256), the same integers with eight instructions fewer per pixel.
+__device__ __forceinline__ uint32_t inverse_rgb_raw(uint32_t dy, uint32_t xb, uint32_t xr, uint32_t my8, uint32_t mcb8, uint32_t mcr8) {
+  const int y8 = (int)(dy & my8), cb8 = (int)((xb ^ 0xFFFFu) & mcb8), cr8 = (int)((xr ^ 0xFFFFu) & mcr8);
+  const int c = 298 * y8;
+  const int r = clamp255((c + 409 * cr8 - 52224 * 256) >> 16);
+  const int g = clamp255((c - 100 * cb8 - 208 * cr8 + 39552 * 256) >> 16);
+  const int b = clamp255((c + 516 * cb8 - 65920 * 256) >> 16);
   return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
 }
 

@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kFlexMaxThreads, 4) csic_flex_kernel(const __g
           uint32_t v[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            v[j] = inverse_rgb((int)((dy[j] >> 8) & my), (int)((255u - (xb[j] >> 8)) & mcb), (int)((255u - (xr[j] >> 8)) & mcr));
+            v[j] = inverse_rgb_raw(dy[j], xb[j], xr[j], my << 8, mcb << 8, mcr << 8);
           sts32(so, v[0] | (v[1] << 24));
           sts32(so + 4, (v[1] >> 8) | (v[2] << 16));
           sts32(so + 8, (v[2] >> 16) | (v[3] << 8));
@@ -414,12 +414,15 @@ __global__ void __launch_bounds__(kFlexMaxThreads, 4) csic_flex_kernel(const __g
       auto row_in = [&](uint32_t row) { return in_s + row * rs_mul + ((D.a0 + row * rs_add) & 15u); };
       auto row_st = [&](uint32_t row) { return out_s + row * st_mul + ((oa0 + row * st_add) & 12u); };
       const uint32_t NW = NC >> 5;
-      if (gpr >= NC && pow2_divides(D.nrows, NW)) {   // wide rows that divide the warps: NW / nrows warps per row, set up once
-        const uint32_t sh = 31u - __clz(NW) - (31u - __clz(D.nrows));      // log2(NW / nrows): both powers of two
+      // rows that divide the warps (the plan makes nrows a power of two): NW / nrows warps per row, everything
+      // row-dependent set up once per warp -- taken when at least 4/5 of the lanes of a row's warps get a granule
+      const uint32_t sh = pow2_divides(D.nrows, NW) ? 31u - __clz(NW) - (31u - __clz(D.nrows)) : 0u;   // log2(NW / nrows)
+      const uint32_t lsh = sh + 5u, iters = (gpr + (1u << lsh) - 1u) >> lsh;                             // lanes per row = 1 << lsh
+      if (pow2_divides(D.nrows, NW) && gpr * 5u >= (iters << lsh) * 4u) {
         const uint32_t parts = 1u << sh, row = (tid >> 5) >> sh, part = (tid >> 5) & (parts - 1u);
         const uint32_t rs = row_in(row), so_row = row_st(row), hv = vhold ? lds32(held_s + row * 4u) : 0u;
         for (uint32_t g = part * 32u + (tid & 31u); g < gpr; g += parts * 32u) granule(row, g, rs, so_row, hv);
-      } else if (gpr >= NC) {      // wide rows: row by row, nothing row-dependent inside the loop
+      } else if (gpr >= 4u * NC) {   // very wide rows: row by row, nothing row-dependent inside the loop
         for (uint32_t row = 0; row < D.nrows; ++row) {
           const uint32_t rs = row_in(row), so_row = row_st(row), hv = vhold ? lds32(held_s + row * 4u) : 0u;
           for (uint32_t g = tid; g < gpr; g += NC) granule(row, g, rs, so_row, hv);
@@ -506,6 +509,11 @@ bool plan_flex_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
     auto tiles_for = [&](int r) { return (uint64_t)k.n_frames * (uint64_t)((k.band_rows + r - 1) / r); };
     while (rows > 1 && tiles_for(rows) < (uint64_t)sm_count * 8u) rows = (rows + 1) / 2;
   }
+  // a power of two lets the consumer warps split evenly over the rows -- unless rounding down would cost more than a
+  // quarter of the tile (then the flat granule loop takes it; B200 map: profiles/r1/perf_map.txt)
+  int p2 = rows;
+  while (p2 & (p2 - 1)) p2 &= p2 - 1;
+  if (p2 * 4 >= rows * 3) rows = p2;
   k.tile_rows = rows;
   k.in_dense = (contiguous && rows > 1) ? 1 : 0;
   k.tiles_per_band = (uint32_t)((k.band_rows + rows - 1) / rows);

@@ -158,12 +158,7 @@ __device__ __forceinline__ void tile_loop(uint32_t in_s, uint32_t out_s, uint8_t
     } else if (FMT == KF_RGB888) {
       uint32_t v[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int y = (int)((dy[j] >> 8) & C.my);
-        const int cb = (int)((255u - (xb[j] >> 8)) & C.mcb);
-        const int cr = (int)((255u - (xr[j] >> 8)) & C.mcr);
-        v[j] = inverse_rgb(y, cb, cr);
-      }
+      for (int j = 0; j < 4; ++j) v[j] = inverse_rgb_raw(dy[j], xb[j], xr[j], C.my << 8, C.mcb << 8, C.mcr << 8);
       const uint32_t a = out_s + q * 12u;
       sts32(a, v[0] | (v[1] << 24));
       sts32(a + 4, (v[1] >> 8) | (v[2] << 16));
