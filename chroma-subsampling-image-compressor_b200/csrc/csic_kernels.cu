@@ -455,7 +455,7 @@ bool plan_pool_kernel(KPlan& k, int sm_count, size_t max_smem_optin) {
   k.n_tiles = (uint32_t)n_tiles;
   auto up128 = [](uint32_t v) { return (v + 127u) & ~127u; };
   k.stage_stride = up128((uint32_t)rows * k.tile_in_bytes + (uint32_t)kPoolMaxRows * 32u);
-  k.out_buf_stride = staged ? up128((uint32_t)rows * k.tile_out_bytes) : 0u;
+  k.out_buf_stride = staged ? (uint32_t)(kMaxConsumerThreads / 32) * 384u / 2u : 0u;   // 2 x stride = one 384-byte slot per warp
   k.stages = 2;
   const uint32_t need = 2u * k.stage_stride + 2u * k.out_buf_stride + 2u * kPoolMetaBytes + 32u + 384u;
   if (need > max_smem_optin) return false;

@@ -90,7 +90,14 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
   constexpr int kHalf = (F * F) / 2;
   const uint32_t n = meta->n_granules;
   uint32_t row = C.row0_of_thread, rem = C.rem0_of_thread;
-  for (uint32_t q = threadIdx.x; q < n; q += C.nthreads) {
+  constexpr bool kStagedFmt = (FMT == KF_YCC888 || FMT == KF_RGB888);
+  // 12-byte formats: whole warps iterate together (lanes past the tile's last granule idle through the body), because
+  // a warp's 32 granules are 384 consecutive output bytes which leave through the warp's own staging slot as 16-byte
+  // stores -- no CTA-wide barrier, no TMA store: the kernel is bound by the integer pipes, a barrier per tile cost 10 %
+  const uint32_t n_loop = kStagedFmt ? (n + 31u) & ~31u : n;
+  for (uint32_t q = threadIdx.x; q < n_loop; q += C.nthreads) {
+    uint32_t w0 = 0, w1 = 0, w2 = 0;
+    if (q < n) {
     int ay[4] = {0, 0, 0, 0}, ab[4] = {0, 0, 0, 0}, ar[4] = {0, 0, 0, 0};
     const uint32_t base = in_s + row * (F * C.seg_row_bytes) + rem * kGranBytes;
     const uint32_t held_pair = C.pool_first ? meta->held_addr[row] : 0u;   // bit 31 | pooled Cb << 8 | pooled Cr
@@ -211,21 +218,19 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
       }
     }
     if (FMT == KF_YCC888 || FMT == KF_RGB888) {
-      uint32_t w0, w1, w2;
       if (FMT == KF_YCC888) {
-        w0 = y[0] | (cb[0] << 8) | (cr[0] << 16) | (y[1] << 24);
-        w1 = cb[1] | (cr[1] << 8) | (y[2] << 16) | (cb[2] << 24);
-        w2 = cr[2] | (y[3] << 8) | (cb[3] << 16) | (cr[3] << 24);
+        // bytes packed with multiply-adds (one IMAD per byte on the FMA pipe) rather than shift + OR on the ALU pipe
+        w0 = ((y[1] * 256u + cr[0]) * 256u + cb[0]) * 256u + y[0];
+        w1 = ((cb[2] * 256u + y[2]) * 256u + cr[1]) * 256u + cb[1];
+        w2 = ((cr[3] * 256u + cb[3]) * 256u + y[3]) * 256u + cr[2];
       } else {
         uint32_t v[4];
 #pragma unroll
         for (int o = 0; o < 4; ++o) v[o] = inverse_rgb((int)y[o], (int)cb[o], (int)cr[o]);
-        w0 = v[0] | (v[1] << 24);
-        w1 = (v[1] >> 8) | (v[2] << 16);
-        w2 = (v[2] >> 16) | (v[3] << 8);
+        w0 = v[1] * 0x1000000u + v[0];
+        w1 = v[2] * 0x10000u + (v[1] >> 8);
+        w2 = v[3] * 0x100u + (v[2] >> 16);
       }
-      const uint32_t a = out_s + q * 12u;
-      sts32(a, w0); sts32(a + 4, w1); sts32(a + 8, w2);
     } else {
       uint32_t v[4];
 #pragma unroll
@@ -233,6 +238,24 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
       if (FMT == KF_SLOT32) __stcs(reinterpret_cast<uint4*>(out_g) + q, make_uint4(v[0], v[1], v[2], v[3]));
       else if (FMT == KF_SLOT16) __stcs(reinterpret_cast<uint2*>(out_g) + q, make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16)));
       else __stcs(reinterpret_cast<uint32_t*>(out_g) + q, v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
+    }
+    }   // q < n
+    if (kStagedFmt) {
+      const uint32_t lane = threadIdx.x & 31u, slot = out_s + (threadIdx.x >> 5) * 384u;
+      sts32(slot + lane * 12u, w0); sts32(slot + lane * 12u + 4u, w1); sts32(slot + lane * 12u + 8u, w2);
+      __syncwarp();
+      const uint32_t q0 = q - lane;                                   // the warp's first granule: 384-byte aligned output
+      const uint32_t valid = min(32u, n - q0) * 12u;                  // bytes of this group that exist
+      uint8_t* o = out_g + (size_t)q0 * 12u;
+      if (lane < 24u) {
+        if ((lane + 1u) * 16u <= valid) {
+          __stcs(reinterpret_cast<uint4*>(o) + lane, lds128(slot + lane * 16u));
+        } else {
+          for (uint32_t wd = lane * 4u; wd < lane * 4u + 4u; ++wd)
+            if ((wd + 1u) * 4u <= valid) __stcs(reinterpret_cast<uint32_t*>(o) + wd, lds32(slot + wd * 4u));
+        }
+      }
+      __syncwarp();
     }
     row += C.drow;
     rem += C.drem;
@@ -243,7 +266,6 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
 template <int F, int FMT, bool IN4>
 __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_pool_kernel(const __grid_constant__ KPlan P) {
   extern __shared__ __align__(128) uint8_t smem[];
-  constexpr bool kStaged = (FMT == KF_YCC888 || FMT == KF_RGB888);
   const uint32_t tid = threadIdx.x;
   const uint32_t NC = blockDim.x - 32u;
   const uint32_t sbase = smem_u32(smem);
@@ -383,10 +405,9 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_pool_kernel(con
     const uint32_t s = i % S;
     mbar_wait(full_bar + s * 8u, (i / S) & 1u);
     const uint32_t in_s = sbase + s * P.stage_stride;
-    const uint32_t out_s = sbase + P.out_buf_off + (i & 1u) * P.out_buf_stride;
+    const uint32_t out_s = sbase + P.out_buf_off;     // 12-byte formats: one 384-byte staging slot per consumer warp
     const PoolMeta* m = reinterpret_cast<const PoolMeta*>(smem + P.meta_off) + s;
     uint8_t* out_g = reinterpret_cast<uint8_t*>(m->out_base);
-    const uint32_t out_bytes = m->n_granules * 12u;
     if (C.trunc) {
       if (hf == 1) pool_tile<F, FMT, IN4, 1, true>(in_s, out_s, out_g, m, C);
       else if (hf == 2) pool_tile<F, FMT, IN4, 2, true>(in_s, out_s, out_g, m, C);
@@ -397,19 +418,9 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_pool_kernel(con
       else pool_tile<F, FMT, IN4, 4, false>(in_s, out_s, out_g, m, C);
     }
 
-    if (kStaged) {
-      fence_proxy_async_smem();
-      if (tid == 0) tma_store_wait_read0();
-      consumer_barrier(NC);
-      if (tid == 0) {
-        tma_store_1d(out_g, out_s, out_bytes, pol);
-        tma_store_commit();
-      }
-    }
     __syncwarp();
     if ((tid & 31u) == 0) mbar_arrive(empty_bar + s * 8u);
   }
-  if (kStaged && tid == 0) tma_store_wait_all();
 }
 
 namespace {
