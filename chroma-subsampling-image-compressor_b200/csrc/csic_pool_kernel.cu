@@ -94,15 +94,22 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
   // 12-byte formats: whole warps iterate together (lanes past the tile's last granule idle through the body), because
   // a warp's 32 granules are 384 consecutive output bytes which leave through the warp's own staging slot as 16-byte
   // stores -- no CTA-wide barrier, no TMA store: the kernel is bound by the integer pipes, a barrier per tile cost 10 %
-  const uint32_t n_loop = kStagedFmt ? (n + 31u) & ~31u : n;
-  for (uint32_t q = threadIdx.x; q < n_loop; q += C.nthreads) {
+  // 8x8 pooling: a granule is 256 input pixels, so a 24 KB tile has only ~32 of them -- four threads share one, two
+  // row parts each, and add their partial sums up with two shfl.xor steps (1080p 0.27 -> 0.49, 4K 0.36 -> 0.63 of the
+  // copy peak; eight threads per granule measured worse).
+  constexpr uint32_t kSplit = (F == 8) ? 4u : 1u;      // threads per granule
+  constexpr uint32_t kGpw = 32u / kSplit;              // granules per warp and iteration
+  const uint32_t sub = threadIdx.x % kSplit;
+  const uint32_t n_loop = (kStagedFmt || kSplit > 1u) ? (n + kGpw - 1u) / kGpw * kGpw : n;
+  for (uint32_t q = threadIdx.x / kSplit; q < n_loop; q += C.nthreads / kSplit) {
     uint32_t w0 = 0, w1 = 0, w2 = 0;
-    if (q < n) {
     int ay[4] = {0, 0, 0, 0}, ab[4] = {0, 0, 0, 0}, ar[4] = {0, 0, 0, 0};
+    uint32_t held_pair = 0;
+    if (q < n) {
     const uint32_t base = in_s + row * (F * C.seg_row_bytes) + rem * kGranBytes;
-    const uint32_t held_pair = C.pool_first ? meta->held_addr[row] : 0u;   // bit 31 | pooled Cb << 8 | pooled Cr
+    held_pair = C.pool_first ? meta->held_addr[row] : 0u;   // bit 31 | pooled Cb << 8 | pooled Cr
 #pragma unroll 1
-    for (int dr = 0; dr < F; ++dr) {
+    for (int dr = (int)(sub * (F / kSplit)); dr < (int)((sub + 1u) * (F / kSplit)); ++dr) {
       uint32_t p[4 * F];
       load_row_part<F, IN4>(base + (uint32_t)dr * C.seg_row_bytes, p);
       // Y: byte 1 of each dp4a result is the pixel's Y.  Gather the F bytes of an output pixel's row part into
@@ -199,6 +206,19 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
         }
       }
     }
+    }   // q < n: accumulation
+    if (kSplit > 1u) {                 // partial sums of the threads that share the granule (adjacent lanes)
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+#pragma unroll
+        for (uint32_t d = 1; d < kSplit; d <<= 1) {
+          ay[o] += __shfl_xor_sync(0xFFFFFFFFu, ay[o], d);
+          ab[o] += __shfl_xor_sync(0xFFFFFFFFu, ab[o], d);
+          ar[o] += __shfl_xor_sync(0xFFFFFFFFu, ar[o], d);
+        }
+      }
+    }
+    if (q < n && sub == 0u) {
     if (C.linear) {                    // back from the complement domain: F*F samples of weight 1 each
 #pragma unroll
       for (int o = 0; o < 4; ++o) { ab[o] = 255 * F * F - ab[o]; ar[o] = 255 * F * F - ar[o]; }
@@ -239,15 +259,15 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
       else if (FMT == KF_SLOT16) __stcs(reinterpret_cast<uint2*>(out_g) + q, make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16)));
       else __stcs(reinterpret_cast<uint32_t*>(out_g) + q, v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
     }
-    }   // q < n
+    }   // q < n && sub == 0: finalise
     if (kStagedFmt) {
-      const uint32_t lane = threadIdx.x & 31u, slot = out_s + (threadIdx.x >> 5) * 384u;
-      sts32(slot + lane * 12u, w0); sts32(slot + lane * 12u + 4u, w1); sts32(slot + lane * 12u + 8u, w2);
+      const uint32_t lane = threadIdx.x & 31u, g = lane / kSplit, slot = out_s + (threadIdx.x >> 5) * 384u;
+      if (sub == 0u) { sts32(slot + g * 12u, w0); sts32(slot + g * 12u + 4u, w1); sts32(slot + g * 12u + 8u, w2); }
       __syncwarp();
-      const uint32_t q0 = q - lane;                                   // the warp's first granule: 384-byte aligned output
-      const uint32_t valid = min(32u, n - q0) * 12u;                  // bytes of this group that exist
+      const uint32_t q0 = q - g;                                      // the warp's first granule: 96 / 384-byte aligned output
+      const uint32_t valid = min(kGpw, n - q0) * 12u;                 // bytes of this group that exist
       uint8_t* o = out_g + (size_t)q0 * 12u;
-      if (lane < 24u) {
+      if (lane < kGpw * 12u / 16u) {
         if ((lane + 1u) * 16u <= valid) {
           __stcs(reinterpret_cast<uint4*>(o) + lane, lds128(slot + lane * 16u));
         } else {
@@ -388,10 +408,11 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_pool_kernel(con
     C.ly = P.cb_bits + P.cr_bits; C.lb = P.cr_bits;
     C.gran_per_row = (uint32_t)P.tile_px >> 2;
     C.nthreads = NC;
-    C.row0_of_thread = tid / C.gran_per_row;
-    C.rem0_of_thread = tid % C.gran_per_row;
-    C.drow = NC / C.gran_per_row;
-    C.drem = NC % C.gran_per_row;
+    constexpr uint32_t kSplit = (F == 8) ? 4u : 1u;      // threads per granule (see pool_tile)
+    C.row0_of_thread = (tid / kSplit) / C.gran_per_row;
+    C.rem0_of_thread = (tid / kSplit) % C.gran_per_row;
+    C.drow = (NC / kSplit) / C.gran_per_row;
+    C.drem = (NC / kSplit) % C.gran_per_row;
     C.seg_row_bytes = seg_row_bytes;
     C.trunc = P.trunc != 0;
     C.vhold = P.vf == 2;
