@@ -58,6 +58,10 @@ WORKLOADS = {
                 "AVERAGE-pooling extension on the cfg5 geometry: 4:2:0 + 4x4 mean + Q_16BIT + RGB888"),
     "thumb128": (128, 128, 32768, 2, 0, (8, 8, 8), 1, "CSQ", 0,
                  "small frames: 128x128 x32768, 4:2:0, f=1, YCC888 (many short rows per tile)"),
+    "cfg4f8": (3840, 2160, 1024, 4, 4, (8, 8, 8), 8, "SQC", 0,
+               "the reference app's defaults (ImageCompressorTopApp.scala:164-173: 4:4:4, 8/8/8, sf=8, spatial -> color -> chroma) on 4K x1024"),
+    "cfg4f4": (3840, 2160, 1024, 2, 0, (8, 8, 8), 4, "CSQ", 0,
+               "4K x1024, 4:2:0 + f=4, YCC888"),
     "thumb64": (64, 64, 131072, 2, 0, (8, 8, 8), 1, "CSQ", 0,
                 "tiny frames: 64x64 x131072, 4:2:0, f=1, YCC888 (a tile never spans two frames)"),
     "thumb32": (32, 32, 524288, 2, 0, (8, 8, 8), 1, "CSQ", 0,
