@@ -196,72 +196,176 @@ __global__ void __launch_bounds__(256) csic_expand_planar_kernel(const __grid_co
   }
 }
 
-// Same decoder, four output pixels per thread (needs Wo % 4 == 0 and a 16-byte-aligned output).  The Y bytes arrive
-// as one word when aligned and the chroma samples of the granule are fetched once.  The output is one contiguous
-// array of 12 bytes per granule, so a warp's 32 granules are 384 consecutive bytes: the lanes park their three words
-// in shared memory and lanes 0..23 write them back out as coalesced 16-byte words.
-template <typename IdxT>   // uint32_t whenever the launch has fewer than 2^32 granules: 32-bit divisions
-__global__ void __launch_bounds__(256) csic_expand_planar4_kernel(const __grid_constant__ KPlan P, const uint8_t* __restrict__ planar,
-                                                                  uint8_t* __restrict__ out, int to_rgb) {
-  __shared__ __align__(16) uint32_t stage[8][96];
+// Same decoder, one CTA per output row, four pixels per thread (needs Wo % 4 == 0).  Everything row-dependent --
+// frame / row split (the only division), held line, plane row addresses, alignment of the row's loads -- is computed once
+// per row; the Y bytes arrive as one word, the chroma samples of a granule as a word / half word / byte when aligned.
+// A16: output rows are 16-byte aligned (Wo % 16 == 0), so a warp's 32 granules = 384 consecutive bytes leave through
+// a shared-memory slot as coalesced 16-byte stores; otherwise three words per granule.
+template <bool A16>
+__global__ void __launch_bounds__(128) csic_expand_planar_rows_kernel(const __grid_constant__ KPlan P, const uint8_t* __restrict__ planar,
+                                                                      uint8_t* __restrict__ out, int to_rgb) {
+  __shared__ __align__(16) uint32_t stage[4][96];
   const uint32_t gpr = (uint32_t)P.Wo >> 2, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const IdxT total = (IdxT)((uint64_t)P.n_frames * (uint64_t)P.Ho * gpr);
+  const uint32_t n_rows = P.n_frames * (uint32_t)P.Ho;
   const int last_c = (P.last_sample_col / P.f) / P.planar_hs;       // plane column of a line's last sample point
-  const int hs_sh = P.planar_hs == 4 ? 2 : (P.planar_hs == 2 ? 1 : 0), vs_sh = P.planar_vs == 2 ? 1 : 0;   // 1, 2, 4 / 1, 2
+  const uint32_t hs_sh = P.planar_hs == 4 ? 2u : (P.planar_hs == 2 ? 1u : 0u), vs_sh = P.planar_vs == 2 ? 1u : 0u;
   const bool vhold = P.vf == 2 && P.f == 1;                         // odd lines replay the line above (f == 1 only)
-  // every warp walks whole groups of 32 granules (the loop bound is warp uniform)
-  for (IdxT base = ((IdxT)blockIdx.x * blockDim.x + threadIdx.x) & ~(IdxT)31; base < total;
-       base += (IdxT)gridDim.x * blockDim.x) {
-    const IdxT idx = base + lane;
-    uint32_t w0 = 0, w1 = 0, w2 = 0;
-    if (idx < total) {
-      const IdxT t = idx / gpr;
-      const uint32_t g = (uint32_t)(idx - t * gpr);
-      const IdxT k = t / (uint32_t)P.Ho;
-      const int ro = (int)(t - k * (uint32_t)P.Ho);
-      const uint8_t* fr = planar + (uint64_t)k * P.out_frame_bytes;
-      const uint8_t* yp = fr + (size_t)ro * P.Wo + 4u * g;
-      uint32_t yw;
-      if ((reinterpret_cast<uintptr_t>(yp) & 3u) == 0) yw = __ldg(reinterpret_cast<const uint32_t*>(yp));
-      else yw = (uint32_t)__ldg(yp) | ((uint32_t)__ldg(yp + 1) << 8) | ((uint32_t)__ldg(yp + 2) << 16) | ((uint32_t)__ldg(yp + 3) << 24);
-      const bool held = vhold && (ro & 1);
-      const size_t crow = (size_t)((held ? ro - 1 : ro) >> vs_sh) * (size_t)P.planar_cw;
-      const uint8_t* cbp = fr + P.planar_cb_off + crow;
-      const uint8_t* crp = fr + P.planar_cr_off + crow;
-      uint32_t v[4];
+  for (uint32_t R = blockIdx.x; R < n_rows; R += gridDim.x) {
+    const uint32_t k = R / (uint32_t)P.Ho, ro = R - k * (uint32_t)P.Ho;
+    const uint8_t* fr = planar + (uint64_t)k * P.out_frame_bytes;
+    const uint8_t* yrow = fr + (size_t)ro * P.Wo;
+    const bool held = vhold && (ro & 1u);
+    const size_t crow = (size_t)((held ? ro - 1u : ro) >> vs_sh) * (size_t)P.planar_cw;
+    const uint8_t* cbp = fr + P.planar_cb_off + crow;
+    const uint8_t* crp = fr + P.planar_cr_off + crow;
+    uint8_t* orow = out + (uint64_t)R * P.Wo * 3u;
+    const bool y_al = (reinterpret_cast<uintptr_t>(yrow) & 3u) == 0;
+    const uint32_t c_al = (uint32_t)((reinterpret_cast<uintptr_t>(cbp) | reinterpret_cast<uintptr_t>(crp)) & 3u);   // 0: words ok, 2: half words ok
+    uint32_t hcb = 0, hcr = 0;
+    if (held) { hcb = __ldg(cbp + last_c); hcr = __ldg(crp + last_c); }
+    for (uint32_t g0 = warp * 32u; g0 < gpr; g0 += blockDim.x) {    // warp uniform
+      const uint32_t g = g0 + lane;
+      uint32_t w0 = 0, w1 = 0, w2 = 0;
+      if (g < gpr) {
+        const uint8_t* yp = yrow + 4u * g;
+        uint32_t yw;
+        if (y_al) yw = __ldg(reinterpret_cast<const uint32_t*>(yp));
+        else yw = (uint32_t)__ldg(yp) | ((uint32_t)__ldg(yp + 1) << 8) | ((uint32_t)__ldg(yp + 2) << 16) | ((uint32_t)__ldg(yp + 3) << 24);
+        // chroma of the four pixels as bytes of cbw / crw
+        uint32_t cbw, crw;
+        if (held) {
+          cbw = hcb * 0x01010101u; crw = hcr * 0x01010101u;
+        } else if (hs_sh == 0) {
+          if (c_al == 0) { cbw = __ldg(reinterpret_cast<const uint32_t*>(cbp + 4u * g)); crw = __ldg(reinterpret_cast<const uint32_t*>(crp + 4u * g)); }
+          else {
+            cbw = (uint32_t)__ldg(cbp + 4u * g) | ((uint32_t)__ldg(cbp + 4u * g + 1) << 8) | ((uint32_t)__ldg(cbp + 4u * g + 2) << 16) | ((uint32_t)__ldg(cbp + 4u * g + 3) << 24);
+            crw = (uint32_t)__ldg(crp + 4u * g) | ((uint32_t)__ldg(crp + 4u * g + 1) << 8) | ((uint32_t)__ldg(crp + 4u * g + 2) << 16) | ((uint32_t)__ldg(crp + 4u * g + 3) << 24);
+          }
+        } else if (hs_sh == 1) {
+          uint32_t b2, r2;
+          if ((c_al & 1u) == 0) { b2 = __ldg(reinterpret_cast<const uint16_t*>(cbp + 2u * g)); r2 = __ldg(reinterpret_cast<const uint16_t*>(crp + 2u * g)); }
+          else { b2 = (uint32_t)__ldg(cbp + 2u * g) | ((uint32_t)__ldg(cbp + 2u * g + 1) << 8); r2 = (uint32_t)__ldg(crp + 2u * g) | ((uint32_t)__ldg(crp + 2u * g + 1) << 8); }
+          cbw = __byte_perm(b2, 0, 0x1100); crw = __byte_perm(r2, 0, 0x1100);      // each sample held for two pixels
+        } else {
+          cbw = (uint32_t)__ldg(cbp + g) * 0x01010101u; crw = (uint32_t)__ldg(crp + g) * 0x01010101u;
+        }
+        uint32_t v[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int sc = held ? last_c : (int)((4u * g + j) >> hs_sh);
-        // consecutive j share a sample when hs > 1: the loads hit the same byte and are served by L1
-        const int y = (int)((yw >> (8 * j)) & 0xFFu), cb = __ldg(cbp + sc), cr = __ldg(crp + sc);
-        v[j] = to_rgb ? inverse_rgb(y, cb, cr) : ((uint32_t)y | ((uint32_t)cb << 8) | ((uint32_t)cr << 16));
+        for (int j = 0; j < 4; ++j) {
+          const int y = (int)((yw >> (8 * j)) & 0xFFu), cb = (int)((cbw >> (8 * j)) & 0xFFu), cr = (int)((crw >> (8 * j)) & 0xFFu);
+          v[j] = to_rgb ? inverse_rgb(y, cb, cr) : ((uint32_t)y | ((uint32_t)cb << 8) | ((uint32_t)cr << 16));
+        }
+        w0 = v[0] | (v[1] << 24); w1 = (v[1] >> 8) | (v[2] << 16); w2 = (v[2] >> 16) | (v[3] << 8);
       }
-      w0 = v[0] | (v[1] << 24); w1 = (v[1] >> 8) | (v[2] << 16); w2 = (v[2] >> 16) | (v[3] << 8);
-    }
-    uint32_t* st = stage[warp];
-    st[3 * lane] = w0; st[3 * lane + 1] = w1; st[3 * lane + 2] = w2;
-    __syncwarp();
-    uint8_t* o = out + (uint64_t)base * 12u;             // granule `base` starts here; 384-byte aligned relative to out
-    const uint64_t valid = (uint64_t)(total - base < 32u ? total - base : 32u) * 12u;   // bytes of this group that exist
-    if (lane < 24u) {
-      if ((uint64_t)(lane + 1u) * 16u <= valid) {
-        __stcs(reinterpret_cast<uint4*>(o) + lane, reinterpret_cast<const uint4*>(st)[lane]);
-      } else {
-        for (uint32_t wd = lane * 4u; wd < lane * 4u + 4u; ++wd)
-          if ((uint64_t)(wd + 1u) * 4u <= valid) __stcs(reinterpret_cast<uint32_t*>(o) + wd, st[wd]);
+      if (A16) {
+        uint32_t* st = stage[warp];
+        st[3 * lane] = w0; st[3 * lane + 1] = w1; st[3 * lane + 2] = w2;
+        __syncwarp();
+        const uint32_t valid = min(32u, gpr - g0) * 12u;                 // bytes of this group that exist
+        uint8_t* o = orow + (size_t)g0 * 12u;
+        if (lane < 24u) {
+          if ((lane + 1u) * 16u <= valid) {
+            __stcs(reinterpret_cast<uint4*>(o) + lane, reinterpret_cast<const uint4*>(st)[lane]);
+          } else {
+            for (uint32_t wd = lane * 4u; wd < lane * 4u + 4u; ++wd)
+              if ((wd + 1u) * 4u <= valid) __stcs(reinterpret_cast<uint32_t*>(o) + wd, st[wd]);
+          }
+        }
+        __syncwarp();
+      } else if (g < gpr) {
+        uint32_t* o = reinterpret_cast<uint32_t*>(orow + (size_t)g * 12u);
+        __stcs(o, w0); __stcs(o + 1, w1); __stcs(o + 2, w2);
       }
     }
-    __syncwarp();
+  }
+}
+
+// Widest variant: sixteen pixels per thread (Wo % 16 == 0, planes and output 16-byte aligned).  What bounds the decoder is
+// bytes in flight -- a thread that waits on one Y word and two chroma half words keeps 16 KB per SM in the air -- so every
+// thread fetches 16 Y bytes and 2 x 4..16 chroma bytes at once (LDG.128 / .64 / .32) and a warp leaves 1536 consecutive
+// output bytes through its shared-memory slot as three rounds of coalesced 16-byte stores.
+__global__ void __launch_bounds__(128) csic_expand_planar16_kernel(const __grid_constant__ KPlan P, const uint8_t* __restrict__ planar,
+                                                                   uint8_t* __restrict__ out, int to_rgb) {
+  __shared__ __align__(16) uint32_t stage[4][12 * 32];
+  const uint32_t gpr = (uint32_t)P.Wo >> 4, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;   // 16-pixel groups per row
+  const uint32_t n_rows = P.n_frames * (uint32_t)P.Ho;
+  const int last_c = (P.last_sample_col / P.f) / P.planar_hs;
+  const uint32_t hs_sh = P.planar_hs == 4 ? 2u : (P.planar_hs == 2 ? 1u : 0u), vs_sh = P.planar_vs == 2 ? 1u : 0u;
+  const bool vhold = P.vf == 2 && P.f == 1;
+  for (uint32_t R = blockIdx.x; R < n_rows; R += gridDim.x) {
+    const uint32_t k = R / (uint32_t)P.Ho, ro = R - k * (uint32_t)P.Ho;
+    const uint8_t* fr = planar + (uint64_t)k * P.out_frame_bytes;
+    const uint8_t* yrow = fr + (size_t)ro * P.Wo;
+    const bool held = vhold && (ro & 1u);
+    const size_t crow = (size_t)((held ? ro - 1u : ro) >> vs_sh) * (size_t)P.planar_cw;
+    const uint8_t* cbp = fr + P.planar_cb_off + crow;
+    const uint8_t* crp = fr + P.planar_cr_off + crow;
+    uint8_t* orow = out + (uint64_t)R * P.Wo * 3u;
+    uint32_t hcb = 0, hcr = 0;
+    if (held) { hcb = (uint32_t)__ldg(cbp + last_c) * 0x01010101u; hcr = (uint32_t)__ldg(crp + last_c) * 0x01010101u; }
+    for (uint32_t g0 = warp * 32u; g0 < gpr; g0 += blockDim.x) {    // warp uniform
+      const uint32_t g = g0 + lane;
+      uint32_t* st = stage[warp];
+      if (g < gpr) {
+        const uint4 yv = __ldg(reinterpret_cast<const uint4*>(yrow) + g);
+        uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w}, cbw[4], crw[4];   // chroma of pixel 4i+j = byte j of cbw[i] / crw[i]
+        if (held) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { cbw[i] = hcb; crw[i] = hcr; }
+        } else if (hs_sh == 0) {
+          const uint4 b = __ldg(reinterpret_cast<const uint4*>(cbp) + g), r = __ldg(reinterpret_cast<const uint4*>(crp) + g);
+          cbw[0] = b.x; cbw[1] = b.y; cbw[2] = b.z; cbw[3] = b.w; crw[0] = r.x; crw[1] = r.y; crw[2] = r.z; crw[3] = r.w;
+        } else if (hs_sh == 1) {       // 8 samples, each held for two pixels
+          const uint2 b = __ldg(reinterpret_cast<const uint2*>(cbp) + g), r = __ldg(reinterpret_cast<const uint2*>(crp) + g);
+          cbw[0] = __byte_perm(b.x, 0, 0x1100); cbw[1] = __byte_perm(b.x, 0, 0x3322); cbw[2] = __byte_perm(b.y, 0, 0x1100); cbw[3] = __byte_perm(b.y, 0, 0x3322);
+          crw[0] = __byte_perm(r.x, 0, 0x1100); crw[1] = __byte_perm(r.x, 0, 0x3322); crw[2] = __byte_perm(r.y, 0, 0x1100); crw[3] = __byte_perm(r.y, 0, 0x3322);
+        } else {                       // 4 samples, each held for four pixels
+          const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(cbp) + g), r = __ldg(reinterpret_cast<const uint32_t*>(crp) + g);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { cbw[i] = __byte_perm(b, 0, 0x1111 * i); crw[i] = __byte_perm(r, 0, 0x1111 * i); }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int y = (int)((yw[i] >> (8 * j)) & 0xFFu), cb = (int)((cbw[i] >> (8 * j)) & 0xFFu), cr = (int)((crw[i] >> (8 * j)) & 0xFFu);
+            v[j] = to_rgb ? inverse_rgb(y, cb, cr) : ((uint32_t)y | ((uint32_t)cb << 8) | ((uint32_t)cr << 16));
+          }
+          st[12 * lane + 3 * i] = v[0] | (v[1] << 24);
+          st[12 * lane + 3 * i + 1] = (v[1] >> 8) | (v[2] << 16);
+          st[12 * lane + 3 * i + 2] = (v[2] >> 16) | (v[3] << 8);
+        }
+      }
+      __syncwarp();
+      const uint32_t valid = min(32u, gpr - g0) * 48u;                // bytes of this group that exist (a multiple of 16)
+      uint4* o = reinterpret_cast<uint4*>(orow + (size_t)g0 * 48u);
+#pragma unroll
+      for (uint32_t c = lane; c < 96u; c += 32u)
+        if ((c + 1u) * 16u <= valid) __stcs(o + c, reinterpret_cast<const uint4*>(st)[c]);
+      __syncwarp();
+    }
   }
 }
 
 int launch_expand_planar(const KPlan& k, const uint8_t* planar, uint8_t* out, int to_rgb, void* stream) {
   const uint64_t total = (uint64_t)k.n_frames * (uint64_t)k.Ho * (uint64_t)k.Wo;
   if (total == 0) return (int)cudaSuccess;
-  if (k.Wo % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
-    const uint64_t blocks = std::min<uint64_t>((total / 4 + 255) / 256, (uint64_t)148 * 32);
-    if (total / 4 + blocks * 256 < (1ull << 32)) csic_expand_planar4_kernel<uint32_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(k, planar, out, to_rgb);
-    else csic_expand_planar4_kernel<uint64_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(k, planar, out, to_rgb);
+  const uint64_t n_rows = (uint64_t)k.n_frames * (uint64_t)k.Ho;
+  if (k.Wo % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0 && n_rows < (1ull << 32)) {
+    const unsigned blocks = (unsigned)std::min<uint64_t>(n_rows, (uint64_t)148 * 16);
+    const unsigned threads = (unsigned)std::min<uint32_t>(128u, (((uint32_t)k.Wo >> 2) + 31u) & ~31u);
+    const uint32_t cw_bytes = (uint32_t)k.planar_cw;              // chroma plane rows must keep the vector loads aligned
+    const bool planes16 = (reinterpret_cast<uintptr_t>(planar) & 15u) == 0 && k.out_frame_bytes % 16 == 0 &&
+                          k.planar_cb_off % 16 == 0 && k.planar_cr_off % 16 == 0 &&
+                          cw_bytes % (16u / (uint32_t)k.planar_hs) == 0 && cw_bytes * (uint32_t)k.planar_hs == (uint32_t)k.Wo;
+    if (k.Wo % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0 && planes16) {
+      const unsigned th16 = (unsigned)std::min<uint32_t>(128u, (((uint32_t)k.Wo >> 4) + 31u) & ~31u);
+      csic_expand_planar16_kernel<<<blocks, th16, 0, (cudaStream_t)stream>>>(k, planar, out, to_rgb);
+    } else if (k.Wo % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0)
+      csic_expand_planar_rows_kernel<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(k, planar, out, to_rgb);
+    else
+      csic_expand_planar_rows_kernel<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(k, planar, out, to_rgb);
     return (int)cudaGetLastError();
   }
   const uint64_t blocks = std::min<uint64_t>((total + 255) / 256, (uint64_t)148 * 64);
