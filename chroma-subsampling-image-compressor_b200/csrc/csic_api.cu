@@ -134,7 +134,10 @@ int build_plan(const csic_params& p, const void* d_rgb, void* d_out, size_t n_fr
   k.hf = g.hf;
   k.vf = g.vf;
   k.last_sample_col = ((p.width - 1) / g.hf) * g.hf;
-  k.case_b = (!g.chroma_first && p.factor > 1) ? 1 : 0;
+  // Spatial before chroma runs the chroma stage with misaligned counters (ImageCompressorTop.scala:52-58) -- which only
+  // matters when that stage holds anything: with 4:4:4 (hf == vf == 1, the application's default) every element is its
+  // own sample point whatever the counters say, so any width takes the fast kernels.
+  k.case_b = (!g.chroma_first && p.factor > 1 && (g.hf > 1 || g.vf > 1)) ? 1 : 0;
   k.quant_first = g.quant_first ? 1 : 0;
   k.trunc = p.round_mode == CSIC_ROUND_TRUNC;
   k.average = (p.pool_mode == CSIC_POOL_AVERAGE && p.factor > 1) ? 1 : 0;
