@@ -88,6 +88,8 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
   constexpr uint32_t kGranBytes = (IN4 ? 16u : 12u) * F;     // one row part of a granule
   constexpr int kShift = (F == 2) ? 2 : (F == 4 ? 4 : 6);    // log2(F*F)
   constexpr int kHalf = (F * F) / 2;
+  constexpr int kH = (F == 8) ? 2 : 1;                       // chunks per row part
+  constexpr int NO = 4 / kH;                                 // output pixels per chunk
   const uint32_t n = meta->n_granules;
   uint32_t row = C.row0_of_thread, rem = C.rem0_of_thread;
   constexpr bool kStagedFmt = (FMT == KF_YCC888 || FMT == KF_RGB888);
@@ -95,8 +97,8 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
   // a warp's 32 granules are 384 consecutive output bytes which leave through the warp's own staging slot as 16-byte
   // stores -- no CTA-wide barrier, no TMA store: the kernel is bound by the integer pipes, a barrier per tile cost 10 %
   // 8x8 pooling: a granule is 256 input pixels, so a 24 KB tile has only ~32 of them -- four threads share one, two
-  // row parts each, and add their partial sums up with two shfl.xor steps (1080p 0.27 -> 0.49, 4K 0.36 -> 0.63 of the
-  // copy peak; eight threads per granule measured worse).
+  // row parts each (in two 16-pixel halves: 56 registers instead of 96), and add their partial sums up with two
+  // shfl.xor steps (1080p 0.27 -> 0.63, 4K 0.36 -> 0.82 of the copy peak; eight threads per granule measured worse).
   constexpr uint32_t kSplit = (F == 8) ? 4u : 1u;      // threads per granule
   constexpr uint32_t kGpw = 32u / kSplit;              // granules per warp and iteration
   const uint32_t sub = threadIdx.x % kSplit;
@@ -110,27 +112,31 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
     held_pair = C.pool_first ? meta->held_addr[row] : 0u;   // bit 31 | pooled Cb << 8 | pooled Cr
 #pragma unroll 1
     for (int dr = (int)(sub * (F / kSplit)); dr < (int)((sub + 1u) * (F / kSplit)); ++dr) {
-      uint32_t p[4 * F];
-      load_row_part<F, IN4>(base + (uint32_t)dr * C.seg_row_bytes, p);
+      // 8x8: the row part is taken in two halves of two output pixels each (16 pixels in registers instead of 32)
+#pragma unroll
+      for (int hh = 0; hh < kH; ++hh) {
+      const int ob = hh * NO;          // first output pixel of this chunk
+      uint32_t p[NO * F];
+      load_row_part<F / kH, IN4>(base + (uint32_t)dr * C.seg_row_bytes + (uint32_t)hh * (NO * F * (IN4 ? 4u : 3u)), p);
       // Y: byte 1 of each dp4a result is the pixel's Y.  Gather the F bytes of an output pixel's row part into
       // words with PRMT (byte 3 of a result is zero: the pad), mask once, and let dp4a add the bytes up.
 #pragma unroll
-      for (int o = 0; o < 4; ++o) {
+      for (int o = 0; o < NO; ++o) {
         uint32_t d[F];
 #pragma unroll
         for (int i = 0; i < F; ++i) d[i] = fwd_y16(p[o * F + i], C.coef_y);
         if (C.linear_y) {          // no quantiser in front: byte 1 of every result goes straight into the sum (FMA pipe)
 #pragma unroll
-          for (int i = 0; i < F; ++i) ay[o] = (int)dp4a_uu(d[i], 1u << 8, (uint32_t)ay[o]);
+          for (int i = 0; i < F; ++i) ay[ob + o] = (int)dp4a_uu(d[i], 1u << 8, (uint32_t)ay[ob + o]);
         } else if (F == 2) {
           const uint32_t w = __byte_perm(d[0], d[1], 0x3351) & C.pre_y4;
-          ay[o] = (int)dp4a_uu(w, 0x01010101u, (uint32_t)ay[o]);
+          ay[ob + o] = (int)dp4a_uu(w, 0x01010101u, (uint32_t)ay[ob + o]);
         } else {
 #pragma unroll
           for (int h = 0; h < F / 4; ++h) {
             const uint32_t lo = __byte_perm(d[4 * h], d[4 * h + 1], 0x3351), hi = __byte_perm(d[4 * h + 2], d[4 * h + 3], 0x3351);
             const uint32_t w = __byte_perm(lo, hi, 0x5410) & C.pre_y4;
-            ay[o] = (int)dp4a_uu(w, 0x01010101u, (uint32_t)ay[o]);
+            ay[ob + o] = (int)dp4a_uu(w, 0x01010101u, (uint32_t)ay[ob + o]);
           }
         }
       }
@@ -143,15 +149,16 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
           // them after the pooling), and rows of an odd counter line replay a pooled pair the producer supplies
           if (!held_pair) {
 #pragma unroll
-            for (int i = 0; i < 4 * F; ++i) {
-              if ((i / F) % HF == 0) {
-                ab[i / F] = (int)dp4a_uu(fwd_nc16<TRUNC>(p[i], C.coef_ncb), 1u << 8, (uint32_t)ab[i / F]);
-                ar[i / F] = (int)dp4a_uu(fwd_nc16<TRUNC>(p[i], C.coef_ncr), 1u << 8, (uint32_t)ar[i / F]);
+            for (int i = 0; i < NO * F; ++i) {
+              if ((ob + i / F) % HF == 0) {
+                ab[ob + i / F] = (int)dp4a_uu(fwd_nc16<TRUNC>(p[i], C.coef_ncb), 1u << 8, (uint32_t)ab[ob + i / F]);
+                ar[ob + i / F] = (int)dp4a_uu(fwd_nc16<TRUNC>(p[i], C.coef_ncr), 1u << 8, (uint32_t)ar[ob + i / F]);
               }
             }
           }
         } else if (C.vhold && (dr & 1)) {
           // nothing is sampled on an odd line: every pixel replays the last sample of the line above
+          if (hh == 0) {
           const uint32_t ha = meta->held_addr[row * (F / 2) + (uint32_t)(dr >> 1)];
           const uint32_t hp = lds8(ha) | (lds8(ha + 1) << 8) | (lds8(ha + 2) << 16);
           const uint32_t xb = fwd_nc16<TRUNC>(hp, C.coef_ncb), xr = fwd_nc16<TRUNC>(hp, C.coef_ncr);
@@ -160,16 +167,17 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
             ab[o] = (int)dp4a_uu(xb, (uint32_t)F << 8, (uint32_t)ab[o]);
             ar[o] = (int)dp4a_uu(xr, (uint32_t)F << 8, (uint32_t)ar[o]);
           }
+          }
         } else {
 #pragma unroll
-          for (int i = 0; i < 4 * F; i += HF) {   // sample points; each is held for HF pixels (ChromaSubsampler.scala:57-65)
+          for (int i = 0; i < NO * F; i += HF) {   // sample points; each is held for HF pixels (ChromaSubsampler.scala:57-65)
             const uint32_t xb = fwd_nc16<TRUNC>(p[i], C.coef_ncb), xr = fwd_nc16<TRUNC>(p[i], C.coef_ncr);
             if (HF <= F) {                        // the HF pixels lie inside one output pixel
-              ab[i / F] = (int)dp4a_uu(xb, (uint32_t)HF << 8, (uint32_t)ab[i / F]);
-              ar[i / F] = (int)dp4a_uu(xr, (uint32_t)HF << 8, (uint32_t)ar[i / F]);
+              ab[ob + i / F] = (int)dp4a_uu(xb, (uint32_t)HF << 8, (uint32_t)ab[ob + i / F]);
+              ar[ob + i / F] = (int)dp4a_uu(xr, (uint32_t)HF << 8, (uint32_t)ar[ob + i / F]);
             } else {                              // ... or cover HF / F whole output pixels
 #pragma unroll
-              for (int o = i / F; o < (i + HF) / F; ++o) {
+              for (int o = ob + i / F; o < ob + (i + HF) / F; ++o) {
                 ab[o] = (int)dp4a_uu(xb, (uint32_t)F << 8, (uint32_t)ab[o]);
                 ar[o] = (int)dp4a_uu(xr, (uint32_t)F << 8, (uint32_t)ar[o]);
               }
@@ -179,32 +187,35 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
       } else if (C.pool_first) {
         if (!held_pair) {
 #pragma unroll
-          for (int i = 0; i < 4 * F; ++i) {
-            if ((i / F) % HF == 0) {
-              ab[i / F] += (int)(((fwd_nc16<TRUNC>(p[i], C.coef_ncb) ^ 0xFFFFu) >> 8) & C.pre_cb);
-              ar[i / F] += (int)(((fwd_nc16<TRUNC>(p[i], C.coef_ncr) ^ 0xFFFFu) >> 8) & C.pre_cr);
+          for (int i = 0; i < NO * F; ++i) {
+            if ((ob + i / F) % HF == 0) {
+              ab[ob + i / F] += (int)(((fwd_nc16<TRUNC>(p[i], C.coef_ncb) ^ 0xFFFFu) >> 8) & C.pre_cb);
+              ar[ob + i / F] += (int)(((fwd_nc16<TRUNC>(p[i], C.coef_ncr) ^ 0xFFFFu) >> 8) & C.pre_cr);
             }
           }
         }
       } else if (C.vhold && (dr & 1)) {
+        if (hh == 0) {
         const uint32_t ha = meta->held_addr[row * (F / 2) + (uint32_t)(dr >> 1)];
         const uint32_t hp = lds8(ha) | (lds8(ha + 1) << 8) | (lds8(ha + 2) << 16);
         const int hb = (int)(((fwd_nc16<TRUNC>(hp, C.coef_ncb) ^ 0xFFFFu) >> 8) & C.pre_cb) * F;
         const int hr = (int)(((fwd_nc16<TRUNC>(hp, C.coef_ncr) ^ 0xFFFFu) >> 8) & C.pre_cr) * F;
 #pragma unroll
         for (int o = 0; o < 4; ++o) { ab[o] += hb; ar[o] += hr; }
+        }
       } else {
         int cb = 0, cr = 0;
 #pragma unroll
-        for (int i = 0; i < 4 * F; ++i) {
+        for (int i = 0; i < NO * F; ++i) {
           if (i % HF == 0) {          // sample point; held for the next HF-1 pixels (ChromaSubsampler.scala:57-65)
             cb = (int)(((fwd_nc16<TRUNC>(p[i], C.coef_ncb) ^ 0xFFFFu) >> 8) & C.pre_cb);
             cr = (int)(((fwd_nc16<TRUNC>(p[i], C.coef_ncr) ^ 0xFFFFu) >> 8) & C.pre_cr);
           }
-          ab[i / F] += cb;
-          ar[i / F] += cr;
+          ab[ob + i / F] += cb;
+          ar[ob + i / F] += cr;
         }
       }
+      }   // hh
     }
     }   // q < n: accumulation
     if (kSplit > 1u) {                 // partial sums of the threads that share the granule (adjacent lanes)
