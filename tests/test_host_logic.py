@@ -165,3 +165,21 @@ def test_product_never_touches_the_oracle():
                     (f, "references the oracle")
     out = subprocess.run(["nm", "-D", os.path.join(pkg, "libcsic.so")], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_every_bench_workload_is_a_legal_parameter_set():
+    """bench.py's named workloads must pass the reference's constructor predicates (csic_validate) and give the
+    algorithmic byte counts DESIGN.md quotes for the BASELINE configurations."""
+    import bench
+    import csic_b200 as csic
+    for name, (W, H, frames, a, b, q, f, order, fmt, desc) in bench.WORKLOADS.items():
+        pool = 1 if name.endswith("avg") else 0
+        p = csic.make_params(W, H, a, b, q[0], q[1], q[2], f, tuple(bench.ORD[c] for c in order), pool_mode=pool, out_format=fmt)
+        ow, oh, _, fb = csic.out_shape(p)
+        assert ow == -(-W // f) and oh == -(-H // f) and fb > 0 and frames > 0, name
+    W, H, _, a, b, q, f, order, fmt, _ = bench.WORKLOADS["cfg4"]
+    fb = csic.out_shape(csic.make_params(W, H, a, b, *q, f, tuple(bench.ORD[c] for c in order), out_format=fmt))[3]
+    assert fb == 8_294_400 and bench.algorithmic_bytes_per_frame(W, H, f, fb) == 20_736_000
+    W, H, _, a, b, q, f, order, fmt, _ = bench.WORKLOADS["cfg3"]
+    fb = csic.out_shape(csic.make_params(W, H, a, b, *q, f, tuple(bench.ORD[c] for c in order), out_format=fmt))[3]
+    assert bench.algorithmic_bytes_per_frame(W, H, f, fb) == 12_441_600
