@@ -66,10 +66,18 @@ __device__ __forceinline__ uint32_t inverse_rgb(int y, int cb, int cr) {
 __device__ __forceinline__ uint32_t inverse_rgb_raw(uint32_t dy, uint32_t xb, uint32_t xr, uint32_t my8, uint32_t mcb8, uint32_t mcr8) {
   const int y8 = (int)(dy & my8), cb8 = (int)((xb ^ 0xFFFFu) & mcb8), cr8 = (int)((xr ^ 0xFFFFu) & mcr8);
   const int c = 298 * y8;
-  const int r = clamp255((c + 409 * cr8 - 52224 * 256) >> 16);
-  const int g = clamp255((c - 100 * cb8 - 208 * cr8 + 39552 * 256) >> 16);
-  const int b = clamp255((c + 516 * cb8 - 65920 * 256) >> 16);
-  return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
+  // clamp the 16.16 values to [0, 0xFFFFFF]: byte 2 is then the clamped channel -- no shift, PRMT picks the bytes
+  const uint32_t r = (uint32_t)__vimin_s32_relu(c + 409 * cr8 - 52224 * 256, 0x00FFFFFF);
+  const uint32_t g = (uint32_t)__vimin_s32_relu(c - 100 * cb8 - 208 * cr8 + 39552 * 256, 0x00FFFFFF);
+  const uint32_t b = (uint32_t)__vimin_s32_relu(c + 516 * cb8 - 65920 * 256, 0x00FFFFFF);
+  return __byte_perm(__byte_perm(r, g, 0x3362), b, 0x3610);     // R | G << 8 | B << 16
+}
+
+// Four 24-bit pixels (R | G << 8 | B << 16) -> the twelve bytes of a granule, three PRMTs.
+__device__ __forceinline__ void pack_rgb_granule(const uint32_t (&v)[4], uint32_t& w0, uint32_t& w1, uint32_t& w2) {
+  w0 = __byte_perm(v[0], v[1], 0x4210);     // R0 G0 B0 R1
+  w1 = __byte_perm(v[1], v[2], 0x5421);     // G1 B1 R2 G2
+  w2 = __byte_perm(v[2], v[3], 0x6542);     // B2 R3 G3 B3
 }
 
 }  // namespace csic

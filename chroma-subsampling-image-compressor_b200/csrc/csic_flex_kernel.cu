@@ -365,9 +365,9 @@ __global__ void __launch_bounds__(kFlexMaxThreads, 4) csic_flex_kernel(const __g
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             v[j] = inverse_rgb_raw(dy[j], xb[j], xr[j], my << 8, mcb << 8, mcr << 8);
-          sts32(so, v[0] | (v[1] << 24));
-          sts32(so + 4, (v[1] >> 8) | (v[2] << 16));
-          sts32(so + 8, (v[2] >> 16) | (v[3] << 8));
+          uint32_t w0, w1, w2;
+          pack_rgb_granule(v, w0, w1, w2);
+          sts32(so, w0); sts32(so + 4, w1); sts32(so + 8, w2);
         } else if (FMT == KF_PLANAR) {
           const uint32_t my4 = my * 0x01010101u;
           sts32(so, __byte_perm(__byte_perm(dy[0], dy[1], 0x0051), __byte_perm(dy[2], dy[3], 0x0051), 0x5410) & my4);

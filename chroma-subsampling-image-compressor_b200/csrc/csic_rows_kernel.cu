@@ -160,9 +160,9 @@ __device__ __forceinline__ void tile_loop(uint32_t in_s, uint32_t out_s, uint8_t
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = inverse_rgb_raw(dy[j], xb[j], xr[j], C.my << 8, C.mcb << 8, C.mcr << 8);
       const uint32_t a = out_s + q * 12u;
-      sts32(a, v[0] | (v[1] << 24));
-      sts32(a + 4, (v[1] >> 8) | (v[2] << 16));
-      sts32(a + 8, (v[2] >> 16) | (v[3] << 8));
+      uint32_t w0, w1, w2;
+      pack_rgb_granule(v, w0, w1, w2);
+      sts32(a, w0); sts32(a + 4, w1); sts32(a + 8, w2);
     } else {
       // bundle slots go straight to global memory: one coalesced 4/8/16-byte store per granule
       uint32_t v[4];
