@@ -47,16 +47,15 @@ __device__ __forceinline__ uint32_t fwd_nc16(uint32_t p, uint32_t coef) {
   return (uint32_t)x;
 }
 
-// max(min(v, 255), 0) in one instruction (VIMNMX with the RELU modifier)
-__device__ __forceinline__ int clamp255(int v) { return __vimin_s32_relu(v, 255); }
 
 // YCbCrUtils.ycbcr2rgb with the -128 offsets folded into the constants.  Returns R | G<<8 | B<<16.
 __device__ __forceinline__ uint32_t inverse_rgb(int y, int cb, int cr) {
   const int c = 298 * y;
-  const int r = clamp255((c + 409 * cr - 52224) >> 8);
-  const int g = clamp255((c - 100 * cb - 208 * cr + 39552) >> 8);
-  const int b = clamp255((c + 516 * cb - 65920) >> 8);
-  return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
+  // clamp the 24.8 values to [0, 0xFFFF]: byte 1 is then the clamped channel -- no shift, PRMT picks the bytes
+  const uint32_t r = (uint32_t)__vimin_s32_relu(c + 409 * cr - 52224, 0xFFFF);
+  const uint32_t g = (uint32_t)__vimin_s32_relu(c - 100 * cb - 208 * cr + 39552, 0xFFFF);
+  const uint32_t b = (uint32_t)__vimin_s32_relu(c + 516 * cb - 65920, 0xFFFF);
+  return __byte_perm(__byte_perm(r, g, 0x3351), b, 0x3510);     // R | G << 8 | B << 16
 }
 
 // The same transform applied straight to the forward results: dy = fwd_y16 (byte 1 = Y), xb / xr = fwd_nc16 (byte 1 =
