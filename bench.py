@@ -204,6 +204,294 @@ def config_dict(name, wl, frames_per_gpu, note=None):
     return c
 
 
+class Env:
+    """Rank bookkeeping + the two process groups: NCCL for the timed barrier / max-over-ranks, gloo for waits
+    that must not spin a host core (ranks idling while rank 0 times the CPU baseline)."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            sys.exit("bench.py needs a CUDA device: there is no CPU fallback for the pixel path")
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        self.gloo = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+            self.gloo = dist.new_group(backend="gloo")
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def idle_barrier(self):
+        if self.dist is not None:
+            self.dist.barrier(group=self.gloo)
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device="cuda")
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather(self, values):
+        """[world][len(values)] floats, same on every rank."""
+        t = self.torch.tensor([float(v) for v in values], dtype=self.torch.float64, device="cuda")
+        if self.dist is None:
+            return [t.tolist()]
+        outt = self.torch.empty((self.world, t.numel()), dtype=self.torch.float64, device="cuda")
+        self.dist.all_gather_into_tensor(outt, t)
+        return outt.tolist()
+
+
+def device_run(env, ctx, name, frames, shard, steps, warmup, graph, in_format=0, verify=True, replays=1, one_gpu_too=False):
+    """Inputs resident in HBM, one kernel launch per step, CUDA events on the launching stream, max over ranks.
+    Every rank does the same untimed work first (parity spot check, full-batch cross-check, W warm-up steps).
+    shard == "bands": every rank owns one aligned row band of EVERY frame of one shared batch (strong scaling)."""
+    import numpy as np
+    import csic_b200 as csic
+    import oracle
+    torch = env.torch
+    wl = WORKLOADS[name]
+    W, H, _, a, b, q, f, order, fmt, desc = wl
+    ops = tuple(ORD[c] for c in order)
+    pool = 1 if name.endswith("avg") else 0
+    p = csic.make_params(W, H, a, b, q[0], q[1], q[2], f, ops, pool_mode=pool, out_format=fmt, in_format=in_format)
+    ipb = 3 if in_format == 0 else 4
+    _, out_h, _, out_fb = csic.out_shape(p)
+
+    gen = torch.Generator(device="cuda").manual_seed(0x5EED + (env.rank if shard == "frames" else 0))
+    rgb = torch.empty((frames, H, W, ipb), dtype=torch.uint8, device="cuda")
+    step_f = max(1, (1 << 29) // (W * H * ipb))      # chunked: randint materialises int64 temporaries for some dtypes
+    for i in range(0, frames, step_f):
+        rgb[i:i + step_f] = torch.randint(0, 256, rgb[i:i + step_f].shape, dtype=torch.uint8, device="cuda", generator=gen)
+    out = torch.empty((frames, out_fb), dtype=torch.uint8, device="cuda")
+
+    # parity spot check (outside the timed region, on every rank): one frame against the oracle
+    nchk = min(2, frames)
+    ctx.process_torch(p, rgb[:nchk], out=out[:nchk])
+    torch.cuda.synchronize()
+    want = oracle.process(oracle.make_params(W, H, a, b, q, f, order, pool_mode=pool, out_format=fmt, in_format=in_format),
+                          rgb[nchk - 1].cpu().numpy())
+    parity = bool(np.array_equal(out[nchk - 1].cpu().numpy(), want[0]))
+
+    band = None
+    if shard == "bands":
+        chroma_first = order.index("C") < order.index("S")
+        band = csic.band_plan(out_h, env.world, f, a, b, chroma_first)[env.rank]
+
+    def step(bnd=band):
+        if bnd is None:
+            ctx.process_torch(p, rgb, out=out)      # one kernel launch on torch's current stream
+        else:
+            ctx.process_torch(p, rgb, out=out, out_row0=bnd[0], out_rows=bnd[1])
+
+    # full-size cross-check (outside the timed region, on every rank so that all ranks enter the timed region equally
+    # warm): the whole batch through the independent generic gather kernel must equal the fast kernel's output
+    full_check = None
+    family_opt = ctx_family(ctx)
+    if verify and family_opt != 1:
+        try:
+            ctx.process_torch(p, rgb, out=out)
+            fam_fast = ctx.last_kernel()[0]
+            ref = torch.empty_like(out)
+            ctx.set_option(0, 1)
+            ctx.process_torch(p, rgb, out=ref)
+            ctx.set_option(0, family_opt)
+            torch.cuda.synchronize()
+            full_check = {"frames": frames, "kernels": [fam_fast, 1], "equal": bool(torch.equal(out, ref))}
+            del ref
+            torch.cuda.empty_cache()
+        except torch.cuda.OutOfMemoryError:
+            full_check = {"skipped": "not enough device memory for a second output buffer"}
+            ctx.set_option(0, family_opt)
+
+    def timed(bnd, sampler):
+        """-> (total ms of `steps` launches on this rank, per-step ms list)"""
+        for _ in range(warmup):
+            step(bnd)
+        env.barrier() if bnd is band else torch.cuda.synchronize()
+        if sampler is not None:
+            sampler.start()
+        if graph:
+            # launch-bound workloads: the K launches are captured once and replayed as one CUDA graph, so the device
+            # time holds no host launch cost; `replays` replays are timed one by one, the median is reported
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                step(bnd)
+                with torch.cuda.graph(g, stream=side):
+                    for _ in range(steps):
+                        step(bnd)
+            torch.cuda.current_stream().wait_stream(side)
+            g.replay()
+            totals = []
+            for _ in range(replays):
+                env.barrier() if bnd is band else torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); g.replay(); e1.record()
+                env.barrier() if bnd is band else torch.cuda.synchronize()
+                totals.append(e0.elapsed_time(e1))
+            return totals, [t / steps for t in totals]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        env.barrier() if bnd is band else torch.cuda.synchronize()
+        ev[0].record()
+        for i in range(steps):
+            step(bnd)
+            ev[i + 1].record()
+        env.barrier() if bnd is band else torch.cuda.synchronize()
+        return [ev[0].elapsed_time(ev[-1])], [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+
+    fam0, launches0 = ctx.last_kernel()
+    sampler = ClockSampler(env.local)
+    totals, step_ms = timed(band, sampler)
+    clocks = sampler.stop()
+    fam, launches1 = ctx.last_kernel()
+    launches_timed = steps * (replays if graph else 1)
+    # max over ranks, replay by replay; the median replay is the figure (one "replay" for stream launches)
+    totals_max = [env.max_over_ranks(t) for t in totals]
+    total_ms_max = statistics.median(totals_max)
+    mp_per_step_all = frames * W * H * (env.world if band is None else 1) / 1e6
+    value = mp_per_step_all * steps / (total_ms_max / 1e3)
+
+    alg_bytes = algorithmic_bytes_per_frame(W, H, f, out_fb, average=bool(pool), ipb=ipb) * frames          # per launch (one rank)
+    if band is not None:
+        alg_bytes = alg_bytes * band[1] // out_h
+    kernel_ms = statistics.median(step_ms) if graph else statistics.mean(step_ms)                        # one launch per step
+    peak, peak_src = load_peak()
+    achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
+    cap_bits = sum(bit for n_, bit in ClockSampler.NAMES.items() if n_ in (clocks.get("reasons") or []))
+    per_rank = env.gather([statistics.median(totals), kernel_ms, min(step_ms), max(step_ms), clocks.get("sm_mhz") or 0, cap_bits])
+    slowest = max(range(env.world), key=lambda r: per_rank[r][0])
+    res = {
+        "workload": name, "value": round(value, 1), "unit": "MP/s", "ms_per_step": round(total_ms_max / steps, 4),
+        "steps": steps, "frames_per_gpu": frames, "sharding": shard, "scaling": "weak" if band is None else "strong",
+        "timed_as": f"cuda_graph_replay (median of {replays} replays of {steps} launches)" if graph else "stream_launches",
+        "per_rank_ms": [round(r[0] / steps, 4) for r in per_rank],
+        "per_rank_sm_mhz": [r[4] for r in per_rank],
+        "per_rank_reasons": [sorted(n_ for n_, bit in ClockSampler.NAMES.items() if int(r[5]) & bit) for r in per_rank],
+        "slowest_rank": slowest,
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": None,
+                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(kernel_ms, 4),
+                     "kernel": {2: "csic_rows_kernel", 3: "csic_pool_kernel", 4: "csic_flex_kernel"}.get(fam, "csic_generic_kernel"),
+                     "peak_source": peak_src, "rank": 0},
+        "clocks": clocks, "gpu_launches": launches_timed * env.world,
+        "parity_spot_check": parity, "full_batch_cross_check": full_check,
+        "step_ms_min": round(min(step_ms), 4), "step_ms_max": round(max(step_ms), 4),
+    }
+    if band is not None:
+        res["band_rows_rank0"] = list(band)
+    if one_gpu_too and band is not None and env.world > 1:
+        # strong scaling needs the one-GPU time of the SAME batch on the SAME box: rank 0 runs all rows alone
+        # (the other ranks wait on a socket, GPUs idle), timed the same way
+        if env.rank == 0:
+            t1, _ = timed((0, out_h), None)
+            one = statistics.median(t1)
+        else:
+            one = 0.0
+        env.idle_barrier()
+        one = env.max_over_ranks(one)
+        res["one_gpu_ms_per_step"] = round(one / steps, 4)
+        res["speedup_vs_one_gpu"] = round(one / total_ms_max, 3)
+    res["_state"] = (p, rgb, out, ipb, out_fb)
+    return res
+
+
+def ctx_family(ctx):
+    return getattr(ctx, "_bench_family", 0)
+
+
+def e2e_run(env, ctx, p, rgb, out, W, H, ipb, out_fb, frames, steps):
+    """The same metric through csic_process_host (the reference-facing C-ABI call) with pinned HOST buffers: every
+    step copies its inputs host->device and its result device->host inside the timed region (wall clock around the
+    synchronous calls, barrier on both sides, max over ranks)."""
+    import numpy as np
+    import csic_b200 as csic
+    torch = env.torch
+    hb = min(frames, max(1, int(3.2e9 // (W * H * ipb))))         # frames per pinned host batch (~3.2 GB)
+    calls = -(-frames // hb)
+    pin_in = csic.PinnedBuffer(hb * H * W * ipb)
+    pin_out = csic.PinnedBuffer(hb * out_fb)
+    hin = torch.from_numpy(pin_in.array)
+    hin.copy_(rgb[:hb].reshape(-1))                               # real pixel data in the pinned buffer
+    torch.cuda.synchronize()
+    hin_np = pin_in.array.reshape(hb, H, W, ipb)
+    hout_np = pin_out.array.reshape(hb, out_fb)
+    e2e_steps = max(1, min(steps, 3))
+
+    def e2e_step():
+        done = 0
+        for _ in range(calls):
+            n = min(hb, frames - done)
+            ctx.process_host(p, hin_np[:n], out=hout_np[:n])   # H2D + kernel + D2H, synchronous
+            done += n
+
+    e2e_step()
+    env.barrier()
+    hb0 = ctx.host_bytes()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    mine = time.perf_counter() - t0
+    env.barrier()
+    dt = time.perf_counter() - t0
+    dt_max = env.max_over_ranks(dt)
+    per_rank = env.gather([mine])
+    e2e_ok = bool(np.array_equal(hout_np[hb - 1], out[hb - 1].cpu().numpy()))
+    h2d = (ctx.host_bytes() - hb0) // e2e_steps
+    d2h = frames * out_fb
+    mp_all = frames * W * H * env.world / 1e6
+    e2e = {"value": round(mp_all * e2e_steps / dt_max, 1), "unit": "MP/s",
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "h2d_note": "per rank; DECIMATE f>1 reads every f-th input row only; csic_process_host ships just those rows",
+           "steps": e2e_steps, "calls_per_step": calls, "host_batch_frames": hb,
+           "api": "csic_process_host (pinned host buffers; chunked H2D/kernel/D2H pipeline)",
+           "matches_device_path": e2e_ok,
+           "per_rank_s_per_step": [round(r[0] / e2e_steps, 4) for r in per_rank],
+           "link_gbs": {"h2d": round(h2d * env.world * e2e_steps / dt_max / 1e9, 2),
+                        "d2h": round(d2h * env.world * e2e_steps / dt_max / 1e9, 2)}}
+    ceil = load_link_ceiling(env.world)
+    if ceil:
+        both = ceil["h2d_gbs"] + ceil["d2h_gbs"]
+        e2e["link_ceiling_gbs"] = ceil
+        e2e["frac_of_ceiling"] = round((e2e["link_gbs"]["h2d"] + e2e["link_gbs"]["d2h"]) / both, 3)
+    pin_in.free(); pin_out.free()
+    return e2e
+
+
+def load_link_ceiling(world):
+    """Measured host<->device link ceiling with `world` GPUs copying at once (tools/pcie_ceiling.py, kind duplex_2d:
+    the H2D/D2H byte mix of the default workload), from profiles/r2/pcie_ceiling.json."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2", "pcie_ceiling.json")))
+        c = d["concurrent"][str(world)]
+        return {"h2d_gbs": c["h2d_gbs"], "d2h_gbs": c["d2h_gbs"], "source": d.get("source", "profiles/r2/pcie_ceiling.json"),
+                "what": c.get("what", "cudaMemcpy2DAsync H2D || cudaMemcpyAsync D2H on all GPUs at once, pinned memory")}
+    except Exception:
+        return None
+
+
+def cpu_baseline(wl):
+    W, H = wl[0], wl[1]
+    cores = os.cpu_count() or 1
+    fr = cores * max(1, min(4, int(3.0e9 / (W * H * 3 * 4 * cores))))
+    mps, _ = oracle_throughput(wl, fr, cores, steps=2, warmup=1)
+    mps1, _ = oracle_throughput(wl, 2, 1, steps=1, warmup=0)      # SURVEY D5 (i): one thread, streaming form
+    return {"value": round(mps, 2), "unit": "MP/s", "cores": cores, "kind": "port",
+            "sample": f"{fr} frames of {W}x{H}, 2 timed passes, {cores} host threads (oracle/csic_oracle.c)",
+            "value_1thread": round(mps1, 2), "sample_1thread": f"2 frames of {W}x{H}, 1 thread",
+            "note": "scalar three-pass CPU restatement of the Scala/Chisel path (the reference itself needs a JVM); "
+                    "other ranks idle on a socket while this runs"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -214,6 +502,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default: the workload's)")
     ap.add_argument("--graph", action="store_true",
                     help="capture the K timed launches into one CUDA graph and time its replay (launch-bound workloads)")
+    ap.add_argument("--replays", type=int, default=5, help="with --graph: timed replays; the median is reported")
     ap.add_argument("--in-format", type=int, default=0, choices=[0, 1, 2], help="0 RGB24, 1 RGBA32, 2 BGRA32")
     ap.add_argument("--generic", action="store_true", help="force the generic gather kernel (family 1)")
     ap.add_argument("--family", type=int, default=0, choices=[0, 1, 2],
@@ -221,6 +510,7 @@ def main():
     ap.add_argument("--no-verify", action="store_true", help="skip the full-batch cross-check against the generic kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the short extra runs of BASELINE configs[2] and configs[4]")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
     ap.add_argument("--tile-bytes", type=int, default=0)
@@ -235,33 +525,17 @@ def main():
         run_reference(args, wl, args.workload)
         return
 
-    import numpy as np
-    import torch
     import csic_b200 as csic
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        sys.exit("bench.py needs a CUDA device: there is no CPU fallback for the pixel path")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
+    env = Env()
+    torch = env.torch
     W, H, frames, a, b, q, f, order, fmt, desc = wl
     frames = args.frames or frames
-    ops = tuple(ORD[c] for c in order)
-    pool = 1 if args.workload.endswith("avg") else 0
-    p = csic.make_params(W, H, a, b, q[0], q[1], q[2], f, ops, pool_mode=pool, out_format=fmt, in_format=args.in_format)
-    ipb = 3 if args.in_format == 0 else 4
-    _, out_h, _, out_fb = csic.out_shape(p)
-    ctx = csic.Context(local)
+    ctx = csic.Context(env.local)
     if args.generic:
         args.family = 1
     if args.family:
         ctx.set_option(0, args.family)
+        ctx._bench_family = args.family
     if args.ctas_per_sm:
         ctx.set_option(2, args.ctas_per_sm)
     if args.stages:
@@ -270,200 +544,84 @@ def main():
         ctx.set_option(4, args.tile_bytes)
     if args.block_threads:
         ctx.set_option(5, args.block_threads)
+    default_run = args.workload == "cfg4" and args.shard == "frames" and not args.family
 
-    # ---- synthetic input, resident in HBM --------------------------------------------------------
-    gen = torch.Generator(device="cuda").manual_seed(0x5EED + rank)
-    rgb = torch.empty((frames, H, W, ipb), dtype=torch.uint8, device="cuda")
-    for i in range(0, frames, 64):      # chunked: randint materialises int64 temporaries for some dtypes
-        rgb[i:i + 64] = torch.randint(0, 256, rgb[i:i + 64].shape, dtype=torch.uint8, device="cuda", generator=gen)
-    out = torch.empty((frames, out_fb), dtype=torch.uint8, device="cuda")
-
-    # parity spot check (outside the timed region): one frame against the oracle
-    parity = None
-    if rank == 0:
-        import oracle
-        nchk = min(2, frames)
-        ctx.process_torch(p, rgb[:nchk], out=out[:nchk])
-        torch.cuda.synchronize()
-        want = oracle.process(oracle.make_params(W, H, a, b, q, f, order, pool_mode=pool, out_format=fmt, in_format=args.in_format),
-                              rgb[nchk - 1].cpu().numpy())
-        parity = bool(np.array_equal(out[nchk - 1].cpu().numpy(), want[0]))
-
-    # row-band sharding: rank r processes output rows [r0, r0+rows) of every frame, zero halo (aligned bands)
-    band = None
-    if args.shard == "bands":
-        chroma_first = order.index("C") < order.index("S")
-        band = csic.band_plan(out_h, world, f, a, b, chroma_first)[rank]
-
-    def step():
-        if band is None:
-            ctx.process_torch(p, rgb, out=out)      # one kernel launch on torch's current stream
-        else:
-            ctx.process_torch(p, rgb, out=out, out_row0=band[0], out_rows=band[1])
-
-    # full-size cross-check (outside the timed region): the whole batch through the independent generic gather
-    # kernel must equal the TMA kernel's output byte for byte
-    full_check = None
-    if rank == 0 and not args.no_verify and args.family != 1:
-        try:
-            ctx.process_torch(p, rgb, out=out)
-            fam_fast = ctx.last_kernel()[0]
-            ref = torch.empty_like(out)
-            ctx.set_option(0, 1)
-            ctx.process_torch(p, rgb, out=ref)
-            ctx.set_option(0, args.family)
-            torch.cuda.synchronize()
-            full_check = {"frames": frames, "kernels": [fam_fast, 1], "equal": bool(torch.equal(out, ref))}
-            del ref
-            torch.cuda.empty_cache()
-        except torch.cuda.OutOfMemoryError:
-            full_check = {"skipped": "not enough device memory for a second output buffer"}
-            ctx.set_option(0, args.family)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident timing --------------------------------------------------------------------
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    fam0, launches0 = ctx.last_kernel()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    if args.graph:
-        # launch-bound workloads: the K launches are captured once and replayed as one CUDA graph, so the
-        # device time no longer contains the host's per-launch cost
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.stream(side):
-            step()
-            with torch.cuda.graph(graph, stream=side):
-                for i in range(args.steps):
-                    step()
-        torch.cuda.current_stream().wait_stream(side)
-        graph.replay()
-        barrier()
-        ev[0].record()
-        graph.replay()
-        ev[-1].record()
-        barrier()
-        total_ms = ev[0].elapsed_time(ev[-1])
-        step_ms = [total_ms / args.steps] * args.steps
-    else:
-        barrier()
-        ev[0].record()
-        for i in range(args.steps):
-            step()
-            ev[i + 1].record()
-        barrier()
-        step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-        total_ms = ev[0].elapsed_time(ev[-1])
-    clocks = sampler.stop() if rank == 0 else None
-    fam, launches1 = ctx.last_kernel()
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
-    mp_per_step_all = frames * W * H * (world if band is None else 1) / 1e6
-    value = mp_per_step_all * args.steps / (total_ms_max / 1e3)
-
-    alg_bytes = algorithmic_bytes_per_frame(W, H, f, out_fb, average=bool(pool), ipb=ipb) * frames          # per launch (one rank)
-    if band is not None:
-        alg_bytes = alg_bytes * band[1] // out_h
-    kernel_ms = statistics.mean(step_ms)                                      # one launch per step
-    peak, peak_src = load_peak()
-    achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
-    traffic = None
+    main_res = device_run(env, ctx, args.workload, frames, args.shard, args.steps, args.warmup, args.graph,
+                          in_format=args.in_format, verify=not args.no_verify, replays=args.replays)
+    p, rgb, out, ipb, out_fb = main_res.pop("_state")
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and args.shard == "frames":
         try:
             tj = json.load(open(tp)).get(args.workload)
-            if tj:      # bytes per frame measured by ncu --set full, scaled to this launch
-                traffic = tj["dram_bytes_per_frame"] * frames
+            if tj:      # DRAM bytes of one launch measured by ncu, per frame x the frames of this launch
+                main_res["roofline"]["traffic"] = tj["dram_bytes_per_frame"] * frames
+                main_res["roofline"]["traffic_source"] = tj.get("source")
         except Exception:
             pass
 
-    # ---- end to end through the C ABI with host buffers --------------------------------------------
     e2e = None
-    if not args.no_e2e and band is None:
-        hb = min(frames, max(1, int(3.2e9 // (W * H * ipb))))         # frames per pinned host batch (~3.2 GB)
-        calls = -(-frames // hb)
-        pin_in = csic.PinnedBuffer(hb * H * W * ipb)
-        pin_out = csic.PinnedBuffer(hb * out_fb)
-        hin = torch.from_numpy(pin_in.array)
-        hin.copy_(rgb[:hb].reshape(-1))                               # real pixel data in the pinned buffer
-        torch.cuda.synchronize()
-        hin_np = pin_in.array.reshape(hb, H, W, ipb)
-        hout_np = pin_out.array.reshape(hb, out_fb)
-        e2e_steps = max(1, min(args.steps, 3))
+    if not args.no_e2e and args.shard == "frames":
+        e2e = e2e_run(env, ctx, p, rgb, out, W, H, ipb, out_fb, frames, args.steps)
+    del rgb, out
+    torch.cuda.empty_cache()
 
-        def e2e_step():
-            done = 0
-            for _ in range(calls):
-                n = min(hb, frames - done)
-                ctx.process_host(p, hin_np[:n], out=hout_np[:n])   # H2D + kernel + D2H, synchronous
-                done += n
+    # ---- the other BASELINE configs, witnessed in the same run (short) -----------------------------
+    also = None
+    if default_run and not args.no_also:
+        also = {}
+        r = device_run(env, ctx, "cfg3", WORKLOADS["cfg3"][2], "frames", max(args.steps, 20), args.warmup, False, verify=False)
+        r.pop("_state")
+        also["configs[2] cfg3"] = slim(r, WORKLOADS["cfg3"][9])
+        torch.cuda.empty_cache()
+        r = device_run(env, ctx, "cfg5", 256, "bands", 50, args.warmup, True, verify=False, replays=7, one_gpu_too=True)
+        r.pop("_state")
+        also["configs[4] cfg5 row bands"] = slim(r, "BASELINE configs[4]: 7680x4320 x256 frames (one shared batch), every rank "
+                                                 "computes one aligned row band of every frame (zero halo), 4:2:0 + f=4 + Q_16BIT + "
+                                                 "RGB888 reconstruct; strong scaling")
+        torch.cuda.empty_cache()
 
-        e2e_step()
-        barrier()
-        hb0 = ctx.host_bytes()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_ok = bool(np.array_equal(hout_np[hb - 1], out[hb - 1].cpu().numpy()))
-        e2e = {"value": round(mp_per_step_all * e2e_steps / float(tt.item()), 1), "unit": "MP/s",
-               "h2d_bytes_per_step": (ctx.host_bytes() - hb0) // e2e_steps, "d2h_bytes_per_step": frames * out_fb,
-               "h2d_note": "DECIMATE f>1 reads every f-th input row only; csic_process_host ships just those rows",
-               "steps": e2e_steps, "calls_per_step": calls, "host_batch_frames": hb,
-               "api": "csic_process_host (pinned host buffers; chunked H2D/kernel/D2H pipeline)",
-               "matches_device_path": e2e_ok}
-        pin_in.free(); pin_out.free()
-
-    # ---- CPU baseline (rank 0, N=1 only; bounded sample) -------------------------------------------
+    # ---- CPU baseline (rank 0, every N; bounded sample; the other ranks wait without spinning) -----
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
-        fr = cores * max(1, min(4, int(3.0e9 / (W * H * 3 * 4 * cores))))
-        mps, _ = oracle_throughput(wl, fr, cores, steps=2, warmup=1)
-        mps1, _ = oracle_throughput(wl, 2, 1, steps=1, warmup=0)      # one thread, streaming form
-        cpu = {"value": round(mps, 2), "unit": "MP/s", "cores": cores, "kind": "port",
-               "sample": f"{fr} frames of {W}x{H}, 2 timed passes, {cores} host threads (oracle/csic_oracle.c)",
-               "value_1thread": round(mps1, 2), "sample_1thread": f"2 frames of {W}x{H}, 1 thread"}
+    if not args.no_cpu:
+        if env.rank == 0:
+            cpu = cpu_baseline(wl)
+        env.idle_barrier()
 
-    if rank == 0:
+    if env.rank == 0:
+        band_note = None if args.shard == "frames" else \
+            f"row-band sharding: {env.world} aligned bands per frame, zero halo, rank 0 band = rows {main_res.get('band_rows_rank0')}"
         line = {
-            "metric": "input megapixels/s", "value": round(value, 1), "unit": "MP/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms_max / args.steps, 4),
-            "higher_is_better": True, "scaling": "weak" if band is None else "strong", "vs_baseline": None, "dtype": "u8",
+            "metric": "input megapixels/s", "value": main_res["value"], "unit": "MP/s", "n_gpus": env.world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"],
+            "higher_is_better": True, "scaling": main_res["scaling"], "vs_baseline": None, "dtype": "u8",
             "data": "synthetic (uniform random bytes, torch.randint, seed 0x5EED+rank, generated in HBM)",
-            "config": dict(config_dict(args.workload, wl, frames, note=None if band is None else
-                                  f"row-band sharding: {world} aligned bands per frame, zero halo, rank 0 band = rows {band}"),
+            "config": dict(config_dict(args.workload, wl, frames, note=band_note),
                            in_format=["RGB24", "RGBA32", "BGRA32"][args.in_format]),
-            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": traffic,
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(kernel_ms, 4),
-                         "kernel": {2: "csic_rows_kernel", 3: "csic_pool_kernel", 4: "csic_flex_kernel"}.get(fam, "csic_generic_kernel"),
-                         "peak_source": peak_src},
-            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": int(launches1 - launches0) * world,
-            "timed_as": "cuda_graph_replay" if args.graph else "stream_launches",
-            "parity_spot_check": parity, "full_batch_cross_check": full_check, "step_ms_min": round(min(step_ms), 4), "step_ms_max": round(max(step_ms), 4),
+            "roofline": main_res["roofline"], "cpu_baseline": cpu, "e2e": e2e, "clocks": main_res["clocks"],
+            "gpu_launches": main_res["gpu_launches"], "timed_as": main_res["timed_as"],
+            "per_rank_ms": main_res["per_rank_ms"], "per_rank_sm_mhz": main_res["per_rank_sm_mhz"],
+            "per_rank_reasons": main_res["per_rank_reasons"], "slowest_rank": main_res["slowest_rank"],
+            "parity_spot_check": main_res["parity_spot_check"], "full_batch_cross_check": main_res["full_batch_cross_check"],
+            "step_ms_min": main_res["step_ms_min"], "step_ms_max": main_res["step_ms_max"],
+            "also": also,
         }
+        for k in ("one_gpu_ms_per_step", "speedup_vs_one_gpu"):
+            if k in main_res:
+                line[k] = main_res[k]
         print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    if env.dist is not None:
+        env.dist.barrier()
+        env.dist.destroy_process_group()
     ctx.close()
+
+
+def slim(r, desc):
+    keep = ("value", "unit", "ms_per_step", "steps", "frames_per_gpu", "sharding", "scaling", "timed_as", "per_rank_ms",
+            "slowest_rank", "gpu_launches", "parity_spot_check", "one_gpu_ms_per_step", "speedup_vs_one_gpu", "band_rows_rank0")
+    d = {"workload": f"{r['workload']}: {desc}"}
+    d.update({k: r[k] for k in keep if k in r})
+    d["roofline"] = {k: r["roofline"][k] for k in ("achieved", "peak", "frac", "kernel", "kernel_ms", "algorithmic_bytes_per_launch")}
+    return d
 
 
 if __name__ == "__main__":

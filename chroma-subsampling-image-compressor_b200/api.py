@@ -170,6 +170,25 @@ class PinnedBuffer:
             pass
 
 
+def _host_args(p, rgb, out):
+    """Shape / dtype / size checks shared by every host entry point: a wrong array must raise here, not become an
+    out-of-bounds native read or write.  -> (rgb [n,H,W,C] contiguous uint8, n, out [n*bytes_per_frame])."""
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+    if rgb.ndim == 3:
+        rgb = rgb[None]
+    ch = 3 if p.in_format == InFormat.RGB24 else 4
+    if rgb.ndim != 4 or rgb.shape[1:] != (p.height, p.width, ch):
+        raise IllegalArgumentException(-9, f"rgb must be [n,{p.height},{p.width},{ch}], got {rgb.shape}")
+    n = rgb.shape[0]
+    fb = out_shape(p)[3]
+    if out is None:
+        out = np.empty((n, fb), dtype=np.uint8)
+    elif not (isinstance(out, np.ndarray) and out.dtype == np.uint8 and out.flags.c_contiguous and out.flags.writeable
+              and out.size == n * fb):
+        raise IllegalArgumentException(-9, f"out must be a writable C-contiguous uint8 array of {n * fb} bytes")
+    return rgb, n, out
+
+
 class Context:
     """`csic_ctx`: one per (host thread, GPU)."""
     KERNEL_AUTO, KERNEL_GENERIC, KERNEL_NO_ALIGNED_TMA = 0, 1, 2
@@ -227,17 +246,7 @@ class Context:
 
     # -- host buffers: NumPy uint8 in, NumPy uint8 out (H2D + kernel + D2H inside)
     def process_host(self, p, rgb, out=None):
-        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
-        if rgb.ndim == 3:
-            rgb = rgb[None]
-        ch = 3 if p.in_format == InFormat.RGB24 else 4
-        if rgb.shape[1:] != (p.height, p.width, ch):
-            raise IllegalArgumentException(-9, f"rgb must be [n,{p.height},{p.width},{ch}], got {rgb.shape}")
-        n = rgb.shape[0]
-        fb = out_shape(p)[3]
-        if out is None:
-            out = np.empty((n, fb), dtype=np.uint8)
-        assert out.dtype == np.uint8 and out.flags.c_contiguous and out.size == n * fb
+        rgb, n, out = _host_args(p, rgb, out)
         check(_ffi.lib().csic_process_host(self._h, ctypes.byref(p), rgb.ctypes.data, n, out.ctypes.data))
         return out
 
@@ -256,9 +265,12 @@ class Context:
     def process_host_band(self, p, rgb, out, out_row0, out_rows):
         """Whole frames in host arrays; computes output rows [out_row0, out_row0+out_rows) of every frame in place
         in `out` ([n, bytes_per_frame]); other rows of `out` are left untouched."""
-        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
-        n = rgb.shape[0]
-        assert out.dtype == np.uint8 and out.flags.c_contiguous and out.size == n * out_shape(p)[3]
+        if out is None:
+            raise IllegalArgumentException(-9, "process_host_band writes a band of an existing output array: out is required")
+        rgb, n, out = _host_args(p, rgb, out)
+        oh = out_shape(p)[1]
+        if not (0 <= int(out_row0) and 0 <= int(out_rows) and int(out_row0) + int(out_rows) <= oh):
+            raise IllegalArgumentException(-9, f"band [{out_row0}, {out_row0}+{out_rows}) is outside 0..{oh}")
         check(_ffi.lib().csic_process_host_band(self._h, ctypes.byref(p), rgb.ctypes.data, n, out.ctypes.data,
                                                 out_row0, out_rows))
         return out
@@ -266,11 +278,20 @@ class Context:
     # -- torch CUDA tensors (plumbing only: torch owns the memory and the stream)
     def process_torch(self, p, rgb, out=None, out_row0=None, out_rows=None):
         import torch
-        assert rgb.is_cuda and rgb.dtype == torch.uint8 and rgb.is_contiguous()
-        n = rgb.numel() // (p.height * p.width * (3 if p.in_format == InFormat.RGB24 else 4))
-        fb = out_shape(p)[3]
+        if not (rgb.is_cuda and rgb.dtype == torch.uint8 and rgb.is_contiguous()):
+            raise IllegalArgumentException(-9, "rgb must be a contiguous CUDA uint8 tensor")
+        frame = p.height * p.width * (3 if p.in_format == InFormat.RGB24 else 4)
+        if rgb.numel() % frame != 0:
+            raise IllegalArgumentException(-9, f"rgb holds {rgb.numel()} bytes, not a multiple of the {frame}-byte frame")
+        n = rgb.numel() // frame
+        _, oh, _, fb = out_shape(p)
         if out is None:
             out = torch.empty((n, fb), dtype=torch.uint8, device=rgb.device)
+        elif not (out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and out.numel() == n * fb
+                  and out.device == rgb.device):
+            raise IllegalArgumentException(-9, f"out must be a contiguous CUDA uint8 tensor of {n * fb} bytes on {rgb.device}")
+        if out_row0 is not None and not (0 <= int(out_row0) and 0 <= int(out_rows) and int(out_row0) + int(out_rows) <= oh):
+            raise IllegalArgumentException(-9, f"band [{out_row0}, {out_row0}+{out_rows}) is outside 0..{oh}")
         # torch's default stream has handle 0, which the C ABI reads as "the context's own stream":
         # name it explicitly as cudaStreamLegacy (0x1) so the launch is ordered with torch's work.
         stream = torch.cuda.current_stream(rgb.device).cuda_stream or 1
@@ -314,12 +335,6 @@ class MultiContext:
             pass
 
     def process_host(self, p, rgb, out=None):
-        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
-        if rgb.ndim == 3:
-            rgb = rgb[None]
-        n = rgb.shape[0]
-        fb = out_shape(p)[3]
-        if out is None:
-            out = np.empty((n, fb), dtype=np.uint8)
+        rgb, n, out = _host_args(p, rgb, out)
         check(_ffi.lib().csic_multi_process_host(self._h, ctypes.byref(p), rgb.ctypes.data, n, out.ctypes.data))
         return out

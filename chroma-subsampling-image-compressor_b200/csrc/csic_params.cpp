@@ -45,7 +45,8 @@ int csic_params_default(int32_t width, int32_t height, csic_params* out) {
   return csic_validate(out, nullptr, 0);
 }
 
-// ImageProcessor.scala:15-29 (params + requires), :42-62 (toYC -> chroma -> spatial, no quantiser).
+// ImageProcessor.scala:15-29 (params + requires, evaluated in the case class's order: width, height, factor,
+// divisibility, chromaParamA, chromaParamB), :42-62 (toYC -> chroma -> spatial, no quantiser).
 int csic_params_from_image_processor(int32_t width, int32_t height, int32_t factor, int32_t chroma_a,
                                      int32_t chroma_b, csic_params* out) {
   if (!out) return CSIC_EINVAL_ARG;
@@ -59,11 +60,12 @@ int csic_params_from_image_processor(int32_t width, int32_t height, int32_t fact
   out->op[0] = CSIC_STEP_CHROMA;
   out->op[1] = CSIC_STEP_SPATIAL;
   out->op[2] = CSIC_STEP_COLOR;   // 8/8/8 quantiser == identity; keeps op[] a permutation
-  int rc = csic_validate(out, nullptr, 0);
-  if (rc != CSIC_OK) return rc;
-  // ImageProcessor.scala:25 -- only ImageProcessorParams demands divisibility.
-  if (width % factor != 0 || height % factor != 0) return CSIC_EINVAL_DIVISIBLE;
-  return CSIC_OK;
+  if (width <= 0 || height <= 0) return CSIC_EINVAL_DIMS;                                     // :22-23
+  if (!(factor == 1 || factor == 2 || factor == 4 || factor == 8)) return CSIC_EINVAL_FACTOR;  // :24
+  if (width % factor != 0 || height % factor != 0) return CSIC_EINVAL_DIVISIBLE;               // :25 (only here)
+  if (!(chroma_a == 4 || chroma_a == 2 || chroma_a == 1)) return CSIC_EINVAL_CHROMA_A;         // :27
+  if (!(chroma_b == chroma_a || chroma_b == 0)) return CSIC_EINVAL_CHROMA_B;                   // :28
+  return csic_validate(out, nullptr, 0);
 }
 
 // Legacy enum surface (pinned by goldens G11-G13, G14-G22, G27).
@@ -90,12 +92,31 @@ int csic_params_from_legacy(int32_t width, int32_t height, int32_t chroma_mode, 
 
 int csic_validate(const csic_params* p, char* msg, size_t n) {
   if (!p) return fail(CSIC_EINVAL_ARG, msg, n, "params is NULL");
-  // SpatialDownsampler.scala:7 / ChromaSubsampler.scala:13-14 / ImageProcessor.scala:22-23
+  // The checks run in the order the reference's constructor evaluates its `require`s, so that a parameter set that
+  // is invalid in several ways reports the SAME first failure as `new ImageCompressorTop(...)`:
+  //   ImageCompressorTop.scala:27-31 (ops) -> :45 new SpatialDownsampler (SpatialDownsampler.scala:7-8: dims, factor)
+  //   -> :46-51 new ColorQuantizer (ColorQuantizer.scala:13-15: Y, Cb, Cr bits) -> :53-59 new ChromaSubsampler
+  //   (ChromaSubsampler.scala:13-18: dims again, param_a, param_b).
+  // ImageCompressorTop.scala:28-31
+  for (int i = 0; i < 3; ++i)
+    if (!is_step(p->op[i]))
+      return fail(CSIC_EINVAL_OPS, msg, n,
+                  "op" + std::to_string(i + 1) + "Type must be a valid reorderable operation.");
+  if (p->op[0] == p->op[1] || p->op[0] == p->op[2] || p->op[1] == p->op[2])
+    return fail(CSIC_EINVAL_OPS, msg, n, "op1, op2, and op3 types must be distinct and form a permutation.");
+  // SpatialDownsampler.scala:7 (ChromaSubsampler.scala:13-14 can no longer fire after it)
   if (p->width <= 0 || p->height <= 0)
     return fail(CSIC_EINVAL_DIMS, msg, n, "Width and height must be positive");
   // SpatialDownsampler.scala:8
   if (!(p->factor == 1 || p->factor == 2 || p->factor == 4 || p->factor == 8))
     return fail(CSIC_EINVAL_FACTOR, msg, n, "Factor must be 1, 2, 4, or 8");
+  // ColorQuantizer.scala:13-15 (originalBitWidth is fixed to 8 by the tops)
+  const int bits[3] = {p->y_bits, p->cb_bits, p->cr_bits};
+  const char* names[3] = {"Y", "Cb", "Cr"};
+  for (int i = 0; i < 3; ++i)
+    if (bits[i] < 1 || bits[i] > 8)
+      return fail(CSIC_EINVAL_QBITS, msg, n,
+                  std::string(names[i]) + " target bits must be between 1 and 8. Got " + std::to_string(bits[i]));
   // ChromaSubsampler.scala:17
   if (!(p->chroma_a == 4 || p->chroma_a == 2 || p->chroma_a == 1))
     return fail(CSIC_EINVAL_CHROMA_A, msg, n,
@@ -105,20 +126,7 @@ int csic_validate(const csic_params* p, char* msg, size_t n) {
     return fail(CSIC_EINVAL_CHROMA_B, msg, n,
                 "param_b must be equal to param_a (" + std::to_string(p->chroma_a) + ") or 0. Got " +
                     std::to_string(p->chroma_b));
-  // ColorQuantizer.scala:13-15 (originalBitWidth is fixed to 8 by the tops)
-  const int bits[3] = {p->y_bits, p->cb_bits, p->cr_bits};
-  const char* names[3] = {"Y", "Cb", "Cr"};
-  for (int i = 0; i < 3; ++i)
-    if (bits[i] < 1 || bits[i] > 8)
-      return fail(CSIC_EINVAL_QBITS, msg, n,
-                  std::string(names[i]) + " target bits must be between 1 and 8. Got " + std::to_string(bits[i]));
-  // ImageCompressorTop.scala:28-31
-  for (int i = 0; i < 3; ++i)
-    if (!is_step(p->op[i]))
-      return fail(CSIC_EINVAL_OPS, msg, n,
-                  "op" + std::to_string(i + 1) + "Type must be a valid reorderable operation.");
-  if (p->op[0] == p->op[1] || p->op[0] == p->op[2] || p->op[1] == p->op[2])
-    return fail(CSIC_EINVAL_OPS, msg, n, "op1, op2, and op3 types must be distinct and form a permutation.");
+  // ---- fields the reference does not have (extensions): checked last ----
   if (p->round_mode != CSIC_ROUND_FLOOR && p->round_mode != CSIC_ROUND_TRUNC)
     return fail(CSIC_EINVAL_MODE, msg, n, "round_mode must be 0 (FLOOR) or 1 (TRUNC)");
   if (p->pool_mode != CSIC_POOL_DECIMATE && p->pool_mode != CSIC_POOL_AVERAGE)

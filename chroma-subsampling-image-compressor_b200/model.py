@@ -108,9 +108,11 @@ class ImageProcessor:
     """class ImageProcessor(p) -- ImageProcessor.scala:31-63: toYC -> chroma -> spatial, no quantiser."""
 
     def __init__(self, p: ImageProcessorParams, out_format=OutFormat.YCC888, ctx=None):
+        from . import _ffi
         self.p = p
-        self.params = p._csic
+        self.params = _ffi.CsicParams.from_buffer_copy(p._csic)    # own copy: p is frozen and may be shared
         self.params.out_format = int(out_format)
+        api.validate(self.params)
         self._ctx = ctx
 
     def process(self, rgb):

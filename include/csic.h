@@ -124,7 +124,8 @@ CSIC_API int csic_params_default(int32_t width, int32_t height, csic_params* out
 
 /* `ImageProcessorParams(width,height,factor,chromaParamA,chromaParamB)` + `class ImageProcessor`
  * (ImageProcessor.scala:15-63): fixed order toYC -> chroma -> spatial, no quantiser (8/8/8), and the
- * extra divisibility requirement (:25). */
+ * extra divisibility requirement (:25); checks in the case class's order (:22-28: width, height, factor,
+ * divisibility, chromaParamA, chromaParamB). */
 CSIC_API int csic_params_from_image_processor(int32_t width, int32_t height, int32_t factor, int32_t chroma_a,
                                      int32_t chroma_b, csic_params* out);
 
@@ -135,8 +136,10 @@ CSIC_API int csic_params_from_legacy(int32_t width, int32_t height, int32_t chro
                             int32_t factor, csic_params* out);
 
 /* All `require(...)` predicates of ChromaSubsampler.scala:13-18, ColorQuantizer.scala:12-15,
- * SpatialDownsampler.scala:7-8, ImageCompressorTop.scala:27-31.  On failure writes the reference's
- * message text (NUL terminated, truncated to n) into msg when msg != NULL. */
+ * SpatialDownsampler.scala:7-8, ImageCompressorTop.scala:27-31, evaluated in the ORDER the Scala constructor
+ * evaluates them (ops :28-31 -> SpatialDownsampler :45 -> ColorQuantizer :46-51 -> ChromaSubsampler :53-59), so a
+ * parameter set that is invalid in several ways reports the same first failure as `new ImageCompressorTop(...)`.
+ * On failure writes the reference's message text (NUL terminated, truncated to n) into msg when msg != NULL. */
 CSIC_API int csic_validate(const csic_params* p, char* msg, size_t n);
 
 /* Output geometry.  out_w x out_h = ceil(W/f) x ceil(H/f): what the DUT emits

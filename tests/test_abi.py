@@ -63,6 +63,51 @@ def test_validation_messages_match_reference():
     assert msg_of(factor=2, width=10, height=7, pool_mode=csic.PoolMode.AVERAGE)[1] == -3
 
 
+def test_doubly_invalid_reports_the_constructors_first_failure():
+    """`new ImageCompressorTop(...)` evaluates its requires in the order ops (:28-31) -> SpatialDownsampler (:45;
+    dims, factor) -> ColorQuantizer (:46-51; Y, Cb, Cr) -> ChromaSubsampler (:53-59; a, b): a parameter set that breaks
+    several of them must raise the message of the FIRST one in that order (missing #6)."""
+    S = csic.ProcessingStep
+    bad_ops = (S.SpatialSampling, S.SpatialSampling, S.ChromaSubsampling)
+    assert msg_of(ops=bad_ops, width=0)[1] == -7                         # ops before dims
+    assert msg_of(ops=bad_ops, factor=3, a=3, y_bits=0)[1] == -7
+    assert "op1Type" in msg_of(ops=(S.NoOp, S.NoOp, S.NoOp), factor=5)[0]
+    assert msg_of(width=0, factor=3)[1] == -1                            # dims before factor
+    assert msg_of(factor=3, y_bits=0)[1] == -2                           # factor (spatial) before quantiser
+    assert msg_of(factor=3, a=3)[1] == -2                                # factor before chroma
+    assert msg_of(y_bits=0, a=3)[1] == -6                                # quantiser before chroma (was the other way round)
+    assert msg_of(cb_bits=9, a=2, b=1)[1] == -6
+    assert msg_of(y_bits=0, cb_bits=0)[0].endswith("Y target bits must be between 1 and 8. Got 0")
+    assert msg_of(cb_bits=0, cr_bits=0)[0].startswith("requirement failed: Cb target bits")
+    assert msg_of(a=3, b=1)[1] == -4                                     # param_a before param_b
+    assert msg_of(a=3, out_format=9)[1] == -4                            # extension fields last
+    assert msg_of(out_format=9)[1] == -8
+
+
+def test_image_processor_params_doubly_invalid_order():
+    """case class ImageProcessorParams (ImageProcessor.scala:22-28): width, height, factor, divisibility, chromaParamA,
+    chromaParamB -- divisibility is checked BEFORE the chroma parameters."""
+    P = csic.ImageProcessorParams
+    for kw, text in (((0, 0, 3, 3, 1), "width must be positive"), ((16, 0, 3, 3, 1), "height must be positive"),
+                     ((10, 16, 3, 3, 1), "factor must be 1, 2, 4, or 8"),
+                     ((10, 16, 4, 3, 1), "Image dimensions must be divisible by spatial downsampling factor."),
+                     ((16, 16, 4, 3, 1), "chromaParamA must be 4, 2, or 1. Got 3")):
+        with pytest.raises(csic.IllegalArgumentException) as e:
+            P(*kw)
+        assert text in str(e.value), (kw, str(e.value))
+
+
+def test_image_processors_do_not_share_a_params_struct():
+    """Two ImageProcessors built from one frozen ImageProcessorParams keep their own out_format."""
+    pp = csic.ImageProcessorParams(16, 16, 2, 2, 0)
+    a = csic.ImageProcessor(pp, out_format=csic.OutFormat.YCC888)
+    b = csic.ImageProcessor(pp, out_format=csic.OutFormat.RGB888)
+    assert a.params.out_format == csic.OutFormat.YCC888 and b.params.out_format == csic.OutFormat.RGB888
+    assert pp._csic.out_format == csic.OutFormat.YCC888
+    with pytest.raises(csic.IllegalArgumentException):
+        csic.ImageProcessor(pp, out_format=9)
+
+
 def test_all_legal_surface_accepted():
     for a, b in ALL_AB:
         for f in (1, 2, 4, 8):
