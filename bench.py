@@ -458,24 +458,68 @@ def e2e_run(env, ctx, p, rgb, out, W, H, ipb, out_fb, frames, steps):
            "per_rank_s_per_step": [round(r[0] / e2e_steps, 4) for r in per_rank],
            "link_gbs": {"h2d": round(h2d * env.world * e2e_steps / dt_max / 1e9, 2),
                         "d2h": round(d2h * env.world * e2e_steps / dt_max / 1e9, 2)}}
-    ceil = load_link_ceiling(env.world)
+    # the ceiling of this figure, measured live on this box in this run: the SAME bytes between the SAME buffers as raw
+    # cudaMemcpy calls (no kernel, no library of ours), all ranks at once
+    ceil = link_probe(env, pin_in.array.ctypes.data, pin_out.array.ctypes.data, rgb.data_ptr(), out.data_ptr(),
+                      hb, H, W, ipb, p.factor if (p.pool_mode == 0 and p.factor > 1 and H % p.factor == 0) else 1, out_fb, calls)
+    if ceil is None:
+        ceil = load_link_ceiling(env.world)
     if ceil:
-        both = ceil["h2d_gbs"] + ceil["d2h_gbs"]
         e2e["link_ceiling_gbs"] = ceil
-        e2e["frac_of_ceiling"] = round((e2e["link_gbs"]["h2d"] + e2e["link_gbs"]["d2h"]) / both, 3)
+        e2e["frac_of_ceiling"] = round((e2e["link_gbs"]["h2d"] + e2e["link_gbs"]["d2h"]) / (ceil["h2d_gbs"] + ceil["d2h_gbs"]), 3)
     pin_in.free(); pin_out.free()
     return e2e
 
 
-def load_link_ceiling(world):
-    """Measured host<->device link ceiling with `world` GPUs copying at once (tools/pcie_ceiling.py, kind duplex_2d:
-    the H2D/D2H byte mix of the default workload), from profiles/r2/pcie_ceiling.json."""
+def link_probe(env, h_in, h_out, d_in, d_out, frames, H, W, ipb, f, out_fb, calls):
+    """Host<->device link ceiling for exactly the traffic of one e2e step: `calls` x (H2D of the rows the pipeline
+    reads of `frames` frames || D2H of their results), as raw cudaMemcpy2DAsync / cudaMemcpyAsync between the same
+    pinned and device buffers on two streams, every rank at the same time; aggregate GB/s = bytes of all ranks /
+    max over ranks of the elapsed time.  cuda-python's runtime bindings issue the copies (plumbing, not product)."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r2", "pcie_ceiling.json")))
-        c = d["concurrent"][str(world)]
-        return {"h2d_gbs": c["h2d_gbs"], "d2h_gbs": c["d2h_gbs"], "source": d.get("source", "profiles/r2/pcie_ceiling.json"),
-                "what": c.get("what", "cudaMemcpy2DAsync H2D || cudaMemcpyAsync D2H on all GPUs at once, pinned memory")}
+        from cuda.bindings import runtime as rt
     except Exception:
+        return None
+
+    def ck(res):
+        if int(res[0]) != 0:
+            raise RuntimeError(f"CUDA error {res[0]} in link_probe")
+        return res[1] if len(res) > 1 else None
+    try:
+        s1 = ck(rt.cudaStreamCreateWithFlags(rt.cudaStreamNonBlocking))
+        s2 = ck(rt.cudaStreamCreateWithFlags(rt.cudaStreamNonBlocking))
+        H2D, D2H = rt.cudaMemcpyKind.cudaMemcpyHostToDevice, rt.cudaMemcpyKind.cudaMemcpyDeviceToHost
+        row = W * ipb
+        rows = frames * (H // f)
+
+        def one():
+            if f > 1:
+                ck(rt.cudaMemcpy2DAsync(d_in, row, h_in, f * row, row, rows, H2D, s1))
+            else:
+                ck(rt.cudaMemcpyAsync(d_in, h_in, rows * row, H2D, s1))
+            ck(rt.cudaMemcpyAsync(h_out, d_out, frames * out_fb, D2H, s2))
+
+        def sync():
+            ck(rt.cudaStreamSynchronize(s1)); ck(rt.cudaStreamSynchronize(s2))
+        one(); sync()
+        best = None
+        for _ in range(2):
+            env.barrier()
+            t0 = time.perf_counter()
+            for _ in range(calls):
+                one()
+            sync()
+            env.barrier()
+            dt = env.max_over_ranks(time.perf_counter() - t0)
+            best = dt if best is None else min(best, dt)
+        ck(rt.cudaStreamDestroy(s1)); ck(rt.cudaStreamDestroy(s2))
+        up, dn = rows * row * calls * env.world, frames * out_fb * calls * env.world
+        return {"h2d_gbs": round(up / best / 1e9, 2), "d2h_gbs": round(dn / best / 1e9, 2),
+                "how": f"live: raw cudaMemcpy{'2D' if f > 1 else ''}Async H2D || cudaMemcpyAsync D2H of the same bytes between the same "
+                       f"pinned/device buffers, {env.world} GPU(s) at once, best of 2 passes, no kernel",
+                "see_also": "profiles/r2/pcie_ceiling.json (every subset of GPUs, every direction)"}
+    except Exception as e:  # noqa: BLE001
+        print(f"link_probe failed: {e}", file=sys.stderr)
         return None
 
 

@@ -51,6 +51,8 @@ PROTOTYPES = {
     "csic_multi_destroy": (_int, [_vp]),
     "csic_multi_size": (_int, [_vp]),
     "csic_multi_process_host": (_int, [_vp, _PP, _vp, _sz, _vp]),
+    "csic_multi_set_option": (_int, [_vp, _int, _i64]),
+    "csic_multi_host_bytes": (_int, [_vp, ctypes.POINTER(ctypes.c_uint64), _int]),
     "csic_host_alloc": (_int, [_sz, ctypes.POINTER(_vp)]),
     "csic_host_free": (_int, [_vp]),
     "csic_synchronize": (_int, [_vp]),

@@ -334,6 +334,18 @@ class MultiContext:
         except Exception:
             pass
 
+    STATIC_SPLIT = 100
+
+    def set_option(self, option, value):
+        check(_ffi.lib().csic_multi_set_option(self._h, int(option), int(value)))
+
+    def host_bytes(self):
+        """Bytes each device has received host -> device so far (shows how the shared cursor divided the batches)."""
+        n = len(self)
+        arr = (ctypes.c_uint64 * n)()
+        check(_ffi.lib().csic_multi_host_bytes(self._h, arr, n))
+        return list(arr)
+
     def process_host(self, p, rgb, out=None):
         rgb, n, out = _host_args(p, rgb, out)
         check(_ffi.lib().csic_multi_process_host(self._h, ctypes.byref(p), rgb.ctypes.data, n, out.ctypes.data))

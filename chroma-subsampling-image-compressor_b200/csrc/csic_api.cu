@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -31,6 +32,24 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 constexpr int kPipe = 3;   // chunks in flight in csic_process_host
 
+// No C++ exception may cross the C ABI (the caller is a JVM, Python or C): std::thread / std::vector / std::string can
+// throw system_error or bad_alloc inside the host pipeline.
+template <typename F>
+int guarded(const char* where, F&& body) {
+  try {
+    return body();
+  } catch (const std::bad_alloc&) {
+    g_last_error = std::string(where) + ": out of host memory";
+    return CSIC_ENOMEM;
+  } catch (const std::exception& e) {
+    g_last_error = std::string(where) + ": " + e.what();
+    return CSIC_ECUDA;
+  } catch (...) {
+    g_last_error = std::string(where) + ": unknown C++ exception";
+    return CSIC_ECUDA;
+  }
+}
+
 }  // namespace
 
 struct csic_ctx {
@@ -42,7 +61,7 @@ struct csic_ctx {
   void* d_in[kPipe] = {nullptr, nullptr, nullptr};
   void* d_out[kPipe] = {nullptr, nullptr, nullptr};
   size_t d_in_cap = 0, d_out_cap = 0;
-  cudaEvent_t ev_h2d[kPipe], ev_k[kPipe], ev_d2h[kPipe];
+  cudaEvent_t ev_h2d[kPipe] = {}, ev_k[kPipe] = {}, ev_d2h[kPipe] = {};
   void* h_in[kPipe] = {nullptr, nullptr, nullptr};    // pinned bounce buffers for pageable callers
   void* h_out[kPipe] = {nullptr, nullptr, nullptr};
   size_t h_in_cap = 0, h_out_cap = 0;
@@ -255,18 +274,25 @@ int csic_create(int device, csic_ctx** out) {
   }
   c->sm_count = prop.multiProcessorCount;
   c->max_smem_optin = prop.sharedMemPerBlockOptin;
-  bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
-  for (int i = 0; ok && i < kPipe; ++i)
-    ok = cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
-         cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming) == cudaSuccess &&
-         cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming) == cudaSuccess;
-  if (ok) ok = csic::rows_kernel_set_attributes(c->max_smem_optin) == (int)cudaSuccess;
-  if (!ok) {
-    int rc = cuda_fail(cudaGetLastError(), "csic_create");
-    delete c;
-    return rc == CSIC_OK ? CSIC_ECUDA : rc;
+  // keep the FIRST failing call's own error code (cudaGetLastError may already read cudaSuccess again), and tear down
+  // whatever was created before it
+  cudaError_t err = cudaSuccess;
+  auto step = [&](cudaError_t r) { if (err == cudaSuccess) err = r; return err == cudaSuccess; };
+  step(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) &&
+      step(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking)) &&
+      step(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+  for (int i = 0; err == cudaSuccess && i < kPipe; ++i)
+    step(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming)) &&
+        step(cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming)) &&
+        step(cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming));
+  if (err == cudaSuccess) step((cudaError_t)csic::rows_kernel_set_attributes(c->max_smem_optin));
+  if (err != cudaSuccess) {
+    const int rc = cuda_fail(err, "csic_create");
+    const std::string keep = g_last_error;
+    cudaGetLastError();
+    csic_destroy(c);
+    g_last_error = keep;
+    return rc;
   }
   *out = c;
   return CSIC_OK;
@@ -275,21 +301,19 @@ int csic_create(int device, csic_ctx** out) {
 int csic_destroy(csic_ctx* ctx) {
   if (!ctx) return CSIC_OK;
   DeviceGuard guard(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
-  cudaStreamSynchronize(ctx->s_h2d);
-  cudaStreamSynchronize(ctx->s_d2h);
+  for (cudaStream_t st : {ctx->stream, ctx->s_h2d, ctx->s_d2h})
+    if (st) cudaStreamSynchronize(st);
   for (int i = 0; i < kPipe; ++i) {
     if (ctx->d_in[i]) cudaFree(ctx->d_in[i]);
     if (ctx->d_out[i]) cudaFree(ctx->d_out[i]);
     if (ctx->h_in[i]) cudaFreeHost(ctx->h_in[i]);
     if (ctx->h_out[i]) cudaFreeHost(ctx->h_out[i]);
-    cudaEventDestroy(ctx->ev_h2d[i]);
-    cudaEventDestroy(ctx->ev_k[i]);
-    cudaEventDestroy(ctx->ev_d2h[i]);
+    if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
+    if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
+    if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]);
   }
-  cudaStreamDestroy(ctx->stream);
-  cudaStreamDestroy(ctx->s_h2d);
-  cudaStreamDestroy(ctx->s_d2h);
+  for (cudaStream_t st : {ctx->stream, ctx->s_h2d, ctx->s_d2h})
+    if (st) cudaStreamDestroy(st);
   delete ctx;
   return CSIC_OK;
 }
@@ -480,8 +504,15 @@ void parallel_rows_copy(uint8_t* dst, size_t dst_step, const uint8_t* src, size_
 // row band).  Frames are cut into chunks that flow through a kPipe-deep ring of device buffers on three streams.
 // Only what the band needs crosses PCIe: its input rows (every f-th one under DECIMATE) and its output rows; the
 // device buffers hold just those rows and the kernel is handed *virtual* frame bases (buffer - first_row * pitch).
+// `share` (optional): a cursor several contexts (GPUs) pull their chunks from, so that a batch is divided by how fast
+// each GPU's host link turns out to be (csic_multi_process_host) instead of evenly.
+struct ChunkShare {
+  std::atomic<size_t> next{0};
+  size_t gpus = 1;
+};
+
 static int host_pipeline_run(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, size_t n_frames, uint8_t* out,
-                             int32_t row0, int32_t rows) {
+                             int32_t row0, int32_t rows, ChunkShare* share) {
   const csic::Geometry g = csic::geometry(*p);
   DeviceGuard guard(ctx->device);
   const bool band = !(row0 == 0 && rows == g.out_h);
@@ -535,10 +566,21 @@ static int host_pipeline_run(csic_ctx* ctx, const csic_params* p, const uint8_t*
   // Frames per chunk: ~opt_chunk_bytes of input, at least one frame, at most what is there.
   size_t per = std::max<size_t>(1, ctx->opt_chunk_bytes / std::max<size_t>(1, dev_frame_bytes));
   per = std::min(per, n_frames);
+  if (share) per = std::min(per, std::max<size_t>(1, n_frames / (share->gpus * (size_t)kPipe)));   // several chunks per GPU
   int rc = ensure_staging(ctx, per * dev_frame_bytes, per * dev_out_frame_bytes);
   if (rc != CSIC_OK) return rc;
 
-  const size_t n_chunks = (n_frames + per - 1) / per;
+  // The chunks this context processes, in order: consecutive ones when it owns the whole batch, otherwise whatever
+  // it pulls from the shared cursor (all contexts use the same `per`: same parameters, same chunk-size option).
+  std::vector<std::pair<size_t, size_t>> mine;   // (first frame, frames)
+  mine.reserve((n_frames + per - 1) / per + 1);  // never reallocates: the drain thread reads entries while this one appends
+  auto next_chunk = [&]() -> bool {
+    const size_t f0 = share ? share->next.fetch_add(per, std::memory_order_relaxed) : mine.size() * per;
+    if (f0 >= n_frames) return false;
+    mine.emplace_back(f0, std::min(per, n_frames - f0));
+    return true;
+  };
+  const size_t n_chunks = share ? (size_t)-1 : (n_frames + per - 1) / per;
   // Pageable caller buffers (a JVM heap, malloc): cudaMemcpyAsync would fall back to the driver's synchronous,
   // single-threaded staging (measured 5 k MP/s vs 31 k MP/s pinned on cfg4).  Gather the needed rows into pinned
   // bounce buffers on several host threads instead, overlapped with the DMA of the neighbouring chunks.
@@ -551,7 +593,7 @@ static int host_pipeline_run(csic_ctx* ctx, const csic_params* p, const uint8_t*
   // scatters chunk j's result from its bounce buffer to the caller once its D2H has landed
   auto drain = [&](size_t j) -> int {
     const int bj = (int)(j % kPipe);
-    const size_t jf0 = j * per, jnf = std::min(per, n_frames - jf0);
+    const size_t jf0 = mine[j].first, jnf = mine[j].second;
     CSIC_CUDA(cudaEventSynchronize(ctx->ev_d2h[bj]));
     const uint8_t* hb = static_cast<const uint8_t*>(ctx->h_out[bj]);
     if (band) {
@@ -582,7 +624,7 @@ static int host_pipeline_run(csic_ctx* ctx, const csic_params* p, const uint8_t*
   auto start_drain = [&](size_t j) {
     adrain.th = std::thread([&adrain, &drain, device, j] {
       cudaSetDevice(device);
-      adrain.rc = drain(j);
+      adrain.rc = guarded("csic_process_host drain", [&] { return drain(j); });
       if (adrain.rc != CSIC_OK) adrain.err = g_last_error;
     });
   };
@@ -590,9 +632,9 @@ static int host_pipeline_run(csic_ctx* ctx, const csic_params* p, const uint8_t*
   // stream and synchronise once -- no cross-stream events on the latency path.
   const bool single = n_chunks == 1 && !bounce;
   cudaStream_t s_in = single ? ctx->stream : ctx->s_h2d, s_out = single ? ctx->stream : ctx->s_d2h;
-  for (size_t c = 0; c < n_chunks; ++c) {
+  for (size_t c = 0; next_chunk(); ++c) {
     const int b = (int)(c % kPipe);
-    const size_t f0 = c * per, nf = std::min(per, n_frames - f0);
+    const size_t f0 = mine[c].first, nf = mine[c].second;
     if (c >= (size_t)kPipe) {
       // buffer reuse: the kernel that read d_in[b] and the copy that drained d_out[b] must be done
       CSIC_CUDA(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_k[b], 0));
@@ -671,7 +713,8 @@ static int host_pipeline_run(csic_ctx* ctx, const csic_params* p, const uint8_t*
   if (bounce) {
     rc = adrain.join();
     if (rc != CSIC_OK) return rc;
-    for (size_t j = n_chunks >= (size_t)kPipe ? n_chunks - ((size_t)kPipe - 1) : 0; j < n_chunks; ++j) {
+    const size_t n_mine = mine.size();
+    for (size_t j = n_mine >= (size_t)kPipe ? n_mine - ((size_t)kPipe - 1) : 0; j < n_mine; ++j) {
       rc = drain(j);
       if (rc != CSIC_OK) return rc;
     }
@@ -689,8 +732,8 @@ static int host_pipeline_run(csic_ctx* ctx, const csic_params* p, const uint8_t*
 // An error in the middle of the pipeline must not leave copies in flight on the caller's buffers or on the staging
 // ring: drain the three streams before reporting it.
 static int host_pipeline(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, size_t n_frames, uint8_t* out,
-                         int32_t row0, int32_t rows) {
-  const int rc = host_pipeline_run(ctx, p, rgb, n_frames, out, row0, rows);
+                         int32_t row0, int32_t rows, ChunkShare* share = nullptr) {
+  const int rc = host_pipeline_run(ctx, p, rgb, n_frames, out, row0, rows, share);
   if (rc != CSIC_OK) {
     const std::string keep = g_last_error;
     DeviceGuard guard(ctx->device);
@@ -709,7 +752,7 @@ int csic_process_host(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, s
   if (rc != CSIC_OK) return rc;
   if (n_frames == 0) return CSIC_OK;
   if (!rgb || !out) return CSIC_EINVAL_ARG;
-  return host_pipeline(ctx, p, rgb, n_frames, out, 0, csic::geometry(*p).out_h);
+  return guarded("csic_process_host", [&] { return host_pipeline(ctx, p, rgb, n_frames, out, 0, csic::geometry(*p).out_h); });
 }
 
 int csic_process_host_band(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, size_t n_frames, uint8_t* out,
@@ -720,7 +763,7 @@ int csic_process_host_band(csic_ctx* ctx, const csic_params* p, const uint8_t* r
   if (n_frames == 0 || out_rows == 0) return CSIC_OK;
   if (!rgb || !out) return CSIC_EINVAL_ARG;
   if (out_row0 < 0 || out_rows < 0 || out_row0 + out_rows > csic::geometry(*p).out_h) return CSIC_EINVAL_ARG;
-  return host_pipeline(ctx, p, rgb, n_frames, out, out_row0, out_rows);
+  return guarded("csic_process_host_band", [&] { return host_pipeline(ctx, p, rgb, n_frames, out, out_row0, out_rows); });
 }
 
 // ---- one process, several GPUs ------------------------------------------------------------------
@@ -729,6 +772,7 @@ int csic_process_host_band(csic_ctx* ctx, const csic_params* p, const uint8_t* r
 // aligned row bands (E2).  No data moves between GPUs.
 struct csic_multi {
   std::vector<csic_ctx*> ctx;
+  bool static_split = false;
 };
 
 int csic_multi_create(const int* devices, int n_devices, csic_multi** out) {
@@ -762,7 +806,26 @@ int csic_multi_destroy(csic_multi* m) {
 
 int csic_multi_size(const csic_multi* m) { return m ? (int)m->ctx.size() : CSIC_EINVAL_ARG; }
 
-int csic_multi_process_host(csic_multi* m, const csic_params* p, const uint8_t* rgb, size_t n_frames, uint8_t* out) {
+int csic_multi_set_option(csic_multi* m, int option, int64_t value) {
+  if (!m) return CSIC_EINVAL_ARG;
+  if (option == CSIC_OPT_MULTI_STATIC_SPLIT) {
+    m->static_split = value != 0;
+    return CSIC_OK;
+  }
+  for (csic_ctx* c : m->ctx) {
+    const int rc = csic_set_option(c, option, value);
+    if (rc != CSIC_OK) return rc;
+  }
+  return CSIC_OK;
+}
+
+int csic_multi_host_bytes(const csic_multi* m, uint64_t* h2d_per_device, int n) {
+  if (!m || !h2d_per_device || n < (int)m->ctx.size()) return CSIC_EINVAL_ARG;
+  for (size_t i = 0; i < m->ctx.size(); ++i) h2d_per_device[i] = m->ctx[i]->h2d_bytes;
+  return CSIC_OK;
+}
+
+static int multi_process_host_impl(csic_multi* m, const csic_params* p, const uint8_t* rgb, size_t n_frames, uint8_t* out) {
   if (!m || !p) return CSIC_EINVAL_ARG;
   int rc = csic_validate(p, nullptr, 0);
   if (rc != CSIC_OK) return rc;
@@ -772,13 +835,28 @@ int csic_multi_process_host(csic_multi* m, const csic_params* p, const uint8_t* 
   const size_t G = m->ctx.size();
   std::vector<int> rcs(G, CSIC_OK);
   std::vector<std::string> errs(G);
-  std::vector<std::thread> th;
+  struct Joiner {   // an exception while spawning must not leave joinable threads behind (std::terminate)
+    std::vector<std::thread> v;
+    ~Joiner() { for (std::thread& t : v) if (t.joinable()) t.join(); }
+  } joiner;
+  std::vector<std::thread>& th = joiner.v;
+  ChunkShare share;
+  share.gpus = G;
   if (n_frames >= G || p->out_format == CSIC_OUT_PLANAR) {
+    // Frames are independent: every GPU's pipeline pulls its next chunk of frames from one shared cursor, so the batch
+    // divides itself by what each GPU's host link delivers (on the 8-GPU boxes of this pool four of the links are
+    // 1.4x slower than the other four when all run at once: profiles/r2/pcie_ceiling.json) instead of evenly.
+    const int32_t out_h = g.out_h;
     for (size_t i = 0; i < G; ++i) {
       const size_t lo = n_frames * i / G, hi = n_frames * (i + 1) / G;
-      if (hi == lo) continue;
-      th.emplace_back([=, &rcs, &errs] {
-        rcs[i] = csic_process_host(m->ctx[i], p, rgb + lo * g.in_frame_bytes, hi - lo, out + lo * g.out_frame_bytes);
+      if (m->static_split && hi == lo) continue;
+      th.emplace_back([=, &rcs, &errs, &share] {
+        cudaSetDevice(m->ctx[i]->device);   // this thread's device from the start: no context is made on device 0
+        rcs[i] = guarded("csic_multi_process_host worker", [&] {
+          return m->static_split   // the even split of round 1, kept for comparison (CSIC_OPT_MULTI_STATIC_SPLIT)
+                     ? host_pipeline(m->ctx[i], p, rgb + lo * g.in_frame_bytes, hi - lo, out + lo * g.out_frame_bytes, 0, out_h)
+                     : host_pipeline(m->ctx[i], p, rgb, n_frames, out, 0, out_h, &share);
+        });
         if (rcs[i] != CSIC_OK) errs[i] = g_last_error;
       });
     }
@@ -791,7 +869,8 @@ int csic_multi_process_host(csic_multi* m, const csic_params* p, const uint8_t* 
       const int r0 = std::min(g.out_h, (int)(units * i / G) * unit), r1 = std::min(g.out_h, (int)(units * (i + 1) / G) * unit);
       if (r1 <= r0) continue;
       th.emplace_back([=, &rcs, &errs] {
-        rcs[i] = csic_process_host_band(m->ctx[i], p, rgb, n_frames, out, r0, r1 - r0);
+        cudaSetDevice(m->ctx[i]->device);
+        rcs[i] = csic_process_host_band(m->ctx[i], p, rgb, n_frames, out, r0, r1 - r0);   // guarded inside
         if (rcs[i] != CSIC_OK) errs[i] = g_last_error;
       });
     }
@@ -803,6 +882,10 @@ int csic_multi_process_host(csic_multi* m, const csic_params* p, const uint8_t* 
       return rcs[i];
     }
   return CSIC_OK;
+}
+
+int csic_multi_process_host(csic_multi* m, const csic_params* p, const uint8_t* rgb, size_t n_frames, uint8_t* out) {
+  return guarded("csic_multi_process_host", [&] { return multi_process_host_impl(m, p, rgb, n_frames, out); });
 }
 
 int csic_host_alloc(size_t bytes, void** out) {

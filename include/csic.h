@@ -220,16 +220,21 @@ CSIC_API int csic_process_host(csic_ctx* ctx, const csic_params* p, const uint8_
 CSIC_API int csic_process_host_band(csic_ctx* ctx, const csic_params* p, const uint8_t* rgb, size_t n_frames,
                                     uint8_t* out, int32_t out_row0, int32_t out_rows);
 
-/* One host process, several GPUs (the reference's host is a single JVM process): one context and one host thread
- * per device.  devices == NULL or n_devices <= 0 -> every visible GPU.  csic_multi_process_host splits the batch
- * by frames, or -- with fewer frames than GPUs -- cuts every frame into aligned row bands; no collective, no
- * peer traffic. */
+/* One host process, several GPUs (the reference's host is a single JVM process -- ImageCompressorTopApp.scala:149-190
+ * drives one DUT from one `main`): one context and one host thread per device.  devices == NULL or n_devices <= 0 ->
+ * every visible GPU.  csic_multi_process_host divides the batch by frames -- every GPU's chunk pipeline pulls its next
+ * chunk from one shared cursor, so GPUs behind faster host links take more of the batch -- or, with fewer frames than
+ * GPUs, cuts every frame into aligned row bands; no collective, no peer traffic.
+ * csic_multi_set_option applies a csic_option to every context; CSIC_OPT_MULTI_STATIC_SPLIT = 1 restores the even
+ * frame split.  csic_multi_host_bytes reports the bytes each device has received so far (n >= csic_multi_size). */
 typedef struct csic_multi csic_multi;
 CSIC_API int csic_multi_create(const int* devices, int n_devices, csic_multi** out);
 CSIC_API int csic_multi_destroy(csic_multi* m);
 CSIC_API int csic_multi_size(const csic_multi* m);
 CSIC_API int csic_multi_process_host(csic_multi* m, const csic_params* p, const uint8_t* rgb, size_t n_frames,
                                      uint8_t* out);
+CSIC_API int csic_multi_set_option(csic_multi* m, int option, int64_t value);
+CSIC_API int csic_multi_host_bytes(const csic_multi* m, uint64_t* h2d_per_device, int n);
 
 /* Pinned host memory helpers for callers that want the fast H2D/D2H path. */
 CSIC_API int csic_host_alloc(size_t bytes, void** out);
@@ -246,7 +251,8 @@ CSIC_API int csic_synchronize(csic_ctx* ctx);
  * DECIMATE pipeline reads only every f-th row (default 0: ship only the rows that are read); HOST_NO_BOUNCE: 1 =
  * do not stage pageable caller buffers through the context's pinned bounce buffers; BLOCK_THREADS: threads per CTA of the row kernel (multiple of 32, <= 512). */
 enum csic_option { CSIC_OPT_KERNEL_FAMILY = 0, CSIC_OPT_HOST_CHUNK_BYTES = 1, CSIC_OPT_GRID_CTAS_PER_SM = 2,
-                   CSIC_OPT_STAGES = 3, CSIC_OPT_TILE_BYTES = 4, CSIC_OPT_BLOCK_THREADS = 5, CSIC_OPT_HOST_FULL_FRAMES = 6, CSIC_OPT_HOST_NO_BOUNCE = 7 };
+                   CSIC_OPT_STAGES = 3, CSIC_OPT_TILE_BYTES = 4, CSIC_OPT_BLOCK_THREADS = 5, CSIC_OPT_HOST_FULL_FRAMES = 6, CSIC_OPT_HOST_NO_BOUNCE = 7,
+                   CSIC_OPT_MULTI_STATIC_SPLIT = 100 /* csic_multi_set_option only */ };
 CSIC_API int csic_set_option(csic_ctx* ctx, int option, int64_t value);
 
 /* Diagnostics: total bytes csic_process_host has copied host -> device on this context. */

@@ -49,6 +49,8 @@ def lib():
         ip = ctypes.POINTER(ctypes.c_int)
         L.csic_oracle_rgb2ycbcr.argtypes = [ctypes.c_int] * 4 + [ip] * 3
         L.csic_oracle_ycbcr2rgb.argtypes = [ctypes.c_int] * 3 + [ip] * 3
+        L.csic_oracle_ycbcr2rgb_array.argtypes = [u8p, ctypes.c_size_t, u8p]
+        L.csic_oracle_ycbcr2rgb_array.restype = None
         L.csic_oracle_quant.argtypes = [ctypes.c_int, ctypes.c_int]
         L.csic_oracle_quant.restype = ctypes.c_int
         for fn in (L.csic_oracle_chroma_stream, L.csic_oracle_spatial_stream, L.csic_oracle_quant_stream):
@@ -102,6 +104,15 @@ def ycbcr2rgb(y, cb, cr):
     r, g, b = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
     lib().csic_oracle_ycbcr2rgb(y, cb, cr, ctypes.byref(r), ctypes.byref(g), ctypes.byref(b))
     return r.value, g.value, b.value
+
+
+def ycbcr2rgb_array(ycc):
+    """uint8 [..., 3] (Y,Cb,Cr) -> uint8 [..., 3] (R,G,B): csic_oracle_ycbcr2rgb applied to every triple."""
+    ycc = np.ascontiguousarray(ycc, dtype=np.uint8)
+    assert ycc.shape[-1] == 3
+    out = np.empty_like(ycc)
+    lib().csic_oracle_ycbcr2rgb_array(ycc.ctypes.data, ycc.size // 3, out.ctypes.data)
+    return out
 
 
 def quant(v, bits):

@@ -64,6 +64,17 @@ void csic_oracle_ycbcr2rgb(int y, int cb, int cr, int* r, int* g, int* b) {
   *b = clamp255(asr8(298 * c + 516 * d + 128));
 }
 
+/* The same function over an array of n interleaved (Y,Cb,Cr) byte triples -> (R,G,B) byte triples: lets a test walk
+ * the whole 2^24 YCbCr cube (the clamps of YCbCr2RGB.scala:17-26 fire on a large part of it, most of which no RGB
+ * input ever reaches through the forward transform). */
+void csic_oracle_ycbcr2rgb_array(const uint8_t* ycc, size_t n, uint8_t* rgb) {
+  for (size_t i = 0; i < n; ++i) {
+    int r, g, b;
+    csic_oracle_ycbcr2rgb(ycc[3 * i], ycc[3 * i + 1], ycc[3 * i + 2], &r, &g, &b);
+    rgb[3 * i] = (uint8_t)r; rgb[3 * i + 1] = (uint8_t)g; rgb[3 * i + 2] = (uint8_t)b;
+  }
+}
+
 /* ColorQuantizer.scala:29-31 (shift = 8 - targetBits), :42-44 ((v >> s) << s). */
 int csic_oracle_quant(int v, int target_bits) {
   int s = 8 - target_bits;
