@@ -72,6 +72,24 @@ WORKLOADS = {
                 "cfg3 with a width no 16-byte rule fits (1918x1078, dense): the any-alignment flex kernel"),
     "cfg4odd": (3838, 2158, 256, 2, 0, (8, 8, 8), 2, "CSQ", 3,
                 "cfg4 with odd dimensions (3838x2158 x256, dense): the any-alignment flex kernel"),
+    "hd_rgb": (1920, 1080, 512, 2, 0, (6, 5, 5), 1, "CSQ", 1,
+               "1080p x512, 4:2:0, f=1, Q_16BIT, fused RGB888 reconstruction (every byte converted: issue-bound case)"),
+    "hd_b128": (1920, 1080, 512, 2, 0, (8, 8, 8), 1, "CSQ", 3,
+                "1080p x512, 4:2:0, f=1, 8/8/8, BUNDLE128 (3 B/px in, 4 B/px out)"),
+    "hd_f2rgb": (1920, 1080, 512, 2, 0, (6, 5, 5), 2, "CSQ", 1,
+                 "1080p x512, 4:2:0 + f=2, Q_16BIT, RGB888"),
+    "wxga_rgb": (1366, 768, 1024, 2, 0, (6, 5, 5), 1, "CSQ", 1,
+                 "1366x768 x1024 dense (no 16-byte rule fits), 4:2:0, f=1, RGB888: flex kernel"),
+    "wxga_f2": (1366, 768, 1024, 2, 0, (8, 8, 8), 2, "CSQ", 0,
+                "1366x768 x1024 dense, 4:2:0 + f=2, YCC888: flex kernel"),
+    "port_f1": (1080, 1920, 512, 2, 0, (8, 8, 8), 1, "CSQ", 0,
+                "1080x1920 portrait x512 dense (3240-byte rows), 4:2:0, f=1, YCC888: flex kernel"),
+    "sq200_f4": (200, 200, 32768, 2, 0, (8, 8, 8), 4, "CSQ", 0,
+                 "200x200 x32768, 4:2:0 + f=4, YCC888 (tiny odd frames)"),
+    "sq96_f8": (96, 96, 131072, 2, 0, (8, 8, 8), 8, "CSQ", 0,
+                "96x96 x131072, 4:2:0 + f=8, YCC888 (12x12 outputs)"),
+    "oddavg": (1366, 768, 512, 2, 0, (8, 8, 8), 2, "CSQ", 0,
+               "AVERAGE extension on 1366x768 (Wo = 683: breaks the pooling kernel's 16-byte rules)"),
     "cfg5": (7680, 4320, 64, 2, 0, (6, 5, 5), 4, "CSQ", 1,
              "BASELINE configs[4]: 7680x4320 x64 frames, 4:2:0 + f=4 + Q_16BIT + RGB888 reconstruct"),
 }
@@ -559,6 +577,8 @@ def main():
     ap.add_argument("--stages", type=int, default=0)
     ap.add_argument("--tile-bytes", type=int, default=0)
     ap.add_argument("--block-threads", type=int, default=0)
+    ap.add_argument("--store-policy", type=int, default=0, choices=[0, 1, 2])
+    ap.add_argument("--chunk-mb", type=int, default=0, help="csic_process_host chunk size (CSIC_OPT_HOST_CHUNK_BYTES)")
     ap.add_argument("--shard", default="frames", choices=["frames", "bands"],
                     help="frames: every rank owns its own batch (weak scaling).  bands: every rank owns one aligned "
                          "row band of EVERY frame of one shared batch (strong scaling; BASELINE configs[4])")
@@ -588,6 +608,10 @@ def main():
         ctx.set_option(4, args.tile_bytes)
     if args.block_threads:
         ctx.set_option(5, args.block_threads)
+    if args.store_policy:
+        ctx.set_option(8, args.store_policy)
+    if args.chunk_mb:
+        ctx.set_option(1, args.chunk_mb << 20)
     default_run = args.workload == "cfg4" and args.shard == "frames" and not args.family
 
     main_res = device_run(env, ctx, args.workload, frames, args.shard, args.steps, args.warmup, args.graph,

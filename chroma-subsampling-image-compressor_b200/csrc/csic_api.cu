@@ -75,6 +75,7 @@ struct csic_ctx {
   uint32_t opt_tile_bytes = 0;
   int opt_block_threads = 0;
   int opt_no_compact = 0;
+  int opt_store_policy = 0;
   uint64_t h2d_bytes = 0;    // bytes csic_process_host has shipped host -> device so far
 };
 
@@ -197,6 +198,7 @@ int run(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t n_frames,
   DeviceGuard guard(ctx->device);
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
   k.block_threads = ctx->opt_block_threads;
+  k.store_policy = ctx->opt_store_policy;
   int err;
   if (ctx->opt_family == 0 && csic::plan_rows_kernel(k, ctx->sm_count, ctx->max_smem_optin, ctx->opt_stages, ctx->opt_tile_bytes)) {
     err = csic::launch_rows(k, ctx->sm_count, ctx->opt_ctas_per_sm, st);
@@ -208,7 +210,7 @@ int run(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t n_frames,
     err = csic::launch_flex(k, ctx->sm_count, ctx->opt_ctas_per_sm, st);
     ctx->last_family = 4;
   } else {
-    err = csic::launch_generic(k, st);
+    err = csic::launch_generic(k, ctx->sm_count, st);
     ctx->last_family = 1;
   }
   ctx->launches += 1;
@@ -347,6 +349,10 @@ int csic_set_option(csic_ctx* ctx, int option, int64_t value) {
     case CSIC_OPT_HOST_NO_BOUNCE:
       ctx->opt_no_bounce = value != 0;
       return CSIC_OK;
+    case CSIC_OPT_STORE_POLICY:
+      if (value < 0 || value > 2) return CSIC_EINVAL_ARG;
+      ctx->opt_store_policy = (int)value;
+      return CSIC_OK;
     case CSIC_OPT_TILE_BYTES:
       if (value < 0 || value > (200 << 10)) return CSIC_EINVAL_ARG;
       ctx->opt_tile_bytes = (uint32_t)value;
@@ -396,7 +402,7 @@ int csic_expand_planar_device(csic_ctx* ctx, const csic_params* p, const void* d
   DeviceGuard guard(ctx->device);
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
   int err = csic::launch_expand_planar(k, static_cast<const uint8_t*>(d_planar), static_cast<uint8_t*>(d_out),
-                                       expand_format == CSIC_OUT_RGB888, st);
+                                       expand_format == CSIC_OUT_RGB888, ctx->sm_count, st);
   ctx->launches += 1;
   if (err != (int)cudaSuccess) return cuda_fail((cudaError_t)err, "expand kernel launch");
   return CSIC_OK;

@@ -72,6 +72,39 @@ __device__ __forceinline__ uint32_t inverse_rgb_raw(uint32_t dy, uint32_t xb, ui
   return __byte_perm(__byte_perm(r, g, 0x3362), b, 0x3610);     // R | G << 8 | B << 16
 }
 
+// The same transform split where the subsampled pipeline lets it be shared: everything that depends on the chroma pair
+// only (three multiply-adds with the -128 offsets and the rounding constants folded in) is computed once per chroma
+// SAMPLE -- every second / fourth pixel under 4:2:x / 4:1:x, once per row on a held line -- and a pixel costs one mask,
+// one multiply and three add-clamp instructions.  (The compiler cannot find this sharing by itself once held and
+// sampled rows have merged in the control flow: 13 instructions per pixel became 7.)
+struct InvChroma { int tr, tg, tb; };
+__device__ __forceinline__ InvChroma inv_chroma_terms(uint32_t xb, uint32_t xr, uint32_t mcb8, uint32_t mcr8) {
+  const int cb8 = (int)((xb ^ 0xFFFFu) & mcb8), cr8 = (int)((xr ^ 0xFFFFu) & mcr8);
+  InvChroma t;
+  t.tr = 409 * cr8 - 52224 * 256;
+  t.tg = -208 * cr8 + (-100 * cb8 + 39552 * 256);
+  t.tb = 516 * cb8 - 65920 * 256;
+  return t;
+}
+// Four pixels -> the twelve RGB bytes of a granule (w0 = R0 G0 B0 R1, w1 = G1 B1 R2 G2, w2 = B2 R3 G3 B3).
+// Each channel is one multiply-add in 16.16 fixed point; its UPPER half word is floor(value), a signed 16-bit number in
+// [-560, 816].  Two channels are then packed into one register by a PRMT (upper halves), clamped to [0, 255] TOGETHER by
+// one VIMNMX.S16x2.RELU (min against 0x00FF00FF, relu), and a third PRMT per output word gathers the four low bytes:
+// 12 IMAD (FMA pipe) + 9 PRMT + 6 VIMNMX (ALU pipe) per granule instead of 12 + 11 + 12 with one clamp per channel.
+__device__ __forceinline__ void inv_granule(const uint32_t (&dy)[4], uint32_t my8, const InvChroma& t0, const InvChroma& t1,
+                                            const InvChroma& t2, const InvChroma& t3, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
+  const int y0 = 298 * (int)(dy[0] & my8), y1 = 298 * (int)(dy[1] & my8), y2 = 298 * (int)(dy[2] & my8), y3 = 298 * (int)(dy[3] & my8);
+  auto pair = [](int a, int b) {      // clamp(a >> 16) in byte 0, clamp(b >> 16) in byte 2
+    return __vimin_s16x2_relu(__byte_perm((uint32_t)a, (uint32_t)b, 0x7632), 0x00FF00FFu);
+  };
+  const uint32_t p0 = pair(y0 + t0.tr, y0 + t0.tg), p1 = pair(y0 + t0.tb, y1 + t1.tr);
+  const uint32_t p2 = pair(y1 + t1.tg, y1 + t1.tb), p3 = pair(y2 + t2.tr, y2 + t2.tg);
+  const uint32_t p4 = pair(y2 + t2.tb, y3 + t3.tr), p5 = pair(y3 + t3.tg, y3 + t3.tb);
+  w0 = __byte_perm(p0, p1, 0x6420);
+  w1 = __byte_perm(p2, p3, 0x6420);
+  w2 = __byte_perm(p4, p5, 0x6420);
+}
+
 // Four 24-bit pixels (R | G << 8 | B << 16) -> the twelve bytes of a granule, three PRMTs.
 __device__ __forceinline__ void pack_rgb_granule(const uint32_t (&v)[4], uint32_t& w0, uint32_t& w1, uint32_t& w2) {
   w0 = __byte_perm(v[0], v[1], 0x4210);     // R0 G0 B0 R1

@@ -40,7 +40,7 @@ constexpr int kFlexConsumers = 256;                  // default: 8 consumer warp
 constexpr int kFlexMaxThreads = 288;                 // 8 consumer warps + the producer warp
 constexpr uint32_t kFlexTileBytes = 24u * 1024u;     // input bytes of one tile (B200 sweep: profiles/r1/sweep_flex.txt)
 constexpr uint32_t kCtaWideSpan = 2048u;             // row spans at least this long are stored by the whole CTA
-constexpr uint32_t kDescBytes = 48u;
+constexpr uint32_t kDescBytes = 80u;
 
 __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) {
   asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
@@ -78,41 +78,6 @@ __device__ __forceinline__ void span_fetch(uint32_t slot, const uint8_t* __restr
     const uintptr_t t0 = end < B ? (end > h1 ? end : h1) : B;              // tail is [t0, B)
     for (uintptr_t x = A; x < h1; ++x) sts8(slot + (uint32_t)(x - base), __ldg(gb + (x - base)));
     for (uintptr_t x = t0; x < B; ++x) sts8(slot + (uint32_t)(x - base), __ldg(gb + (x - base)));
-  }
-}
-
-// shared [ssrc, ssrc+len) -> global [g, g+len): 16-byte stores aligned on the global address.  The staging rows are
-// laid out so that (ssrc & 12) == (g & 12): the shared side of a chunk is then one LDS.128, plus one word when the
-// low two address bits differ.
-__device__ __forceinline__ void span_store(uint8_t* __restrict__ g, uint32_t ssrc, uint32_t len, uint32_t t,
-                                           uint32_t nthr) {
-  const uint32_t head = min(len, (16u - ((uint32_t)reinterpret_cast<uintptr_t>(g) & 15u)) & 15u);
-  const uint32_t nchunk = (len - head) >> 4;
-  const uint32_t tail = len - head - (nchunk << 4);
-  const uint32_t s0 = ssrc + head, sa = s0 & ~3u, sh = (s0 & 3u) * 8u;
-  if (sh == 0 && (sa & 15u) == 0) {
-    for (uint32_t c = t; c < nchunk; c += nthr) __stcs(reinterpret_cast<uint4*>(g + head + (c << 4)), lds128(sa + (c << 4)));
-  } else if ((sa & 15u) == 12u) {
-    for (uint32_t c = t; c < nchunk; c += nthr) {
-      const uint32_t a = sa + (c << 4);
-      const uint32_t w0 = lds32(a);
-      const uint4 v = lds128(a + 4);
-      __stcs(reinterpret_cast<uint4*>(g + head + (c << 4)),
-             make_uint4(__funnelshift_r(w0, v.x, sh), __funnelshift_r(v.x, v.y, sh), __funnelshift_r(v.y, v.z, sh),
-                        __funnelshift_r(v.z, v.w, sh)));
-    }
-  } else {
-    for (uint32_t c = t; c < nchunk; c += nthr) {
-      const uint32_t a = sa + (c << 4);
-      const uint32_t w0 = lds32(a), w1 = lds32(a + 4), w2 = lds32(a + 8), w3 = lds32(a + 12), w4 = lds32(a + 16);
-      __stcs(reinterpret_cast<uint4*>(g + head + (c << 4)),
-             make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
-                        __funnelshift_r(w3, w4, sh)));
-    }
-  }
-  for (uint32_t i = nthr - 1u - t; i < head + tail; i += nthr) {
-    const uint32_t off = i < head ? i : len - tail + (i - head);
-    g[off] = (uint8_t)lds8(ssrc + off);
   }
 }
 
@@ -172,27 +137,233 @@ template <int FMT> struct FlexFmt {
   static constexpr uint32_t kUnit = (FMT == KF_YCC888 || FMT == KF_RGB888) ? 12u : (FMT == KF_SLOT32 ? 16u : (FMT == KF_SLOT16 ? 8u : 4u));
 };
 
-// Where a tile sits.  Written to shared memory by the producer before it arms the stage's mbarrier, read by every
-// thread after the barrier's phase flips.
+// Everything the consumer warps need to know about a tile, computed by the producer warp (which has the time: it
+// only issues a few bulk copies per tile) and written to shared memory before it arms the stage's mbarrier; read by
+// every thread after the barrier's phase flips as five vector loads.  Round 1 had each of the 256 consumer threads
+// redo this arithmetic (64-bit output address, row assignment mode, a `% stages` division) for every tile: about 200
+// of the 770 warp-instructions a 16 KB tile cost (ncu, 1366x768).
 struct FlexDesc {
-  uint32_t k, ro0, nrows;    // frame, first output row, rows
-  uint32_t col0, ncols, npx; // first slot, slots (pad slots included), pixels (>= 1)
-  uint32_t a0;               // (address of the tile's first input byte) & 15
-  uint32_t pad[5];
+  uint32_t k, ro0, nrows, col0;            // frame, first output row, rows, first slot
+  uint32_t npx, a0, gpr, last_px;          // pixels (>= 1), (address of the first input byte) & 15, granules per row, npx - 1
+  uint32_t obase_lo, obase_hi, st_mul, st_add;   // global address of the first output byte; staging row j sits at
+                                           //   out_s + j * st_mul + ((obase_lo + j * st_add) & 12)
+  uint32_t mode, sh, magic, n_gran;        // how granules are dealt to threads (flex_consume), log2(warps per row), 2^32 / gpr
+  uint32_t row_out, out_one, ncols, pad;   // output bytes per row, "whole dense rows: one packed span", slots (pad slots incl.)
 };
 static_assert(sizeof(FlexDesc) == kDescBytes, "kDescBytes out of sync");
 
 }  // namespace
+
+// The consumer warps' loop over this CTA's tiles.
+template <int FMT, bool TRUNC, uint32_t HFE, uint32_t PXB>
+__device__ __forceinline__ void flex_consume(const KPlan& P, uint8_t* smem, uint32_t n_my) {
+  constexpr uint32_t kUnit = FlexFmt<FMT>::kUnit, kOpx = kUnit / 4u;
+  const uint32_t tid = threadIdx.x, NC = blockDim.x - 32u, NW = NC >> 5;
+  const uint32_t sbase = smem_u32(smem), out_s = sbase + P.out_buf_off, held_base = sbase + P.meta_off;
+  const uint32_t S = (uint32_t)P.stages, full0 = sbase + P.bar_off, empty0 = full0 + 8u * S, desc0 = full0 + 16u * S;
+  const uint32_t in_stage = P.stage_stride * (uint32_t)P.tile_rows + 32u;     // bytes of one input stage
+  const uint32_t ipb = (uint32_t)P.in_px_bytes, pxb = (uint32_t)P.f * ipb;
+  const uint32_t nsplit = (uint32_t)P.nsplit;
+  const bool vhold = P.vf == 2;
+  const uint32_t my = P.qmask & 0xFFu, mcb = (P.qmask >> 8) & 0xFFu, mcr = (P.qmask >> 16) & 0xFFu;
+  const uint32_t qm0 = my | (mcb << 8) | (mcr << 16) | (my << 24);
+  const uint32_t qm1 = mcb | (mcr << 8) | (my << 16) | (mcb << 24);
+  const uint32_t qm2 = mcr | (my << 8) | (mcb << 16) | (mcr << 24);
+  const int shy = 8 + P.sy, shb = 8 + P.scb, shr = 8 + P.scr, ly = P.cb_bits + P.cr_bits, lb = P.cr_bits;
+  const bool q8 = FMT == KF_SLOT32 && P.sy == 0 && P.scb == 0 && P.scr == 0;
+  const uint32_t vs_sh = P.planar_vs == 2 ? 1u : 0u, hs_sh = P.planar_hs == 4 ? 2u : (P.planar_hs == 2 ? 1u : 0u);
+  // Input rows of a tile land in stage s at  in(s) + j * rs_mul + ((a0 + j * rs_add) & 15),  a0 = src0 & 15.
+  const uint32_t rs_mul = P.in_dense ? P.in_row_bytes : P.stage_stride;
+  const uint32_t rs_add = P.in_dense ? 0u : (((uint32_t)P.row_step * P.in_row_bytes) & 15u);
+
+  // How the granules of a tile are dealt to the threads (FlexDesc::mode, chosen by the producer):
+  //   0  the rows divide the warps (the plan makes nrows a power of two): NW / nrows warps per row, everything
+  //      row-dependent set up once per warp -- taken when at least 4/5 of the lanes of a row's warps get a granule
+  //   1  very wide rows: row by row with the whole CTA          2  narrow rows that fill whole warps: row by row per warp
+  //   3  one flat loop over the tile's granules
+  uint32_t s = 0, ph = 0;
+  for (uint32_t it = 0; it < n_my; ++it) {
+    mbar_wait(full0 + s * 8u, ph);
+    const uint32_t da = desc0 + s * kDescBytes;
+    const uint4 d0 = lds128(da), d1 = lds128(da + 16u), d2 = lds128(da + 32u), d3 = lds128(da + 48u);
+    const uint32_t Dk = d0.x, Dro0 = d0.y, Dnrows = d0.z, Dcol0 = d0.w, Dnpx = d1.x, Da0 = d1.y;
+    consumer_barrier(NC);          // the previous tile has left the staging area
+
+    // ---- compute -------------------------------------------------------------------------------------------
+    const uint32_t in_s = sbase + s * in_stage, held_s = held_base + s * (uint32_t)kFlexMaxRows * 4u;
+    const uint32_t gpr = d1.z, last_px = d1.w;
+    uint8_t* obase = reinterpret_cast<uint8_t*>((uint64_t)d2.x | ((uint64_t)d2.y << 32));
+    const uint4 d4 = lds128(da + 64u);   // row_out, out_one (read before the stage goes back to the producer)
+    // staging row j sits at  out_s + j * st_mul + ((oa0 + j * st_add) & 12):  the output row's own offset modulo 16,
+    // rounded down to a word
+    const uint32_t oa0 = d2.x, st_mul = d2.z, st_add = d2.w;
+    // PLANAR: chroma rows of the tile are the output rows with ro % vs == 0
+    uint8_t* fout = P.out + (uint64_t)Dk * P.out_frame_bytes;
+    const uint32_t c_first = (Dro0 + (1u << vs_sh) - 1u) >> vs_sh;
+    const uint32_t c_last1 = ((Dro0 + Dnrows - 1u) >> vs_sh) + 1u;
+    const uint32_t nrc = (FMT == KF_PLANAR && c_last1 > c_first) ? c_last1 - c_first : 0u;
+    const uint32_t ccols = (Dnpx + (1u << hs_sh) - 1u) >> hs_sh;
+    const uint32_t cb_s = out_s + Dnrows * st_mul + 16u, cr_s = cb_s + nrc * ccols;
+
+    // one granule: (row, g) of the tile; rs = shared address of the row's first input byte, so_row = of its staging
+    // row, hv = the row's held pixel (0: the row samples its own chroma)
+    auto granule = [&](uint32_t row, uint32_t g, uint32_t rs, uint32_t so_row, uint32_t hv) {
+      const uint32_t c = g * 4u;
+      uint32_t p[4], dy[4], xb[4], xr[4];
+      if (c + 3u <= last_px) {
+        load_granule_any<PXB>(rs + c * pxb, pxb, p);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) p[j] = lds_px(rs + min(c + j, last_px) * pxb);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dy[j] = fwd_y16(p[j], P.coef_y);
+      const uint32_t so = so_row + g * kUnit;
+      if (FMT == KF_RGB888) {
+        // fused reconstruction: the chroma-only part of YCbCr2RGB per chroma SAMPLE (once per granule on a held row,
+        // every HFE-th pixel otherwise), the per-pixel part in emit()
+        const uint32_t my8 = my << 8, mcb8 = mcb << 8, mcr8 = mcr << 8;
+        auto emit = [&](const InvChroma& t0, const InvChroma& t1, const InvChroma& t2, const InvChroma& t3) {
+          uint32_t w0, w1, w2;
+        inv_granule(dy, my8, t0, t1, t2, t3, w0, w1, w2);
+          sts32(so, w0); sts32(so + 4, w1); sts32(so + 8, w2);
+        };
+        if (hv) {
+          const InvChroma t = inv_chroma_terms(fwd_nc16<TRUNC>(hv & 0x00FFFFFFu, P.coef_ncb), fwd_nc16<TRUNC>(hv & 0x00FFFFFFu, P.coef_ncr), mcb8, mcr8);
+          emit(t, t, t, t);
+        } else {
+          InvChroma t[4];
+#pragma unroll
+          for (int j = 0; j < 4; j += (int)HFE) t[j] = inv_chroma_terms(fwd_nc16<TRUNC>(p[j], P.coef_ncb), fwd_nc16<TRUNC>(p[j], P.coef_ncr), mcb8, mcr8);
+          emit(t[0], t[1 - 1 % HFE], t[2 - 2 % HFE], t[3 - 3 % HFE]);
+        }
+        return;
+      }
+      if (hv) {
+        const uint32_t hb = fwd_nc16<TRUNC>(hv & 0x00FFFFFFu, P.coef_ncb), hr = fwd_nc16<TRUNC>(hv & 0x00FFFFFFu, P.coef_ncr);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { xb[j] = hb; xr[j] = hr; }
+      } else {
+        // sample where j % HFE == 0, hold in between (ChromaSubsampler.scala:57-65)
+        xb[0] = fwd_nc16<TRUNC>(p[0], P.coef_ncb); xr[0] = fwd_nc16<TRUNC>(p[0], P.coef_ncr);
+        if (HFE == 1) { xb[1] = fwd_nc16<TRUNC>(p[1], P.coef_ncb); xr[1] = fwd_nc16<TRUNC>(p[1], P.coef_ncr); }
+        else { xb[1] = xb[0]; xr[1] = xr[0]; }
+        if (HFE <= 2) { xb[2] = fwd_nc16<TRUNC>(p[2], P.coef_ncb); xr[2] = fwd_nc16<TRUNC>(p[2], P.coef_ncr); }
+        else { xb[2] = xb[0]; xr[2] = xr[0]; }
+        if (HFE == 1) { xb[3] = fwd_nc16<TRUNC>(p[3], P.coef_ncb); xr[3] = fwd_nc16<TRUNC>(p[3], P.coef_ncr); }
+        else { xb[3] = xb[2]; xr[3] = xr[2]; }
+      }
+      if (FMT == KF_YCC888) {
+        // byte 1 of dy is Y, byte 1 of xb/xr is ~Cb/~Cr: gather with PRMT, flip and quantise per word
+        uint32_t t, u;
+        t = __byte_perm(dy[0], xb[0], 0x0051); u = __byte_perm(xr[0], dy[1], 0x0051);
+        sts32(so, (__byte_perm(t, u, 0x5410) ^ 0x00FFFF00u) & qm0);
+        t = __byte_perm(xb[1], xr[1], 0x0051); u = __byte_perm(dy[2], xb[2], 0x0051);
+        sts32(so + 4, (__byte_perm(t, u, 0x5410) ^ 0xFF00FFFFu) & qm1);
+        t = __byte_perm(xr[2], dy[3], 0x0051); u = __byte_perm(xb[3], xr[3], 0x0051);
+        sts32(so + 8, (__byte_perm(t, u, 0x5410) ^ 0xFFFF00FFu) & qm2);
+      } else if (FMT == KF_PLANAR) {
+        const uint32_t my4 = my * 0x01010101u;
+        sts32(so, __byte_perm(__byte_perm(dy[0], dy[1], 0x0051), __byte_perm(dy[2], dy[3], 0x0051), 0x5410) & my4);
+        if (!hv) {               // a sampled line: its sample points go to the chroma planes (hs == HFE here)
+          const uint32_t crow = (((Dro0 + row) >> vs_sh) - c_first) * ccols + (c >> hs_sh);
+          if (HFE == 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (c + j <= last_px) { sts8(cb_s + crow + j, (~(xb[j] >> 8)) & mcb); sts8(cr_s + crow + j, (~(xr[j] >> 8)) & mcr); }
+          } else if (HFE == 2) {
+            sts8(cb_s + crow, (~(xb[0] >> 8)) & mcb); sts8(cr_s + crow, (~(xr[0] >> 8)) & mcr);
+            if (c + 2 <= last_px) { sts8(cb_s + crow + 1, (~(xb[2] >> 8)) & mcb); sts8(cr_s + crow + 1, (~(xr[2] >> 8)) & mcr); }
+          } else {
+            sts8(cb_s + crow, (~(xb[0] >> 8)) & mcb); sts8(cr_s + crow, (~(xr[0] >> 8)) & mcr);
+          }
+        }
+      } else {
+        uint32_t v[4];
+        if (q8) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)   // (Cr, Cb, Y, 0): dy < 65536 so its byte 3 is the zero pad
+            v[j] = __byte_perm(__byte_perm(xr[j], xb[j], 0x0051), dy[j], 0x7510) ^ 0x0000FFFFu;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            v[j] = ((dy[j] >> shy) << ly) | (((xb[j] ^ 0xFFFFu) >> shb) << lb) | ((xr[j] ^ 0xFFFFu) >> shr);
+        }
+        if (c + 3u > last_px) {        // the row's zero pad slots
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (c + j > last_px) v[j] = 0u;
+        }
+        if (FMT == KF_SLOT32) {
+          if ((so & 15u) == 0) sts128(so, v[0], v[1], v[2], v[3]);
+          else if ((so & 7u) == 0) { sts64(so, v[0], v[1]); sts64(so + 8, v[2], v[3]); }
+          else { sts32(so, v[0]); sts32(so + 4, v[1]); sts32(so + 8, v[2]); sts32(so + 12, v[3]); }
+        } else if (FMT == KF_SLOT16) {
+          if ((so & 7u) == 0) sts64(so, v[0] | (v[1] << 16), v[2] | (v[3] << 16));
+          else { sts32(so, v[0] | (v[1] << 16)); sts32(so + 4, v[2] | (v[3] << 16)); }
+        } else {
+          sts32(so, v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
+        }
+      }
+    };
+    auto row_in = [&](uint32_t row) { return in_s + row * rs_mul + ((Da0 + row * rs_add) & 15u); };
+    auto row_st = [&](uint32_t row) { return out_s + row * st_mul + ((oa0 + row * st_add) & 12u); };
+    if (d3.x == 0u) {
+      const uint32_t parts = 1u << d3.y, row = (tid >> 5) >> d3.y, part = (tid >> 5) & (parts - 1u);
+      const uint32_t rs = row_in(row), so_row = row_st(row), hv = vhold ? lds32(held_s + row * 4u) : 0u;
+      for (uint32_t g = part * 32u + (tid & 31u); g < gpr; g += parts * 32u) granule(row, g, rs, so_row, hv);
+    } else if (d3.x == 1u) {     // very wide rows: row by row, nothing row-dependent inside the loop
+      for (uint32_t row = 0; row < Dnrows; ++row) {
+        const uint32_t rs = row_in(row), so_row = row_st(row), hv = vhold ? lds32(held_s + row * 4u) : 0u;
+        for (uint32_t g = tid; g < gpr; g += NC) granule(row, g, rs, so_row, hv);
+      }
+    } else if (d3.x == 2u) {     // narrow rows that fill whole warps, a whole number of rows per warp: row by row per warp
+      for (uint32_t row = tid >> 5; row < Dnrows; row += NW) {
+        const uint32_t rs = row_in(row), so_row = row_st(row), hv = vhold ? lds32(held_s + row * 4u) : 0u;
+        for (uint32_t g = tid & 31u; g < gpr; g += 32u) granule(row, g, rs, so_row, hv);
+      }
+    } else {                       // narrow rows: one flat loop over the tile's granules
+      for (uint32_t q = tid; q < d3.w; q += NC) {
+        const uint32_t row = gpr > 1u ? __umulhi(q, d3.z) : q, g = q - row * gpr;
+        granule(row, g, row_in(row), row_st(row), vhold ? lds32(held_s + row * 4u) : 0u);
+      }
+    }
+    consumer_barrier(NC);          // staging complete; every read of input stage s, its held words and descriptor is done
+    if (tid == 0) mbar_arrive(empty0 + s * 8u);
+
+    // ---- store ---------------------------------------------------------------------------------------------
+    if (d4.y) {
+      span_store(obase, out_s + (oa0 & 12u), Dnrows * d4.x, tid, NC);
+    } else {
+      for_each_span(Dnrows, d4.x, NC, [&](uint32_t j, uint32_t t, uint32_t n) {
+        span_store(obase + (uint64_t)j * P.out_row_bytes, out_s + j * st_mul + ((oa0 + j * st_add) & 12u), d4.x, t, n);
+      });
+    }
+    if (FMT == KF_PLANAR && nrc) {
+      const uint64_t coff = (uint64_t)c_first * (uint32_t)P.planar_cw + (Dcol0 >> hs_sh);
+      uint8_t* cb_g = fout + P.planar_cb_off + coff;
+      uint8_t* cr_g = fout + P.planar_cr_off + coff;
+      if (nsplit == 1) {                                       // ccols == planar_cw: chroma rows are contiguous
+        span_store(cb_g, cb_s, nrc * ccols, tid, NC);
+        span_store(cr_g, cr_s, nrc * ccols, tid, NC);
+      } else {
+        for_each_span(nrc, ccols, NC, [&](uint32_t j, uint32_t t, uint32_t n) {
+          span_store(cb_g + (uint64_t)j * (uint32_t)P.planar_cw, cb_s + j * ccols, ccols, t, n);
+          span_store(cr_g + (uint64_t)j * (uint32_t)P.planar_cw, cr_s + j * ccols, ccols, t, n);
+        });
+      }
+    }
+    if (++s == S) { s = 0u; ph ^= 1u; }
+  }
+}
 
 template <int FMT, bool TRUNC>
 __global__ void __launch_bounds__(kFlexMaxThreads, 4) csic_flex_kernel(const __grid_constant__ KPlan P) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr uint32_t kUnit = FlexFmt<FMT>::kUnit, kOpx = kUnit / 4u;
   const uint32_t tid = threadIdx.x, NT = blockDim.x;
-  const uint32_t sbase = smem_u32(smem), out_s = sbase + P.out_buf_off, held_base = sbase + P.meta_off;
+  const uint32_t sbase = smem_u32(smem), held_base = sbase + P.meta_off;
   const uint32_t bar0 = sbase + P.bar_off;
   const uint32_t S = (uint32_t)P.stages;
-  const FlexDesc* descs = reinterpret_cast<const FlexDesc*>(smem + P.bar_off + 16u * S);
   const uint32_t in_stage = P.stage_stride * (uint32_t)P.tile_rows + 32u;     // bytes of one input stage
   const uint32_t ipb = (uint32_t)P.in_px_bytes, f = (uint32_t)P.f, pxb = f * ipb;
   const uint32_t nsplit = (uint32_t)P.nsplit;
@@ -201,19 +372,8 @@ __global__ void __launch_bounds__(kFlexMaxThreads, 4) csic_flex_kernel(const __g
   const uint64_t rstep = (uint64_t)(uint32_t)P.row_step * P.in_row_bytes;
   const uint32_t n_my = (P.n_tiles > blockIdx.x) ? (P.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   if (n_my == 0) return;
-  // quantiser masks / shifts
-  const uint32_t my = P.qmask & 0xFFu, mcb = (P.qmask >> 8) & 0xFFu, mcr = (P.qmask >> 16) & 0xFFu;
-  const uint32_t qm0 = my | (mcb << 8) | (mcr << 16) | (my << 24);
-  const uint32_t qm1 = mcb | (mcr << 8) | (my << 16) | (mcb << 24);
-  const uint32_t qm2 = mcr | (my << 8) | (mcb << 16) | (mcr << 24);
-  const int shy = 8 + P.sy, shb = 8 + P.scb, shr = 8 + P.scr, ly = P.cb_bits + P.cr_bits, lb = P.cr_bits;
-  const bool q8 = FMT == KF_SLOT32 && P.sy == 0 && P.scb == 0 && P.scr == 0;
-  const uint32_t vs_sh = P.planar_vs == 2 ? 1u : 0u, hs_sh = P.planar_hs == 4 ? 2u : (P.planar_hs == 2 ? 1u : 0u);
-
   // Input rows of a tile land in stage s at  in(s) + j * rs_mul + ((a0 + j * rs_add) & 15),  a0 = src0 & 15.
   const uint32_t rs_mul = P.in_dense ? P.in_row_bytes : P.stage_stride;
-  const uint32_t rs_add = P.in_dense ? 0u : ((uint32_t)rstep & 15u);
-
   const uint32_t NC = NT - 32u;    // consumer threads; the last warp is the producer
   const uint32_t full0 = bar0, empty0 = bar0 + 8u * S;
   if (tid == 0) {
@@ -239,9 +399,10 @@ __global__ void __launch_bounds__(kFlexMaxThreads, 4) csic_flex_kernel(const __g
     const uintptr_t lim_hi = reinterpret_cast<uintptr_t>(P.in) + (uint64_t)(P.n_frames - 1u) * P.in_frame_bytes +
                              (uint64_t)((uint32_t)(P.row0 + P.band_rows - 1) * (uint32_t)P.row_step) * P.in_row_bytes +
                              ((uint32_t)P.Wo - 1u) * pxb + ipb;
-    for (uint32_t j = 0; j < n_my; ++j) {
-      const uint32_t s = j % S, bar = full0 + s * 8u, in_s = sbase + s * in_stage;
-      if (j >= S) mbar_wait(empty0 + s * 8u, ((j / S) - 1u) & 1u);         // the consumers drained the previous use
+    uint32_t s = 0, ph = 1;                 // stage and the parity of the empty-barrier phase to wait for (from the second lap)
+    for (uint32_t j = 0; j < n_my; ++j, s = (s + 1u == S) ? 0u : s + 1u, ph ^= (s == 0u) ? 1u : 0u) {
+      const uint32_t bar = full0 + s * 8u, in_s = sbase + s * in_stage;
+      if (j >= S) mbar_wait(empty0 + s * 8u, ph);                          // the consumers drained the previous use
       FlexDesc* d = reinterpret_cast<FlexDesc*>(smem + P.bar_off + 16u * S) + s;
       const uint32_t ro0 = (uint32_t)P.row0 + ptb * (uint32_t)P.tile_rows;
       const uint32_t nrows = min((uint32_t)P.tile_rows, (uint32_t)(P.row0 + P.band_rows) - ro0);
@@ -268,8 +429,24 @@ __global__ void __launch_bounds__(kFlexMaxThreads, 4) csic_flex_kernel(const __g
         if (hp) { h0 = ldg8_now(hp); h1 = ldg8_now(hp + 1); h2 = ldg8_now(hp + 2); hvalid = 0x80000000u; }
       }
       if (lane == 0) {
-        d->k = pk; d->ro0 = ro0; d->nrows = nrows; d->col0 = col0; d->ncols = ncols; d->npx = npx;
-        d->a0 = (uint32_t)reinterpret_cast<uintptr_t>(src0) & 15u;
+        const uint32_t NWc = NC >> 5, gpr = (ncols + 3u) >> 2, srow = gpr * kUnit, row_out = ncols * kOpx;
+        const uint64_t ob = reinterpret_cast<uint64_t>(P.out) + (uint64_t)pk * P.out_frame_bytes + (uint64_t)ro0 * P.out_row_bytes +
+                            (uint64_t)col0 * kOpx;
+        const uint32_t out_one = (P.out_dense && nsplit == 1u && row_out == srow) ? 1u : 0u;   // whole dense rows: one packed span
+        const uint32_t sh = pow2_divides(nrows, NWc) ? 31u - __clz(NWc) - (31u - __clz(nrows)) : 0u;   // log2(NW / nrows)
+        const uint32_t lsh = sh + 5u, iters = (gpr + (1u << lsh) - 1u) >> lsh;                          // lanes per row = 1 << lsh
+        uint32_t mode;
+        if (pow2_divides(nrows, NWc) && gpr * 5u >= (iters << lsh) * 4u) mode = 0u;
+        else if (gpr >= 4u * NC) mode = 1u;
+        else if ((gpr & 31u) == 0u && (NWc & (NWc - 1u)) == 0u && (nrows & (NWc - 1u)) == 0u) mode = 2u;
+        else mode = 3u;
+        d->k = pk; d->ro0 = ro0; d->nrows = nrows; d->col0 = col0;
+        d->npx = npx; d->a0 = (uint32_t)reinterpret_cast<uintptr_t>(src0) & 15u; d->gpr = gpr; d->last_px = npx - 1u;
+        d->obase_lo = (uint32_t)ob; d->obase_hi = (uint32_t)(ob >> 32);
+        d->st_mul = out_one ? srow : srow + 16u; d->st_add = out_one ? 0u : P.out_row_bytes;
+        d->mode = mode; d->sh = sh; d->magic = gpr > 1u ? 0xFFFFFFFFu / gpr + 1u : 0u;   // q / gpr == umulhi(q, magic) for q < 65536
+        d->n_gran = nrows * gpr;
+        d->row_out = row_out; d->out_one = out_one; d->ncols = ncols; d->pad = 0u;
       }
       if (P.in_dense) {            // consecutive rows are contiguous in memory: one span
         if (lane == 0) span_fetch(in_s, src0, (nrows - 1u) * P.in_row_bytes + len_in, bar, pol, lim_lo, lim_hi);
@@ -294,187 +471,18 @@ __global__ void __launch_bounds__(kFlexMaxThreads, 4) csic_flex_kernel(const __g
   }
 
   // ============================== consumer warps =============================================================
-  for (uint32_t it = 0; it < n_my; ++it) {
-    const uint32_t s = it % S;
-    mbar_wait(full0 + s * 8u, (it / S) & 1u);
-    const FlexDesc D = descs[s];
-    consumer_barrier(NC);          // the previous tile has left the staging area
-
-    // ---- compute -------------------------------------------------------------------------------------------
-    const uint32_t in_s = sbase + s * in_stage, held_s = held_base + s * (uint32_t)kFlexMaxRows * 4u;
-    const uint32_t gpr = (D.ncols + 3u) >> 2;                  // granules per row
-    const uint32_t n_gran = D.nrows * gpr, srow = gpr * kUnit;
-    const uint32_t row_out = D.ncols * kOpx;
-    uint8_t* fout = P.out + (uint64_t)D.k * P.out_frame_bytes;
-    uint8_t* obase = fout + (uint64_t)D.ro0 * P.out_row_bytes + (uint64_t)D.col0 * kOpx;
-    // staging row j sits at  out_s + j * st_mul + ((oa0 + j * st_add) & 12):  the output row's own offset modulo 16,
-    // rounded down to a word
-    const bool out_one = P.out_dense && nsplit == 1 && row_out == srow;   // whole dense rows: one packed span
-    const uint32_t oa0 = (uint32_t)reinterpret_cast<uintptr_t>(obase);
-    const uint32_t st_mul = out_one ? srow : srow + 16u, st_add = out_one ? 0u : P.out_row_bytes;
-    // PLANAR: chroma rows of the tile are the output rows with ro % vs == 0
-    const uint32_t c_first = (D.ro0 + (1u << vs_sh) - 1u) >> vs_sh;
-    const uint32_t c_last1 = ((D.ro0 + D.nrows - 1u) >> vs_sh) + 1u;
-    const uint32_t nrc = (FMT == KF_PLANAR && c_last1 > c_first) ? c_last1 - c_first : 0u;
-    const uint32_t ccols = (D.npx + (1u << hs_sh) - 1u) >> hs_sh;
-    const uint32_t cb_s = out_s + D.nrows * st_mul + 16u, cr_s = cb_s + nrc * ccols;
-    const uint32_t last_px = D.npx - 1u;
-    // the loop is instantiated per chroma hold width (1, 2 or 4 output pixels) and per pixel stride class: no
-    // per-granule branches or moves
-    auto compute = [&](auto hfe_tag, auto pxb_tag) {
-      constexpr uint32_t HFE = decltype(hfe_tag)::value, PXB = decltype(pxb_tag)::value;
-      // one granule: (row, g) of the tile; rs = shared address of the row's first input byte, so_row = of its staging
-      // row, hv = the row's held pixel (0: the row samples its own chroma)
-      auto granule = [&](uint32_t row, uint32_t g, uint32_t rs, uint32_t so_row, uint32_t hv) {
-        const uint32_t c = g * 4u;
-        uint32_t p[4], dy[4], xb[4], xr[4];
-        if (c + 3u <= last_px) {
-          load_granule_any<PXB>(rs + c * pxb, pxb, p);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) p[j] = lds_px(rs + min(c + j, last_px) * pxb);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dy[j] = fwd_y16(p[j], P.coef_y);
-        if (hv) {
-          const uint32_t hb = fwd_nc16<TRUNC>(hv & 0x00FFFFFFu, P.coef_ncb), hr = fwd_nc16<TRUNC>(hv & 0x00FFFFFFu, P.coef_ncr);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { xb[j] = hb; xr[j] = hr; }
-        } else {
-          // sample where j % HFE == 0, hold in between (ChromaSubsampler.scala:57-65)
-          xb[0] = fwd_nc16<TRUNC>(p[0], P.coef_ncb); xr[0] = fwd_nc16<TRUNC>(p[0], P.coef_ncr);
-          if (HFE == 1) { xb[1] = fwd_nc16<TRUNC>(p[1], P.coef_ncb); xr[1] = fwd_nc16<TRUNC>(p[1], P.coef_ncr); }
-          else { xb[1] = xb[0]; xr[1] = xr[0]; }
-          if (HFE <= 2) { xb[2] = fwd_nc16<TRUNC>(p[2], P.coef_ncb); xr[2] = fwd_nc16<TRUNC>(p[2], P.coef_ncr); }
-          else { xb[2] = xb[0]; xr[2] = xr[0]; }
-          if (HFE == 1) { xb[3] = fwd_nc16<TRUNC>(p[3], P.coef_ncb); xr[3] = fwd_nc16<TRUNC>(p[3], P.coef_ncr); }
-          else { xb[3] = xb[2]; xr[3] = xr[2]; }
-        }
-        const uint32_t so = so_row + g * kUnit;
-        if (FMT == KF_YCC888) {
-          // byte 1 of dy is Y, byte 1 of xb/xr is ~Cb/~Cr: gather with PRMT, flip and quantise per word
-          uint32_t t, u;
-          t = __byte_perm(dy[0], xb[0], 0x0051); u = __byte_perm(xr[0], dy[1], 0x0051);
-          sts32(so, (__byte_perm(t, u, 0x5410) ^ 0x00FFFF00u) & qm0);
-          t = __byte_perm(xb[1], xr[1], 0x0051); u = __byte_perm(dy[2], xb[2], 0x0051);
-          sts32(so + 4, (__byte_perm(t, u, 0x5410) ^ 0xFF00FFFFu) & qm1);
-          t = __byte_perm(xr[2], dy[3], 0x0051); u = __byte_perm(xb[3], xr[3], 0x0051);
-          sts32(so + 8, (__byte_perm(t, u, 0x5410) ^ 0xFFFF00FFu) & qm2);
-        } else if (FMT == KF_RGB888) {
-          uint32_t v[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            v[j] = inverse_rgb_raw(dy[j], xb[j], xr[j], my << 8, mcb << 8, mcr << 8);
-          uint32_t w0, w1, w2;
-          pack_rgb_granule(v, w0, w1, w2);
-          sts32(so, w0); sts32(so + 4, w1); sts32(so + 8, w2);
-        } else if (FMT == KF_PLANAR) {
-          const uint32_t my4 = my * 0x01010101u;
-          sts32(so, __byte_perm(__byte_perm(dy[0], dy[1], 0x0051), __byte_perm(dy[2], dy[3], 0x0051), 0x5410) & my4);
-          if (!hv) {               // a sampled line: its sample points go to the chroma planes (hs == HFE here)
-            const uint32_t crow = (((D.ro0 + row) >> vs_sh) - c_first) * ccols + (c >> hs_sh);
-            if (HFE == 1) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (c + j <= last_px) { sts8(cb_s + crow + j, (~(xb[j] >> 8)) & mcb); sts8(cr_s + crow + j, (~(xr[j] >> 8)) & mcr); }
-            } else if (HFE == 2) {
-              sts8(cb_s + crow, (~(xb[0] >> 8)) & mcb); sts8(cr_s + crow, (~(xr[0] >> 8)) & mcr);
-              if (c + 2 <= last_px) { sts8(cb_s + crow + 1, (~(xb[2] >> 8)) & mcb); sts8(cr_s + crow + 1, (~(xr[2] >> 8)) & mcr); }
-            } else {
-              sts8(cb_s + crow, (~(xb[0] >> 8)) & mcb); sts8(cr_s + crow, (~(xr[0] >> 8)) & mcr);
-            }
-          }
-        } else {
-          uint32_t v[4];
-          if (q8) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)   // (Cr, Cb, Y, 0): dy < 65536 so its byte 3 is the zero pad
-              v[j] = __byte_perm(__byte_perm(xr[j], xb[j], 0x0051), dy[j], 0x7510) ^ 0x0000FFFFu;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              v[j] = ((dy[j] >> shy) << ly) | (((xb[j] ^ 0xFFFFu) >> shb) << lb) | ((xr[j] ^ 0xFFFFu) >> shr);
-          }
-          if (c + 3u > last_px) {        // the row's zero pad slots
-#pragma unroll
-            for (int j = 0; j < 4; ++j) if (c + j > last_px) v[j] = 0u;
-          }
-          if (FMT == KF_SLOT32) {
-            if ((so & 15u) == 0) sts128(so, v[0], v[1], v[2], v[3]);
-            else if ((so & 7u) == 0) { sts64(so, v[0], v[1]); sts64(so + 8, v[2], v[3]); }
-            else { sts32(so, v[0]); sts32(so + 4, v[1]); sts32(so + 8, v[2]); sts32(so + 12, v[3]); }
-          } else if (FMT == KF_SLOT16) {
-            if ((so & 7u) == 0) sts64(so, v[0] | (v[1] << 16), v[2] | (v[3] << 16));
-            else { sts32(so, v[0] | (v[1] << 16)); sts32(so + 4, v[2] | (v[3] << 16)); }
-          } else {
-            sts32(so, v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
-          }
-        }
-      };
-      auto row_in = [&](uint32_t row) { return in_s + row * rs_mul + ((D.a0 + row * rs_add) & 15u); };
-      auto row_st = [&](uint32_t row) { return out_s + row * st_mul + ((oa0 + row * st_add) & 12u); };
-      const uint32_t NW = NC >> 5;
-      // rows that divide the warps (the plan makes nrows a power of two): NW / nrows warps per row, everything
-      // row-dependent set up once per warp -- taken when at least 4/5 of the lanes of a row's warps get a granule
-      const uint32_t sh = pow2_divides(D.nrows, NW) ? 31u - __clz(NW) - (31u - __clz(D.nrows)) : 0u;   // log2(NW / nrows)
-      const uint32_t lsh = sh + 5u, iters = (gpr + (1u << lsh) - 1u) >> lsh;                             // lanes per row = 1 << lsh
-      if (pow2_divides(D.nrows, NW) && gpr * 5u >= (iters << lsh) * 4u) {
-        const uint32_t parts = 1u << sh, row = (tid >> 5) >> sh, part = (tid >> 5) & (parts - 1u);
-        const uint32_t rs = row_in(row), so_row = row_st(row), hv = vhold ? lds32(held_s + row * 4u) : 0u;
-        for (uint32_t g = part * 32u + (tid & 31u); g < gpr; g += parts * 32u) granule(row, g, rs, so_row, hv);
-      } else if (gpr >= 4u * NC) {   // very wide rows: row by row, nothing row-dependent inside the loop
-        for (uint32_t row = 0; row < D.nrows; ++row) {
-          const uint32_t rs = row_in(row), so_row = row_st(row), hv = vhold ? lds32(held_s + row * 4u) : 0u;
-          for (uint32_t g = tid; g < gpr; g += NC) granule(row, g, rs, so_row, hv);
-        }
-      } else if ((gpr & 31u) == 0u && (NW & (NW - 1u)) == 0u && (D.nrows & (NW - 1u)) == 0u) {
-        // narrow rows that fill whole warps, a whole number of rows per warp: row by row per warp
-        for (uint32_t row = tid >> 5; row < D.nrows; row += NW) {
-          const uint32_t rs = row_in(row), so_row = row_st(row), hv = vhold ? lds32(held_s + row * 4u) : 0u;
-          for (uint32_t g = tid & 31u; g < gpr; g += 32u) granule(row, g, rs, so_row, hv);
-        }
-      } else {                     // narrow rows: one flat loop over the tile's granules
-        const uint32_t gpr_magic = gpr > 1u ? 0xFFFFFFFFu / gpr + 1u : 0u;   // q / gpr == umulhi(q, magic) for q < 65536
-        for (uint32_t q = tid; q < n_gran; q += NC) {
-          const uint32_t row = gpr > 1u ? __umulhi(q, gpr_magic) : q, g = q - row * gpr;
-          granule(row, g, row_in(row), row_st(row), vhold ? lds32(held_s + row * 4u) : 0u);
-        }
-      }
-    };
-    auto compute_hfe = [&](auto pxb_tag) {
-      if (hfe == 1u) compute(std::integral_constant<uint32_t, 1u>{}, pxb_tag);
-      else if (hfe == 2u) compute(std::integral_constant<uint32_t, 2u>{}, pxb_tag);
-      else compute(std::integral_constant<uint32_t, 4u>{}, pxb_tag);
-    };
-    if (pxb == 3u) compute_hfe(std::integral_constant<uint32_t, 3u>{});         // RGB24, f = 1
-    else if (pxb == 6u) compute_hfe(std::integral_constant<uint32_t, 6u>{});    // RGB24, f = 2
-    else compute_hfe(std::integral_constant<uint32_t, 0u>{});                   // sampled pixels on a common byte phase
-    consumer_barrier(NC);          // staging complete; every read of input stage s, its held words and descriptor is done
-    if (tid == 0) mbar_arrive(empty0 + s * 8u);
-
-    // ---- store ---------------------------------------------------------------------------------------------
-    if (out_one) {
-      span_store(obase, out_s + (oa0 & 12u), D.nrows * row_out, tid, NC);
-    } else {
-      for_each_span(D.nrows, row_out, NC, [&](uint32_t j, uint32_t t, uint32_t n) {
-        span_store(obase + (uint64_t)j * P.out_row_bytes, out_s + j * st_mul + ((oa0 + j * st_add) & 12u), row_out, t, n);
-      });
-    }
-    if (FMT == KF_PLANAR && nrc) {
-      const uint64_t coff = (uint64_t)c_first * (uint32_t)P.planar_cw + (D.col0 >> hs_sh);
-      uint8_t* cb_g = fout + P.planar_cb_off + coff;
-      uint8_t* cr_g = fout + P.planar_cr_off + coff;
-      if (nsplit == 1) {                                       // ccols == planar_cw: chroma rows are contiguous
-        span_store(cb_g, cb_s, nrc * ccols, tid, NC);
-        span_store(cr_g, cr_s, nrc * ccols, tid, NC);
-      } else {
-        for_each_span(nrc, ccols, NC, [&](uint32_t j, uint32_t t, uint32_t n) {
-          span_store(cb_g + (uint64_t)j * (uint32_t)P.planar_cw, cb_s + j * ccols, ccols, t, n);
-          span_store(cr_g + (uint64_t)j * (uint32_t)P.planar_cw, cr_s + j * ccols, ccols, t, n);
-        });
-      }
-    }
-  }
+  // One specialisation per (chroma hold width, pixel stride class), chosen once per CTA: no per-tile dispatch, and a
+  // CTA only ever runs one copy of the loop (the nine copies used to thrash the instruction cache: ncu showed
+  // `no_instruction` stalls of 1.3 per issue on 1366x768 f = 2).
+  auto run = [&](auto hfe_tag) {
+    constexpr uint32_t H = decltype(hfe_tag)::value;
+    if (pxb == 3u) flex_consume<FMT, TRUNC, H, 3u>(P, smem, n_my);          // RGB24, f = 1
+    else if (pxb == 6u) flex_consume<FMT, TRUNC, H, 6u>(P, smem, n_my);     // RGB24, f = 2
+    else flex_consume<FMT, TRUNC, H, 0u>(P, smem, n_my);                    // sampled pixels on a common byte phase
+  };
+  if (hfe == 1u) run(std::integral_constant<uint32_t, 1u>{});
+  else if (hfe == 2u) run(std::integral_constant<uint32_t, 2u>{});
+  else run(std::integral_constant<uint32_t, 4u>{});
 }
 
 // ---- planning and dispatch ---------------------------------------------------------------------------------

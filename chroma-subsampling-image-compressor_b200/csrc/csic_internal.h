@@ -52,6 +52,7 @@ struct KPlan {
   int32_t compact;                       // input holds only the rows a DECIMATE pipeline reads (every f-th), densely
   int32_t row_step;                      // input rows between consecutive output rows: f, or 1 when compact
   uint32_t n_frames;
+  int32_t store_policy;                  // CSIC_OPT_STORE_POLICY (row kernel): 0 streaming / evict-first stores, 1 default write-back, 2 .cg
   // ---- TMA row kernel only ----
   int32_t hfe;                           // chroma hold width in *output* pixels inside a 4-pixel granule
   int32_t nsplit, tile_px;               // segments per output row, output pixels per row segment
@@ -71,8 +72,8 @@ struct KPlan {
 bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_stages, uint32_t force_tile_bytes);
 
 // Both return a cudaError_t as int.
-int launch_generic(const KPlan& k, void* stream);
-int launch_expand_planar(const KPlan& k, const uint8_t* planar, uint8_t* out, int to_rgb, void* stream);
+int launch_generic(const KPlan& k, int sm_count, void* stream);
+int launch_expand_planar(const KPlan& k, const uint8_t* planar, uint8_t* out, int to_rgb, int sm_count, void* stream);
 int launch_rows(const KPlan& k, int sm_count, int force_ctas_per_sm, void* stream);
 constexpr int kDefaultBlockThreads = 256;   // consumer threads; one producer warp is added at launch
 constexpr int kMaxConsumerThreads = 512;

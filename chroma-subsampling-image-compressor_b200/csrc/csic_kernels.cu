@@ -22,176 +22,281 @@
 
 #include "csic_internal.h"
 #include "csic_device_math.cuh"
+#include "csic_tma.cuh"
 
 namespace csic {
 
 // ================================================================================================
-// Generic gather kernel
+// Generic gather kernel: any legal parameter set, any width, pitch and alignment
 // ================================================================================================
-__device__ __forceinline__ uint32_t load_px(const uint8_t* __restrict__ frame, uint32_t row_bytes, int r, int c, int ipb) {
-  // r is a row of the frame as stored (see KPlan::compact); ipb = bytes per input pixel (3 or 4)
-  const uint8_t* q = frame + (size_t)r * row_bytes + (size_t)c * (size_t)ipb;
-  return (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16);
-}
+// What runs when no staged kernel is eligible: spatial-before-chroma shapes whose counter lines are not whole output
+// rows (e.g. W = 13, f = 2), the AVERAGE extension on shapes that break the pooling kernel's 16-byte rules -- and
+// every parameter set when a test forces it (CSIC_OPT_KERNEL_FAMILY = 1), which makes it the independent second
+// implementation the other kernels are cross-checked against.
+//
+// One CTA per output row (grid-stride); the frame / row split -- the only division outside the case-B source map --
+// happens once per row.  A thread computes one granule of four output slots:
+//   load    every pixel is three bytes at an arbitrary address = two aligned LDG.32 and a funnel shift through L1 (the
+//           second word never lies beyond the last word that holds a byte of the input); a thread's loads are all
+//           independent, so a warp keeps 8 .. 200 of them in flight;
+//   chroma  closed-form source maps of ChromaSubsampler.scala:52-65; case A resolves inside the granule (hold width
+//           hfe divides 4), held lines replay one pixel per row; case B (ImageCompressorTop.scala:52-58) maps every
+//           element through the full-size counters;
+//   store   a warp's 32 granules are consecutive output bytes: staged in the warp's shared-memory slot at the output's
+//           own offset modulo 16 and written as 16-byte st.global.cs aligned on the GLOBAL address (span_store).
+// Round 1's version -- one thread per slot, three divisions, byte loads and byte stores -- ran at 0.13 - 0.30 of the
+// copy peak.
 
-// Chroma source of full-resolution pixel (r, c): ChromaSubsampler.scala:52-65 in closed form.
-__device__ __forceinline__ void chroma_src_full(const KPlan& P, int r, int c, int& sr, int& sc) {
-  if (P.vf == 2 && (r & 1)) {
-    sr = r - 1;                 // nothing is sampled on an odd line: the latch still holds the last
-    sc = P.last_sample_col;     // sample point of the line above
-  } else {
-    sr = r;
-    sc = c - (c % P.hf);
-  }
+// three colour bytes (low three bytes of the result) at an arbitrary global address
+__device__ __forceinline__ uint32_t ldg_px(const uint8_t* p, const uint8_t* last_word) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* lo = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  if (((uint32_t)a & 3u) <= 1u) return __ldg(lo) >> (((uint32_t)a & 3u) * 8u);     // the three bytes sit in one word
+  const uint32_t* hi = reinterpret_cast<const uint32_t*>(min(reinterpret_cast<uintptr_t>(lo + 1), reinterpret_cast<uintptr_t>(last_word)));
+  return __funnelshift_r(__ldg(lo), __ldg(hi), ((uint32_t)a & 3u) * 8u);
 }
 
 // Chroma source, in *output grid* coordinates, when the chroma stage runs on the downsampled stream
 // but counts with the full W x H (ImageCompressorTop.scala:52-58).
 __device__ __forceinline__ void chroma_src_case_b(const KPlan& P, int ro, int co, int& sro, int& sco) {
   const uint32_t m = (uint32_t)ro * (uint32_t)P.Wo + (uint32_t)co;
-  const uint32_t col = m % (uint32_t)P.W;
-  const uint32_t line = (m / (uint32_t)P.W) % (uint32_t)P.H;
+  const uint32_t line = m / (uint32_t)P.W;           // m < Wo * Ho <= W * H: the `% H` of the counters never wraps
+  const uint32_t col = m - line * (uint32_t)P.W;
   uint32_t src;
   if (P.vf == 2 && (line & 1)) src = (line - 1) * (uint32_t)P.W + (uint32_t)P.last_sample_col;
   else src = m - (col % (uint32_t)P.hf);
   sro = (int)(src / (uint32_t)P.Wo);
-  sco = (int)(src % (uint32_t)P.Wo);
+  sco = (int)(src - (uint32_t)sro * (uint32_t)P.Wo);
 }
 
+constexpr uint32_t kGatherSlot = 32u * 16u + 32u;   // a warp's 32 granules of up to 16 bytes + alignment offset + read-ahead slack
 
-// One bundle slot; rows of a caller's sub-buffer need not be slot aligned.
-__device__ __forceinline__ void store_slot(uint8_t* orow, int co, uint32_t v, int slot_bytes) {
-  uint8_t* o = orow + (size_t)co * (size_t)slot_bytes;
-  if ((reinterpret_cast<uintptr_t>(o) & (uintptr_t)(slot_bytes - 1)) == 0) {
-    if (slot_bytes == 1) *o = (uint8_t)v;
-    else if (slot_bytes == 2) *reinterpret_cast<uint16_t*>(o) = (uint16_t)v;
-    else *reinterpret_cast<uint32_t*>(o) = v;
-  } else {
-    for (int i = 0; i < slot_bytes; ++i) o[i] = (uint8_t)(v >> (8 * i));
-  }
-}
+template <bool TRUNC, int FMT>
+__global__ void __launch_bounds__(128) csic_generic_kernel(const __grid_constant__ KPlan P) {
+  __shared__ __align__(16) uint8_t stage[4][kGatherSlot];
+  constexpr uint32_t kG = (FMT == KF_YCC888 || FMT == KF_RGB888) ? 12u : (FMT == KF_SLOT32 ? 16u : (FMT == KF_SLOT16 ? 8u : 4u));
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t Wo = (uint32_t)P.Wo, spr = (uint32_t)P.slots_per_row, gpr = (spr + 3u) >> 2;
+  const uint32_t n_rows = P.n_frames * (uint32_t)P.band_rows;
+  const uint32_t f = (uint32_t)P.f, ipb = (uint32_t)P.in_px_bytes, pxb = f * ipb;
+  const uint32_t hfe = P.case_b ? 1u : (uint32_t)max(1, P.hf / P.f);         // case A: hold width inside a granule, in output pixels
+  const bool avg = P.average && f > 1;
+  const uint32_t row_bytes = (FMT == KF_YCC888 || FMT == KF_RGB888) ? Wo * 3u : (FMT == KF_PLANAR ? Wo : spr * (uint32_t)P.slot_bytes);
+  // last aligned word that still holds a byte this launch may read: the end of the band's last input row (the host
+  // band path hands over buffers that hold only the band's rows)
+  const uint32_t last_out_row = (uint32_t)(P.row0 + P.band_rows - 1);
+  const uint32_t last_in_row = P.compact ? last_out_row : (avg ? (last_out_row + 1u) * f - 1u : last_out_row * f);
+  const uint8_t* last_word = reinterpret_cast<const uint8_t*>(
+      (reinterpret_cast<uintptr_t>(P.in) + (uint64_t)(P.n_frames - 1u) * P.in_frame_bytes + (uint64_t)last_in_row * P.in_row_bytes +
+       (uint64_t)(uint32_t)P.W * ipb - 1u) & ~(uintptr_t)3);
+  const uint32_t my = P.qmask & 0xFFu, mcb = (P.qmask >> 8) & 0xFFu, mcr = (P.qmask >> 16) & 0xFFu;
+  const uint32_t sbase = smem_u32(stage[warp]);
+  const int fsh = 31 - __clz(P.f);                                          // log2(f)
 
-// IdxT: uint32_t whenever the launch has fewer than 2^32 output slots (three 32-bit divisions per slot instead
-// of three 64-bit ones).
-template <bool TRUNC, typename IdxT>
-__global__ void __launch_bounds__(256) csic_generic_kernel(const __grid_constant__ KPlan P) {
-  const IdxT total = (IdxT)((uint64_t)P.n_frames * (uint64_t)P.band_rows * (uint64_t)P.slots_per_row);
-  for (IdxT idx = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (IdxT)gridDim.x * blockDim.x) {
-    const int co = (int)(idx % (uint32_t)P.slots_per_row);
-    const IdxT t = idx / (uint32_t)P.slots_per_row;
-    const int ro = P.row0 + (int)(t % (uint32_t)P.band_rows);
-    const uint64_t k = (uint64_t)(t / (uint32_t)P.band_rows);
-    uint8_t* orow = P.out + k * P.out_frame_bytes + (size_t)ro * P.out_row_bytes;
-    if (co >= P.Wo) {   // BUNDLE row padding: zero slots
-      store_slot(orow, co, 0u, P.slot_bytes);
-      continue;
+  for (uint32_t R = blockIdx.x; R < n_rows; R += gridDim.x) {
+    const uint32_t k = R / (uint32_t)P.band_rows, ro = (uint32_t)P.row0 + (R - k * (uint32_t)P.band_rows);
+    const uint8_t* frame = P.in + (uint64_t)k * P.in_frame_bytes;
+    uint8_t* fout = P.out + (uint64_t)k * P.out_frame_bytes;
+    uint8_t* orow = fout + (uint64_t)ro * P.out_row_bytes;
+    // stored row of a full-resolution row (KPlan::compact: only every f-th row is stored, DECIMATE reads no other)
+    auto in_row = [&](uint32_t r) { return frame + (uint64_t)(P.compact ? (r >> fsh) : r) * P.in_row_bytes; };
+    // case A, DECIMATE: the row's own pixels and -- on a held line (odd full-resolution line of 4:2:0 / 4:1:0, f == 1
+    // only) -- the one pixel whose chroma the whole row replays
+    const uint8_t* yrow = in_row(ro * f);
+    const bool held_row = !P.case_b && !avg && P.vf == 2 && ((ro * f) & 1u);
+    uint32_t hxb = 0, hxr = 0;
+    if (held_row) {
+      const uint32_t hp = ldg_px(in_row(ro * f - 1u) + (uint32_t)P.last_sample_col * ipb, last_word);
+      hxb = fwd_nc16<TRUNC>(hp, P.coef_ncb); hxr = fwd_nc16<TRUNC>(hp, P.coef_ncr);
     }
-    const uint8_t* frame = P.in + k * P.in_frame_bytes;
-    const int f = P.f;
-    int y, cb, cr;
-    if (!P.average || f == 1) {
-      const int yr = ro * f, yc = co * f;
-      int sr, sc;
-      if (!P.case_b) {
-        chroma_src_full(P, yr, yc, sr, sc);
-      } else {
-        int sro, sco;
-        chroma_src_case_b(P, ro, co, sro, sco);
-        sr = sro * f;
-        sc = sco * f;
-      }
-      if (P.compact) {   // only every f-th row is stored; DECIMATE with f > 1 never reads another one
-        y = (int)(fwd_y16(load_px(frame, P.in_row_bytes, yr / f, yc, P.in_px_bytes), P.coef_y) >> 8);
-        sr /= f;
-      } else {
-        y = (int)(fwd_y16(load_px(frame, P.in_row_bytes, yr, yc, P.in_px_bytes), P.coef_y) >> 8);
-      }
-      const uint32_t pc = load_px(frame, P.in_row_bytes, sr, sc, P.in_px_bytes);
-      cb = 255 - (int)(fwd_nc16<TRUNC>(pc, P.coef_ncb) >> 8);
-      cr = 255 - (int)(fwd_nc16<TRUNC>(pc, P.coef_ncr) >> 8);
-      y = (y >> P.sy) << P.sy;
-      cb = (cb >> P.scb) << P.scb;
-      cr = (cr >> P.scr) << P.scr;
-    } else {
-      // AVERAGE extension: mean over the f x f block of the stream entering the spatial stage.
-      const int qy = P.quant_first ? P.sy : 0, qcb = P.quant_first ? P.scb : 0, qcr = P.quant_first ? P.scr : 0;
-      int bro = ro, bco = co;   // block supplying chroma
-      if (P.case_b) chroma_src_case_b(P, ro, co, bro, bco);
-      int sy_ = 0, scb_ = 0, scr_ = 0;
-      for (int dr = 0; dr < f; ++dr)
-        for (int dc = 0; dc < f; ++dc) {
-          const int r = ro * f + dr, c = co * f + dc;
-          int yy = (int)(fwd_y16(load_px(frame, P.in_row_bytes, r, c, P.in_px_bytes), P.coef_y) >> 8);
-          sy_ += (yy >> qy) << qy;
-          int sr, sc;
-          if (!P.case_b) {
-            chroma_src_full(P, r, c, sr, sc);   // chroma stage ran at full resolution, before pooling
+    for (uint32_t g0 = warp * 32u; g0 < gpr; g0 += blockDim.x) {            // warp uniform
+      const uint32_t g = g0 + lane, c0 = 4u * g;
+      uint8_t* og = orow + (size_t)g0 * kG;                                  // first output byte of this warp's group
+      const uint32_t st = sbase + ((uint32_t)reinterpret_cast<uintptr_t>(og) & 12u);
+      if (g < gpr) {
+        uint32_t y[4], cb[4], cr[4];                                         // final channel values (quantised)
+        if (!avg) {
+          uint32_t p[4], xb[4], xr[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) p[j] = ldg_px(yrow + (size_t)min(c0 + j, Wo - 1u) * pxb, last_word);
+          if (held_row) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { xb[j] = hxb; xr[j] = hxr; }
+          } else if (!P.case_b) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                                    // sample where j % hfe == 0, hold in between
+              if (j == 0 || (uint32_t)j % hfe == 0u) { xb[j] = fwd_nc16<TRUNC>(p[j], P.coef_ncb); xr[j] = fwd_nc16<TRUNC>(p[j], P.coef_ncr); }
+              else { xb[j] = xb[j - 1]; xr[j] = xr[j - 1]; }
+            }
           } else {
-            sr = bro * f + dr;                  // pooling first: own chroma of the source block
-            sc = bco * f + dc;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              int sro, sco;
+              chroma_src_case_b(P, (int)ro, (int)min(c0 + j, Wo - 1u), sro, sco);
+              const uint32_t pc = ldg_px(in_row((uint32_t)sro * f) + (size_t)sco * pxb, last_word);
+              xb[j] = fwd_nc16<TRUNC>(pc, P.coef_ncb); xr[j] = fwd_nc16<TRUNC>(pc, P.coef_ncr);
+            }
           }
-          const uint32_t pc = load_px(frame, P.in_row_bytes, sr, sc, P.in_px_bytes);
-          const int b0 = 255 - (int)(fwd_nc16<TRUNC>(pc, P.coef_ncb) >> 8);
-          const int r0 = 255 - (int)(fwd_nc16<TRUNC>(pc, P.coef_ncr) >> 8);
-          scb_ += (b0 >> qcb) << qcb;
-          scr_ += (r0 >> qcr) << qcr;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            y[j] = (fwd_y16(p[j], P.coef_y) >> 8) & my;
+            cb[j] = (~(xb[j] >> 8)) & mcb;
+            cr[j] = (~(xr[j] >> 8)) & mcr;
+          }
+        } else {
+          // AVERAGE extension: mean over the f x f block of the stream entering the spatial stage, round half up; the
+          // quantiser before or after the mean as op[] says
+          const uint32_t qy = P.quant_first ? my : 0xFFu, qb = P.quant_first ? mcb : 0xFFu, qr = P.quant_first ? mcr : 0xFFu;
+          const uint32_t half = (f * f) >> 1, sh = 2u * (uint32_t)fsh;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t co = min(c0 + j, Wo - 1u);
+            int bro = (int)ro, bco = (int)co;                                // block supplying chroma
+            if (P.case_b) chroma_src_case_b(P, (int)ro, (int)co, bro, bco);
+            uint32_t sy = 0, sb = 0, sr = 0;
+            for (uint32_t dr = 0; dr < f; ++dr) {
+              const uint8_t* rp = in_row(ro * f + dr) + (size_t)co * pxb;
+              // chroma-first: an odd full-resolution line replays (line - 1, lastSampleCol); pooling-first: the own
+              // chroma of every pixel of the source block
+              const bool hl = !P.case_b && P.vf == 2 && (dr & 1u);
+              const uint8_t* cp = P.case_b ? in_row((uint32_t)bro * f + dr) + (size_t)bco * pxb
+                                           : (hl ? in_row(ro * f + dr - 1u) + (uint32_t)P.last_sample_col * ipb : rp);
+              uint32_t xb = 0, xr = 0;
+              for (uint32_t dc = 0; dc < f; ++dc) {
+                const uint32_t pv = ldg_px(rp + dc * ipb, last_word);
+                sy += (fwd_y16(pv, P.coef_y) >> 8) & qy;
+                if (P.case_b || (!hl && ((co * f + dc) % (uint32_t)P.hf) == 0u) || (hl && dc == 0u)) {
+                  const uint32_t pc = P.case_b ? ldg_px(cp + dc * ipb, last_word) : (hl ? ldg_px(cp, last_word) : pv);
+                  xb = (~(fwd_nc16<TRUNC>(pc, P.coef_ncb) >> 8)) & qb;
+                  xr = (~(fwd_nc16<TRUNC>(pc, P.coef_ncr) >> 8)) & qr;
+                } else if (!hl && dc == 0u) {
+                  // the block starts inside a hold group (hf > f): its sample point lies left of the block
+                  const uint32_t sc = (co * f) - ((co * f) % (uint32_t)P.hf);
+                  const uint32_t pc = ldg_px(in_row(ro * f + dr) + (size_t)sc * ipb, last_word);
+                  xb = (~(fwd_nc16<TRUNC>(pc, P.coef_ncb) >> 8)) & qb;
+                  xr = (~(fwd_nc16<TRUNC>(pc, P.coef_ncr) >> 8)) & qr;
+                }
+                sb += xb & 0xFFu; sr += xr & 0xFFu;
+              }
+            }
+            y[j] = (sy + half) >> sh; cb[j] = (sb + half) >> sh; cr[j] = (sr + half) >> sh;
+            if (!P.quant_first) { y[j] &= my; cb[j] &= mcb; cr[j] &= mcr; }
+          }
         }
-      const int sh = 2 * (31 - __clz(f)), half = (f * f) >> 1;
-      y = (sy_ + half) >> sh;
-      cb = (scb_ + half) >> sh;
-      cr = (scr_ + half) >> sh;
-      if (!P.quant_first) {
-        y = (y >> P.sy) << P.sy;
-        cb = (cb >> P.scb) << P.scb;
-        cr = (cr >> P.scr) << P.scr;
+        // ---- pack the granule into the warp's staging slot ----
+        const uint32_t so = st + kG * lane;
+        if (FMT == KF_YCC888 || FMT == KF_RGB888) {
+          uint32_t v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            v[j] = FMT == KF_RGB888 ? inverse_rgb((int)y[j], (int)cb[j], (int)cr[j]) : (y[j] | (cb[j] << 8) | (cr[j] << 16));
+          uint32_t w0, w1, w2;
+          pack_rgb_granule(v, w0, w1, w2);
+          sts32(so, w0); sts32(so + 4u, w1); sts32(so + 8u, w2);
+        } else if (FMT == KF_PLANAR) {
+          sts32(so, y[0] | (y[1] << 8) | (y[2] << 16) | (y[3] << 24));
+          if (ro % (uint32_t)P.planar_vs == 0u) {                            // surviving chroma sample points of this row
+            const size_t crow = (size_t)(ro / (uint32_t)P.planar_vs) * (size_t)P.planar_cw;
+#pragma unroll
+            for (uint32_t j = 0; j < 4u; ++j)
+              if ((j & ((uint32_t)P.planar_hs - 1u)) == 0u && c0 + j < Wo) {
+                fout[P.planar_cb_off + crow + (c0 + j) / (uint32_t)P.planar_hs] = (uint8_t)cb[j];
+                fout[P.planar_cr_off + crow + (c0 + j) / (uint32_t)P.planar_hs] = (uint8_t)cr[j];
+              }
+          }
+        } else {
+          uint32_t v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            v[j] = (c0 + j < Wo) ? ((y[j] >> P.sy) << (P.cb_bits + P.cr_bits)) | ((cb[j] >> P.scb) << P.cr_bits) | (cr[j] >> P.scr)
+                                 : 0u;                                        // BUNDLE row padding: zero slots
+          if (FMT == KF_SLOT32) { sts32(so, v[0]); sts32(so + 4u, v[1]); sts32(so + 8u, v[2]); sts32(so + 12u, v[3]); }
+          else if (FMT == KF_SLOT16) { sts32(so, v[0] | (v[1] << 16)); sts32(so + 4u, v[2] | (v[3] << 16)); }
+          else sts32(so, v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
+        }
       }
-    }
-    if (P.kformat == KF_YCC888) {
-      uint8_t* o = orow + (size_t)co * 3;
-      o[0] = (uint8_t)y; o[1] = (uint8_t)cb; o[2] = (uint8_t)cr;
-    } else if (P.kformat == KF_PLANAR) {
-      orow[co] = (uint8_t)y;                        // Y plane; out_row_bytes == Wo
-      if (ro % P.planar_vs == 0 && co % P.planar_hs == 0) {   // a surviving chroma sample point
-        uint8_t* fo = P.out + k * P.out_frame_bytes;
-        const size_t ci = (size_t)(ro / P.planar_vs) * (size_t)P.planar_cw + (size_t)(co / P.planar_hs);
-        fo[P.planar_cb_off + ci] = (uint8_t)cb;
-        fo[P.planar_cr_off + ci] = (uint8_t)cr;
-      }
-    } else if (P.kformat == KF_RGB888) {
-      const uint32_t v = inverse_rgb(y, cb, cr);
-      uint8_t* o = orow + (size_t)co * 3;
-      o[0] = (uint8_t)v; o[1] = (uint8_t)(v >> 8); o[2] = (uint8_t)(v >> 16);
-    } else {
-      const uint32_t v = ((uint32_t)(y >> P.sy) << (P.cb_bits + P.cr_bits)) |
-                         ((uint32_t)(cb >> P.scb) << P.cr_bits) | (uint32_t)(cr >> P.scr);
-      store_slot(orow, co, v, P.slot_bytes);
+      __syncwarp();
+      span_store(og, st, min(32u * kG, row_bytes - g0 * kG), lane, 32u);   // the row's last granule may be partial
+      __syncwarp();
     }
   }
 }
 
-// Decoder of the PLANAR format: one thread per output pixel, chroma fetched with the reference's replay rule
-// (ChromaSubsampler.scala:52-65) expressed in output coordinates (chroma before spatial, or f == 1).
-__global__ void __launch_bounds__(256) csic_expand_planar_kernel(const __grid_constant__ KPlan P, const uint8_t* __restrict__ planar,
-                                                                 uint8_t* __restrict__ out, int to_rgb) {
-  const uint64_t total = (uint64_t)P.n_frames * (uint64_t)P.Ho * (uint64_t)P.Wo;
-  const int last_o = P.last_sample_col / P.f;        // last sample column of a line, in output pixels
-  for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (uint64_t)gridDim.x * blockDim.x) {
-    const int co = (int)(idx % (uint32_t)P.Wo);
-    const uint64_t t = idx / (uint32_t)P.Wo;
-    const int ro = (int)(t % (uint32_t)P.Ho);
-    const uint64_t k = t / (uint32_t)P.Ho;
-    const uint8_t* f = planar + k * P.out_frame_bytes;
-    const bool held = P.vf == 2 && ((ro * P.f) & 1);   // only possible for f == 1
-    const int sr = (held ? ro - 1 : ro) / P.planar_vs;
-    const int sc = (held ? last_o : co - co % P.planar_hs) / P.planar_hs;
-    const size_t ci = (size_t)sr * (size_t)P.planar_cw + (size_t)sc;
-    const int y = f[(size_t)ro * P.Wo + co], cb = f[P.planar_cb_off + ci], cr = f[P.planar_cr_off + ci];
-    uint8_t* o = out + (k * (uint64_t)P.Ho * P.Wo + (uint64_t)ro * P.Wo + co) * 3;
-    if (to_rgb) {
-      const uint32_t v = inverse_rgb(y, cb, cr);
-      o[0] = (uint8_t)v; o[1] = (uint8_t)(v >> 8); o[2] = (uint8_t)(v >> 16);
-    } else {
-      o[0] = (uint8_t)y; o[1] = (uint8_t)cb; o[2] = (uint8_t)cr;
+// Decoder of the PLANAR format for ANY width and any alignment of the planes and of the output: chroma fetched with the
+// reference's replay rule (ChromaSubsampler.scala:52-65) expressed in output coordinates (chroma before spatial, or
+// f == 1).  One CTA per output row; the only division (frame / row split) and everything row-dependent happen once
+// per row.  A thread decodes one granule of four pixels (the row's last granule may be partial):
+//   load   Y bytes of a granule are one word at an arbitrary byte address = two aligned LDG.32 and a funnel shift (the
+//          second word is never fetched beyond the last word that holds a byte of the buffer); chroma samples likewise
+//          (4:4:4) or one / two byte loads (hs = 4 / 2);
+//   store  a warp's 32 granules are 384 consecutive output bytes: they go to the warp's shared-memory slot at the
+//          output's own offset modulo 16 (rounded down to a word) and leave as 16-byte st.global.cs aligned on the
+//          GLOBAL address (span_store: LDS.128 + at most four funnel shifts), head / tail bytes one by one.
+// Before: one thread per pixel, three divisions, three byte loads and three byte stores each -- 0.10 of the copy peak.
+__device__ __forceinline__ uint32_t ldg_word_at(const uint8_t* p, const uint8_t* last_word) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* lo = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  if (((uint32_t)a & 3u) == 0u) return __ldg(lo);
+  const uint32_t* hi = reinterpret_cast<const uint32_t*>(min(reinterpret_cast<uintptr_t>(lo + 1), reinterpret_cast<uintptr_t>(last_word)));
+  return __funnelshift_r(__ldg(lo), __ldg(hi), ((uint32_t)a & 3u) * 8u);
+}
+
+__global__ void __launch_bounds__(128) csic_expand_planar_any_kernel(const __grid_constant__ KPlan P, const uint8_t* __restrict__ planar,
+                                                                     uint8_t* __restrict__ out, int to_rgb) {
+  __shared__ __align__(16) uint8_t stage[4][384 + 32];               // per warp: 32 granules + alignment offset + read-ahead slack
+  const uint32_t Wo = (uint32_t)P.Wo, gpr = (Wo + 3u) >> 2, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t n_rows = P.n_frames * (uint32_t)P.Ho;
+  const int last_c = (P.last_sample_col / P.f) / P.planar_hs;       // plane column of a line's last sample point
+  const uint32_t hs_sh = P.planar_hs == 4 ? 2u : (P.planar_hs == 2 ? 1u : 0u), vs_sh = P.planar_vs == 2 ? 1u : 0u;
+  const bool vhold = P.vf == 2 && P.f == 1;                         // odd lines replay the line above (f == 1 only)
+  // last aligned word that still holds a byte of the planar buffer (loads never go past it)
+  const uint8_t* last_word = reinterpret_cast<const uint8_t*>(
+      (reinterpret_cast<uintptr_t>(planar) + (uint64_t)P.n_frames * P.out_frame_bytes - 1u) & ~(uintptr_t)3);
+  const uint32_t sbase = smem_u32(stage[warp]);
+  for (uint32_t R = blockIdx.x; R < n_rows; R += gridDim.x) {
+    const uint32_t k = R / (uint32_t)P.Ho, ro = R - k * (uint32_t)P.Ho;
+    const uint8_t* fr = planar + (uint64_t)k * P.out_frame_bytes;
+    const uint8_t* yrow = fr + (size_t)ro * Wo;
+    const bool held = vhold && (ro & 1u);
+    const size_t crow = (size_t)((held ? ro - 1u : ro) >> vs_sh) * (size_t)P.planar_cw;
+    const uint8_t* cbp = fr + P.planar_cb_off + crow;
+    const uint8_t* crp = fr + P.planar_cr_off + crow;
+    uint8_t* orow = out + (uint64_t)R * Wo * 3u;
+    uint32_t hcb = 0, hcr = 0;
+    if (held) { hcb = (uint32_t)__ldg(cbp + last_c) * 0x01010101u; hcr = (uint32_t)__ldg(crp + last_c) * 0x01010101u; }
+    for (uint32_t g0 = warp * 32u; g0 < gpr; g0 += blockDim.x) {    // warp uniform
+      const uint32_t g = g0 + lane;
+      uint8_t* og = orow + (size_t)g0 * 12u;                          // first output byte of this warp's group
+      const uint32_t st = sbase + ((uint32_t)reinterpret_cast<uintptr_t>(og) & 12u);
+      if (g < gpr) {
+        const uint32_t yw = ldg_word_at(yrow + 4u * g, last_word);
+        uint32_t cbw, crw;                                            // chroma of the four pixels as bytes
+        if (held) {
+          cbw = hcb; crw = hcr;
+        } else if (hs_sh == 0) {
+          cbw = ldg_word_at(cbp + 4u * g, last_word); crw = ldg_word_at(crp + 4u * g, last_word);
+        } else if (hs_sh == 1) {                                      // two samples, each held for two pixels
+          const uint32_t c1 = min(2u * g + 1u, (uint32_t)P.planar_cw - 1u);
+          const uint32_t b2 = (uint32_t)__ldg(cbp + 2u * g) | ((uint32_t)__ldg(cbp + c1) << 8);
+          const uint32_t r2 = (uint32_t)__ldg(crp + 2u * g) | ((uint32_t)__ldg(crp + c1) << 8);
+          cbw = __byte_perm(b2, 0, 0x1100); crw = __byte_perm(r2, 0, 0x1100);
+        } else {
+          cbw = (uint32_t)__ldg(cbp + g) * 0x01010101u; crw = (uint32_t)__ldg(crp + g) * 0x01010101u;
+        }
+        uint32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int y = (int)((yw >> (8 * j)) & 0xFFu), cb = (int)((cbw >> (8 * j)) & 0xFFu), cr = (int)((crw >> (8 * j)) & 0xFFu);
+          v[j] = to_rgb ? inverse_rgb(y, cb, cr) : ((uint32_t)y | ((uint32_t)cb << 8) | ((uint32_t)cr << 16));
+        }
+        uint32_t w0, w1, w2;
+        pack_rgb_granule(v, w0, w1, w2);
+        sts32(st + 12u * lane, w0); sts32(st + 12u * lane + 4u, w1); sts32(st + 12u * lane + 8u, w2);
+      }
+      __syncwarp();
+      const uint32_t bytes = min(32u * 12u, Wo * 3u - g0 * 12u);      // the row's last granule may hold fewer than four pixels
+      span_store(og, st, bytes, lane, 32u);
+      __syncwarp();
     }
   }
 }
@@ -348,12 +453,12 @@ __global__ void __launch_bounds__(128) csic_expand_planar16_kernel(const __grid_
   }
 }
 
-int launch_expand_planar(const KPlan& k, const uint8_t* planar, uint8_t* out, int to_rgb, void* stream) {
+int launch_expand_planar(const KPlan& k, const uint8_t* planar, uint8_t* out, int to_rgb, int sm_count, void* stream) {
   const uint64_t total = (uint64_t)k.n_frames * (uint64_t)k.Ho * (uint64_t)k.Wo;
   if (total == 0) return (int)cudaSuccess;
   const uint64_t n_rows = (uint64_t)k.n_frames * (uint64_t)k.Ho;
   if (k.Wo % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0 && n_rows < (1ull << 32)) {
-    const unsigned blocks = (unsigned)std::min<uint64_t>(n_rows, (uint64_t)148 * 16);
+    const unsigned blocks = (unsigned)std::min<uint64_t>(n_rows, (uint64_t)sm_count * 16);
     const unsigned threads = (unsigned)std::min<uint32_t>(128u, (((uint32_t)k.Wo >> 2) + 31u) & ~31u);
     const uint32_t cw_bytes = (uint32_t)k.planar_cw;              // chroma plane rows must keep the vector loads aligned
     const bool planes16 = (reinterpret_cast<uintptr_t>(planar) & 15u) == 0 && k.out_frame_bytes % 16 == 0 &&
@@ -368,24 +473,38 @@ int launch_expand_planar(const KPlan& k, const uint8_t* planar, uint8_t* out, in
       csic_expand_planar_rows_kernel<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(k, planar, out, to_rgb);
     return (int)cudaGetLastError();
   }
-  const uint64_t blocks = std::min<uint64_t>((total + 255) / 256, (uint64_t)148 * 64);
-  csic_expand_planar_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(k, planar, out, to_rgb);
+  if (n_rows >= (1ull << 32)) return (int)cudaErrorInvalidValue;
+  const unsigned threads = (unsigned)std::min<uint32_t>(128u, ((((uint32_t)k.Wo + 3u) >> 2) + 31u) & ~31u);
+  const unsigned blocks = (unsigned)std::min<uint64_t>(n_rows, (uint64_t)sm_count * (2048u / threads));
+  csic_expand_planar_any_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(k, planar, out, to_rgb);
   return (int)cudaGetLastError();
 }
 
-int launch_generic(const KPlan& k, void* stream) {
-  const uint64_t total = (uint64_t)k.n_frames * (uint64_t)k.band_rows * (uint64_t)k.slots_per_row;
-  if (total == 0) return (int)cudaSuccess;
-  const uint64_t blocks = std::min<uint64_t>((total + 255) / 256, (uint64_t)148 * 64);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (total + blocks * 256 < (1ull << 32)) {
-    if (k.trunc) csic_generic_kernel<true, uint32_t><<<(unsigned)blocks, 256, 0, st>>>(k);
-    else csic_generic_kernel<false, uint32_t><<<(unsigned)blocks, 256, 0, st>>>(k);
-  } else {
-    if (k.trunc) csic_generic_kernel<true, uint64_t><<<(unsigned)blocks, 256, 0, st>>>(k);
-    else csic_generic_kernel<false, uint64_t><<<(unsigned)blocks, 256, 0, st>>>(k);
-  }
+namespace {
+template <int FMT>
+int launch_generic_fmt(const KPlan& k, unsigned blocks, unsigned threads, cudaStream_t st) {
+  if (k.trunc) csic_generic_kernel<true, FMT><<<blocks, threads, 0, st>>>(k);
+  else csic_generic_kernel<false, FMT><<<blocks, threads, 0, st>>>(k);
   return (int)cudaGetLastError();
+}
+}  // namespace
+
+int launch_generic(const KPlan& k, int sm_count, void* stream) {
+  const uint64_t n_rows = (uint64_t)k.n_frames * (uint64_t)k.band_rows;
+  if (n_rows == 0 || k.slots_per_row == 0) return (int)cudaSuccess;
+  if (n_rows >= (1ull << 32)) return (int)cudaErrorInvalidValue;
+  const uint32_t gpr = ((uint32_t)k.slots_per_row + 3u) >> 2;
+  const unsigned threads = (unsigned)std::min<uint32_t>(128u, (gpr + 31u) & ~31u);
+  const unsigned blocks = (unsigned)std::min<uint64_t>(n_rows, (uint64_t)sm_count * (2048u / threads));
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (k.kformat) {
+    case KF_YCC888: return launch_generic_fmt<KF_YCC888>(k, blocks, threads, st);
+    case KF_RGB888: return launch_generic_fmt<KF_RGB888>(k, blocks, threads, st);
+    case KF_SLOT8: return launch_generic_fmt<KF_SLOT8>(k, blocks, threads, st);
+    case KF_SLOT16: return launch_generic_fmt<KF_SLOT16>(k, blocks, threads, st);
+    case KF_PLANAR: return launch_generic_fmt<KF_PLANAR>(k, blocks, threads, st);
+    default: return launch_generic_fmt<KF_SLOT32>(k, blocks, threads, st);
+  }
 }
 
 // ================================================================================================

@@ -82,9 +82,20 @@ __device__ __forceinline__ void load_row_part(uint32_t a, uint32_t (&p)[4 * F]) 
   }
 }
 
-template <int F, int FMT, bool IN4, int HF, bool TRUNC>
+// MODE resolves the per-launch flags at compile time for the common pipelines, so that the inner loop carries no
+// uniform branches on them (ncu, 4K 2x2: 27 of the 325 warp-instructions per granule were such branches and their
+// predicate logic):  0 = every flag read at run time (quantiser in front of the pooling, or TRUNC rounding);
+// 1..3 = no quantiser in front (complement-domain sums): 1 chroma stage first, 4:2:0 / 4:1:0 (odd lines replay a
+// held pair); 2 chroma stage first, no vertical hold; 3 pooling first (the application's default order).
+template <int F, int FMT, bool IN4, int HF, bool TRUNC, int MODE>
 __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t* __restrict__ out_g,
-                                          const PoolMeta* __restrict__ meta, const PoolConst& C) {
+                                          const PoolMeta* __restrict__ meta, const PoolConst& CC) {
+  struct Flags {
+    bool linear, linear_y, pool_first, vhold;
+  };
+  const Flags C_f = MODE == 0 ? Flags{CC.linear, CC.linear_y, CC.pool_first, CC.vhold}
+                              : Flags{true, F == 2, MODE == 3, MODE == 1};
+  const PoolConst& C = CC;
   constexpr uint32_t kGranBytes = (IN4 ? 16u : 12u) * F;     // one row part of a granule
   constexpr int kShift = (F == 2) ? 2 : (F == 4 ? 4 : 6);    // log2(F*F)
   constexpr int kHalf = (F * F) / 2;
@@ -109,8 +120,9 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
     uint32_t held_pair = 0;
     if (q < n) {
     const uint32_t base = in_s + row * (F * C.seg_row_bytes) + rem * kGranBytes;
-    held_pair = C.pool_first ? meta->held_addr[row] : 0u;   // bit 31 | pooled Cb << 8 | pooled Cr
-#pragma unroll 1
+    held_pair = C_f.pool_first ? meta->held_addr[row] : 0u;   // bit 31 | pooled Cb << 8 | pooled Cr
+    // two row parts per trip: `dr & 1` (is this an odd, i.e. held, line?) is then a compile-time value
+#pragma unroll 2
     for (int dr = (int)(sub * (F / kSplit)); dr < (int)((sub + 1u) * (F / kSplit)); ++dr) {
       // 8x8: the row part is taken in two halves of two output pixels each (16 pixels in registers instead of 32)
 #pragma unroll
@@ -125,7 +137,7 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
         uint32_t d[F];
 #pragma unroll
         for (int i = 0; i < F; ++i) d[i] = fwd_y16(p[o * F + i], C.coef_y);
-        if (C.linear_y) {          // no quantiser in front: byte 1 of every result goes straight into the sum (FMA pipe)
+        if (C_f.linear_y) {          // no quantiser in front: byte 1 of every result goes straight into the sum (FMA pipe)
 #pragma unroll
           for (int i = 0; i < F; ++i) ay[ob + o] = (int)dp4a_uu(d[i], 1u << 8, (uint32_t)ay[ob + o]);
         } else if (F == 2) {
@@ -140,11 +152,11 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
           }
         }
       }
-      if (C.linear) {
+      if (C_f.linear) {
         // No quantiser in front of the pooling: the chroma value is 255 - byte1(x) (x = fwd_nc16 < 65536), so the sums are
         // taken in the complement domain -- weight * byte1(x) accumulated by ONE dp4a per sample and channel (coefficient
         // `weight` on byte 1), on the FMA pipe instead of four ALU-pipe instructions -- and flipped once after the loop.
-        if (C.pool_first) {
+        if (C_f.pool_first) {
           // every pixel's own chroma is pooled; only output pixels on a sample column are needed (the others replay
           // them after the pooling), and rows of an odd counter line replay a pooled pair the producer supplies
           if (!held_pair) {
@@ -156,7 +168,7 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
               }
             }
           }
-        } else if (C.vhold && (dr & 1)) {
+        } else if (C_f.vhold && (dr & 1)) {
           // nothing is sampled on an odd line: every pixel replays the last sample of the line above
           if (hh == 0) {
           const uint32_t ha = meta->held_addr[row * (F / 2) + (uint32_t)(dr >> 1)];
@@ -184,7 +196,7 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
             }
           }
         }
-      } else if (C.pool_first) {
+      } else if (C_f.pool_first) {
         if (!held_pair) {
 #pragma unroll
           for (int i = 0; i < NO * F; ++i) {
@@ -194,7 +206,7 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
             }
           }
         }
-      } else if (C.vhold && (dr & 1)) {
+      } else if (C_f.vhold && (dr & 1)) {
         if (hh == 0) {
         const uint32_t ha = meta->held_addr[row * (F / 2) + (uint32_t)(dr >> 1)];
         const uint32_t hp = lds8(ha) | (lds8(ha + 1) << 8) | (lds8(ha + 2) << 16);
@@ -230,7 +242,7 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
       }
     }
     if (q < n && sub == 0u) {
-    if (C.linear) {                    // back from the complement domain: F*F samples of weight 1 each
+    if (C_f.linear) {                    // back from the complement domain: F*F samples of weight 1 each
 #pragma unroll
       for (int o = 0; o < 4; ++o) { ab[o] = 255 * F * F - ab[o]; ar[o] = 255 * F * F - ar[o]; }
     }
@@ -241,7 +253,7 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
       cb[o] = (uint32_t)((ab[o] + kHalf) >> kShift) & C.post_cb;
       cr[o] = (uint32_t)((ar[o] + kHalf) >> kShift) & C.post_cr;
     }
-    if (C.pool_first) {                // the chroma stage on the pooled stream (ChromaSubsampler.scala:57-65)
+    if (C_f.pool_first) {                // the chroma stage on the pooled stream (ChromaSubsampler.scala:57-65)
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
         if (held_pair) { cb[o] = (held_pair >> 8) & 0xFFu & C.post_cb; cr[o] = held_pair & 0xFFu & C.post_cr; }
@@ -294,8 +306,11 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
   }
 }
 
+// Register budget instead of launch bounds: four CTAs per SM of 288 threads (2x2) need <= 56 registers, of 224 threads
+// (4x4, 8x8: six consumer warps) <= 73.  With __launch_bounds__(544) alone ptxas settled on 56 for every factor and
+// spilled 24-60 bytes per thread in the 4x4 / 8x8 loops; at 72 nothing spills.
 template <int F, int FMT, bool IN4>
-__global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_pool_kernel(const __grid_constant__ KPlan P) {
+__global__ void __maxnreg__(F == 2 ? 56 : 72) csic_pool_kernel(const __grid_constant__ KPlan P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t tid = threadIdx.x;
   const uint32_t NC = blockDim.x - 32u;
@@ -432,6 +447,8 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_pool_kernel(con
     C.linear_y = F == 2 && C.pre_y == 0xFFu;   // B200: pays for 2x2 only (4x4: the PRMT gather + one dp4a is cheaper)
   }
   const int hf = P.hf;
+  // which specialisation of pool_tile (see its MODE parameter)
+  const int mode = C.trunc ? 4 : ((C.linear && C.pre_y == 0xFFu) ? (C.pool_first ? 3 : (C.vhold ? 1 : 2)) : 0);
 
   for (uint32_t i = 0; i < n_my; ++i) {
     const uint32_t s = i % S;
@@ -440,14 +457,18 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_pool_kernel(con
     const uint32_t out_s = sbase + P.out_buf_off;     // 12-byte formats: one 384-byte staging slot per consumer warp
     const PoolMeta* m = reinterpret_cast<const PoolMeta*>(smem + P.meta_off) + s;
     uint8_t* out_g = reinterpret_cast<uint8_t*>(m->out_base);
-    if (C.trunc) {
-      if (hf == 1) pool_tile<F, FMT, IN4, 1, true>(in_s, out_s, out_g, m, C);
-      else if (hf == 2) pool_tile<F, FMT, IN4, 2, true>(in_s, out_s, out_g, m, C);
-      else pool_tile<F, FMT, IN4, 4, true>(in_s, out_s, out_g, m, C);
-    } else {
-      if (hf == 1) pool_tile<F, FMT, IN4, 1, false>(in_s, out_s, out_g, m, C);
-      else if (hf == 2) pool_tile<F, FMT, IN4, 2, false>(in_s, out_s, out_g, m, C);
-      else pool_tile<F, FMT, IN4, 4, false>(in_s, out_s, out_g, m, C);
+    switch (mode) {
+#define CSIC_POOL_HF(TR, MD)                                                            \
+      if (hf == 1) pool_tile<F, FMT, IN4, 1, TR, MD>(in_s, out_s, out_g, m, C);         \
+      else if (hf == 2) pool_tile<F, FMT, IN4, 2, TR, MD>(in_s, out_s, out_g, m, C);    \
+      else pool_tile<F, FMT, IN4, 4, TR, MD>(in_s, out_s, out_g, m, C);                 \
+      break;
+      case 1: CSIC_POOL_HF(false, 1)
+      case 2: CSIC_POOL_HF(false, 2)
+      case 3: CSIC_POOL_HF(false, 3)
+      case 4: CSIC_POOL_HF(true, 0)
+      default: CSIC_POOL_HF(false, 0)
+#undef CSIC_POOL_HF
     }
 
     __syncwarp();

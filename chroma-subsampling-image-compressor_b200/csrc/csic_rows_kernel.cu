@@ -73,6 +73,7 @@ struct LoopConst {
   uint32_t gran_per_row;
   uint32_t out_pitch, out_dense, ragged, Wo;  // pitched / padded output rows (see KPlan)
   uint32_t pl_cb_off, pl_cr_off, pl_crow_bytes, pl_vs_shift;   // PLANAR staging: region offsets, bytes per chroma row
+  uint32_t st_mode;                          // bundle stores: 0 st.global.cs (streaming), 1 default write-back, 2 st.global.cg
   uint32_t nthreads;                         // consumer threads per CTA
   uint32_t row0_of_thread, rem0_of_thread;   // threadIdx.x / gran_per_row, threadIdx.x % gran_per_row
   uint32_t drow, drem;                       // blockDim.x / gran_per_row, blockDim.x % gran_per_row
@@ -102,6 +103,28 @@ __device__ __forceinline__ void tile_loop(uint32_t in_s, uint32_t out_s, uint8_t
     row += C.drow;
     rem += C.drem;
     if (rem >= C.gran_per_row) { rem -= C.gran_per_row; ++row; }
+    if (FMT == KF_RGB888) {
+      // fused reconstruction: the chroma-only part of YCbCr2RGB is computed per chroma SAMPLE inside each branch
+      // (once per granule on a held row, every HFE-th pixel otherwise), the per-pixel part in emit()
+      const uint32_t my8 = C.my << 8, mcb8 = C.mcb << 8, mcr8 = C.mcr << 8;
+      const uint32_t a = out_s + q * 12u;
+      auto emit = [&](const InvChroma& t0, const InvChroma& t1, const InvChroma& t2, const InvChroma& t3) {
+        uint32_t w0, w1, w2;
+        inv_granule(dy, my8, t0, t1, t2, t3, w0, w1, w2);
+        sts32(a, w0); sts32(a + 4, w1); sts32(a + 8, w2);
+      };
+      if (HELD && haddr != 0) {
+        const uint32_t hp = lds8(haddr) | (lds8(haddr + 1) << 8) | (lds8(haddr + 2) << 16);
+        const InvChroma t = inv_chroma_terms(fwd_nc16<TRUNC>(hp, C.coef_ncb), fwd_nc16<TRUNC>(hp, C.coef_ncr), mcb8, mcr8);
+        emit(t, t, t, t);
+      } else {
+        InvChroma t[4];
+#pragma unroll
+        for (int j = 0; j < 4; j += HFE) t[j] = inv_chroma_terms(fwd_nc16<TRUNC>(p[j], C.coef_ncb), fwd_nc16<TRUNC>(p[j], C.coef_ncr), mcb8, mcr8);
+        emit(t[0], t[1 - 1 % HFE], t[2 - 2 % HFE], t[3 - 3 % HFE]);
+      }
+      continue;
+    }
     if (HELD && haddr != 0) {
       const uint32_t hp = lds8(haddr) | (lds8(haddr + 1) << 8) | (lds8(haddr + 2) << 16);
       const uint32_t hb = fwd_nc16<TRUNC>(hp, C.coef_ncb), hr = fwd_nc16<TRUNC>(hp, C.coef_ncr);
@@ -155,14 +178,6 @@ __device__ __forceinline__ void tile_loop(uint32_t in_s, uint32_t out_s, uint8_t
       const uint32_t w2 = (__byte_perm(t, u, 0x5410) ^ 0xFFFF00FFu) & C.qm2;
       const uint32_t a = out_s + q * 12u;
       sts32(a, w0); sts32(a + 4, w1); sts32(a + 8, w2);
-    } else if (FMT == KF_RGB888) {
-      uint32_t v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = inverse_rgb_raw(dy[j], xb[j], xr[j], C.my << 8, C.mcb << 8, C.mcr << 8);
-      const uint32_t a = out_s + q * 12u;
-      uint32_t w0, w1, w2;
-      pack_rgb_granule(v, w0, w1, w2);
-      sts32(a, w0); sts32(a + 4, w1); sts32(a + 8, w2);
     } else {
       // bundle slots go straight to global memory: one coalesced 4/8/16-byte store per granule
       uint32_t v[4];
@@ -182,9 +197,22 @@ __device__ __forceinline__ void tile_loop(uint32_t in_s, uint32_t out_s, uint8_t
       }
       constexpr uint32_t kG = (FMT == KF_SLOT32) ? 16u : (FMT == KF_SLOT16 ? 8u : 4u);
       uint8_t* dst = out_g + (C.out_dense ? q * kG : orow * C.out_pitch + orem * kG);
-      if (FMT == KF_SLOT32) __stcs(reinterpret_cast<uint4*>(dst), make_uint4(v[0], v[1], v[2], v[3]));
-      else if (FMT == KF_SLOT16) __stcs(reinterpret_cast<uint2*>(dst), make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16)));
-      else __stcs(reinterpret_cast<uint32_t*>(dst), v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
+      if (FMT == KF_SLOT32) {
+        const uint4 w = make_uint4(v[0], v[1], v[2], v[3]);
+        if (C.st_mode == 0u) __stcs(reinterpret_cast<uint4*>(dst), w);
+        else if (C.st_mode == 1u) *reinterpret_cast<uint4*>(dst) = w;
+        else __stcg(reinterpret_cast<uint4*>(dst), w);
+      } else if (FMT == KF_SLOT16) {
+        const uint2 w = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
+        if (C.st_mode == 0u) __stcs(reinterpret_cast<uint2*>(dst), w);
+        else if (C.st_mode == 1u) *reinterpret_cast<uint2*>(dst) = w;
+        else __stcg(reinterpret_cast<uint2*>(dst), w);
+      } else {
+        const uint32_t w = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+        if (C.st_mode == 0u) __stcs(reinterpret_cast<uint32_t*>(dst), w);
+        else if (C.st_mode == 1u) *reinterpret_cast<uint32_t*>(dst) = w;
+        else __stcg(reinterpret_cast<uint32_t*>(dst), w);
+      }
     }
   }
 }
@@ -214,6 +242,7 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(con
   const uint32_t S = (uint32_t)P.stages;
   const uint32_t n_my = (P.n_tiles > blockIdx.x) ? (P.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const uint64_t pol = policy_evict_first();   // every byte is touched exactly once: do not keep it in L2
+  const uint64_t pol_st = P.store_policy == 1 ? policy_evict_normal() : pol;   // experiment knob (CSIC_OPT_STORE_POLICY)
   const uint32_t full_bar = sbase + P.bar_off, empty_bar = full_bar + S * 8u;
 
   if (tid == 0) {
@@ -330,6 +359,7 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(con
     C.pl_crow_bytes = (uint32_t)P.tile_px / (uint32_t)max(1, P.planar_hs);
     C.pl_cr_off = C.pl_cb_off + (uint32_t)((P.tile_rows + P.planar_vs - 1) / max(1, P.planar_vs)) * C.pl_crow_bytes;
     C.pl_vs_shift = P.planar_vs == 2 ? 1u : 0u;
+    C.st_mode = (uint32_t)P.store_policy;
     C.nthreads = NC;
     C.row0_of_thread = tid / C.gran_per_row;
     C.rem0_of_thread = tid % C.gran_per_row;
@@ -363,17 +393,17 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(con
       consumer_barrier(NC);
       if (tid == 0) {
         if (FMT == KF_PLANAR) {
-          tma_store_1d(out_g, out_s, out_bytes, pol);
+          tma_store_1d(out_g, out_s, out_bytes, pol_st);
           if (nrc) {
-            tma_store_1d(reinterpret_cast<void*>(cb_g), out_s + C.pl_cb_off, nrc * C.pl_crow_bytes, pol);
-            tma_store_1d(reinterpret_cast<void*>(cr_g), out_s + C.pl_cr_off, nrc * C.pl_crow_bytes, pol);
+            tma_store_1d(reinterpret_cast<void*>(cb_g), out_s + C.pl_cb_off, nrc * C.pl_crow_bytes, pol_st);
+            tma_store_1d(reinterpret_cast<void*>(cr_g), out_s + C.pl_cr_off, nrc * C.pl_crow_bytes, pol_st);
           }
         } else if (P.out_dense) {
-          tma_store_1d(out_g, out_s, out_bytes, pol);
+          tma_store_1d(out_g, out_s, out_bytes, pol_st);
         } else {                       // pitched output rows: one bulk store per row of the tile
           const uint32_t nrows = out_bytes / P.tile_out_bytes;
           for (uint32_t j = 0; j < nrows; ++j)
-            tma_store_1d(out_g + (uint64_t)j * P.out_row_bytes, out_s + j * P.tile_out_bytes, P.tile_out_bytes, pol);
+            tma_store_1d(out_g + (uint64_t)j * P.out_row_bytes, out_s + j * P.tile_out_bytes, P.tile_out_bytes, pol_st);
         }
         tma_store_commit();
       }

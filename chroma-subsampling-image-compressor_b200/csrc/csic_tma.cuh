@@ -63,6 +63,12 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
   return pol;
 }
 
+__device__ __forceinline__ uint64_t policy_evict_normal() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
@@ -89,6 +95,41 @@ __device__ __forceinline__ uint4 lds128(uint32_t a) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
   return v;
+}
+
+// shared [ssrc, ssrc+len) -> global [g, g+len): 16-byte stores aligned on the global address.  The staging rows are
+// laid out so that (ssrc & 12) == (g & 12): the shared side of a chunk is then one LDS.128, plus one word when the
+// low two address bits differ.
+__device__ __forceinline__ void span_store(uint8_t* __restrict__ g, uint32_t ssrc, uint32_t len, uint32_t t,
+                                           uint32_t nthr) {
+  const uint32_t head = min(len, (16u - ((uint32_t)reinterpret_cast<uintptr_t>(g) & 15u)) & 15u);
+  const uint32_t nchunk = (len - head) >> 4;
+  const uint32_t tail = len - head - (nchunk << 4);
+  const uint32_t s0 = ssrc + head, sa = s0 & ~3u, sh = (s0 & 3u) * 8u;
+  if (sh == 0 && (sa & 15u) == 0) {
+    for (uint32_t c = t; c < nchunk; c += nthr) __stcs(reinterpret_cast<uint4*>(g + head + (c << 4)), lds128(sa + (c << 4)));
+  } else if ((sa & 15u) == 12u) {
+    for (uint32_t c = t; c < nchunk; c += nthr) {
+      const uint32_t a = sa + (c << 4);
+      const uint32_t w0 = lds32(a);
+      const uint4 v = lds128(a + 4);
+      __stcs(reinterpret_cast<uint4*>(g + head + (c << 4)),
+             make_uint4(__funnelshift_r(w0, v.x, sh), __funnelshift_r(v.x, v.y, sh), __funnelshift_r(v.y, v.z, sh),
+                        __funnelshift_r(v.z, v.w, sh)));
+    }
+  } else {
+    for (uint32_t c = t; c < nchunk; c += nthr) {
+      const uint32_t a = sa + (c << 4);
+      const uint32_t w0 = lds32(a), w1 = lds32(a + 4), w2 = lds32(a + 8), w3 = lds32(a + 12), w4 = lds32(a + 16);
+      __stcs(reinterpret_cast<uint4*>(g + head + (c << 4)),
+             make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                        __funnelshift_r(w3, w4, sh)));
+    }
+  }
+  for (uint32_t i = nthr - 1u - t; i < head + tail; i += nthr) {
+    const uint32_t off = i < head ? i : len - tail + (i - head);
+    g[off] = (uint8_t)lds8(ssrc + off);
+  }
 }
 
 
