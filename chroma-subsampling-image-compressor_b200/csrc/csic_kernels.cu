@@ -47,13 +47,28 @@ namespace csic {
 // Round 1's version -- one thread per slot, three divisions, byte loads and byte stores -- ran at 0.13 - 0.30 of the
 // copy peak.
 
-// three colour bytes (low three bytes of the result) at an arbitrary global address
-__device__ __forceinline__ uint32_t ldg_px(const uint8_t* p, const uint8_t* last_word) {
+// A stored input row as the gather kernel addresses it: word-aligned base, byte phase of its first pixel, and the last
+// word index a load may touch (the word holding the last byte this launch may read).  Set up once per row with 64-bit
+// arithmetic; every pixel is then 32-bit offset arithmetic (round 2's first version did the 64-bit pointer math and
+// the clamp per pixel: 382 warp-instructions per DECIMATE granule, now ~150).
+struct GRow {
+  const uint32_t* base;
+  uint32_t a0, maxw;
+};
+__device__ __forceinline__ GRow grow_at(const uint8_t* p, const uint8_t* last_word) {
   const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-  const uint32_t* lo = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-  if (((uint32_t)a & 3u) <= 1u) return __ldg(lo) >> (((uint32_t)a & 3u) * 8u);     // the three bytes sit in one word
-  const uint32_t* hi = reinterpret_cast<const uint32_t*>(min(reinterpret_cast<uintptr_t>(lo + 1), reinterpret_cast<uintptr_t>(last_word)));
-  return __funnelshift_r(__ldg(lo), __ldg(hi), ((uint32_t)a & 3u) * 8u);
+  GRow r;
+  r.base = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  r.a0 = (uint32_t)a & 3u;
+  const uintptr_t lw = reinterpret_cast<uintptr_t>(last_word), ba = reinterpret_cast<uintptr_t>(r.base);
+  r.maxw = lw >= ba ? (uint32_t)min((lw - ba) >> 2, (uintptr_t)0x3FFFFFFFu) : 0u;
+  return r;
+}
+// three colour bytes (low three bytes of the result) at byte offset `off` of the row: two aligned LDG.32 through L1
+// and a funnel shift; the second word is never fetched beyond GRow::maxw
+__device__ __forceinline__ uint32_t grow_px(const GRow& r, uint32_t off) {
+  const uint32_t o = r.a0 + off, wi = o >> 2;
+  return __funnelshift_r(__ldg(r.base + wi), __ldg(r.base + min(wi + 1u, r.maxw)), (o & 3u) * 8u);
 }
 
 // Chroma source, in *output grid* coordinates, when the chroma stage runs on the downsampled stream
@@ -71,16 +86,19 @@ __device__ __forceinline__ void chroma_src_case_b(const KPlan& P, int ro, int co
 
 constexpr uint32_t kGatherSlot = 32u * 16u + 32u;   // a warp's 32 granules of up to 16 bytes + alignment offset + read-ahead slack
 
-template <bool TRUNC, int FMT>
+// AF: 0 = DECIMATE (or f == 1); 2 / 4 / 8 = the AVERAGE extension with that factor (block loops unrolled)
+template <bool TRUNC, int FMT, int AF>
 __global__ void __launch_bounds__(128) csic_generic_kernel(const __grid_constant__ KPlan P) {
   __shared__ __align__(16) uint8_t stage[4][kGatherSlot];
   constexpr uint32_t kG = (FMT == KF_YCC888 || FMT == KF_RGB888) ? 12u : (FMT == KF_SLOT32 ? 16u : (FMT == KF_SLOT16 ? 8u : 4u));
+  constexpr bool avg = AF > 1;
+  constexpr uint32_t NR = avg ? (uint32_t)AF : 1u;                          // input rows per output row
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t Wo = (uint32_t)P.Wo, spr = (uint32_t)P.slots_per_row, gpr = (spr + 3u) >> 2;
   const uint32_t n_rows = P.n_frames * (uint32_t)P.band_rows;
   const uint32_t f = (uint32_t)P.f, ipb = (uint32_t)P.in_px_bytes, pxb = f * ipb;
   const uint32_t hfe = P.case_b ? 1u : (uint32_t)max(1, P.hf / P.f);         // case A: hold width inside a granule, in output pixels
-  const bool avg = P.average && f > 1;
+  const uint32_t hfm = (uint32_t)P.hf - 1u;                                  // hf is 1, 2 or 4
   const uint32_t row_bytes = (FMT == KF_YCC888 || FMT == KF_RGB888) ? Wo * 3u : (FMT == KF_PLANAR ? Wo : spr * (uint32_t)P.slot_bytes);
   // last aligned word that still holds a byte this launch may read: the end of the band's last input row (the host
   // band path hands over buffers that hold only the band's rows)
@@ -100,14 +118,29 @@ __global__ void __launch_bounds__(128) csic_generic_kernel(const __grid_constant
     uint8_t* orow = fout + (uint64_t)ro * P.out_row_bytes;
     // stored row of a full-resolution row (KPlan::compact: only every f-th row is stored, DECIMATE reads no other)
     auto in_row = [&](uint32_t r) { return frame + (uint64_t)(P.compact ? (r >> fsh) : r) * P.in_row_bytes; };
-    // case A, DECIMATE: the row's own pixels and -- on a held line (odd full-resolution line of 4:2:0 / 4:1:0, f == 1
-    // only) -- the one pixel whose chroma the whole row replays
-    const uint8_t* yrow = in_row(ro * f);
-    const bool held_row = !P.case_b && !avg && P.vf == 2 && ((ro * f) & 1u);
-    uint32_t hxb = 0, hxr = 0;
+    // the input rows of this output row: its own (DECIMATE) or the AF rows of its blocks (AVERAGE)
+    GRow rows[NR];
+#pragma unroll
+    for (uint32_t dr = 0; dr < NR; ++dr) rows[dr] = grow_at(in_row(ro * f + dr), last_word);
+    // Held chroma, one pixel per held line: DECIMATE case A on an odd full-resolution line of 4:2:0 / 4:1:0 (f == 1
+    // only) replays the last sample point of the line above (ChromaSubsampler.scala:62-65); AVERAGE with the chroma
+    // stage first does so for every odd line dr of the block rows.
+    uint32_t hxb[NR / 2u + 1u], hxr[NR / 2u + 1u];
+    const bool vheld = !P.case_b && P.vf == 2;
+    const bool held_row = !avg && vheld && ((ro * f) & 1u);
+#pragma unroll
+    for (uint32_t h = 0; h < NR / 2u + 1u; ++h) { hxb[h] = 0u; hxr[h] = 0u; }
     if (held_row) {
-      const uint32_t hp = ldg_px(in_row(ro * f - 1u) + (uint32_t)P.last_sample_col * ipb, last_word);
-      hxb = fwd_nc16<TRUNC>(hp, P.coef_ncb); hxr = fwd_nc16<TRUNC>(hp, P.coef_ncr);
+      const GRow hr = grow_at(in_row(ro * f - 1u), last_word);
+      const uint32_t hp = grow_px(hr, (uint32_t)P.last_sample_col * ipb);
+      hxb[0] = fwd_nc16<TRUNC>(hp, P.coef_ncb); hxr[0] = fwd_nc16<TRUNC>(hp, P.coef_ncr);
+    }
+    if (avg && vheld) {
+#pragma unroll
+      for (int h = 0; h < (int)(NR / 2u); ++h) {                             // odd line 2h + 1 replays (2h, lastSampleCol)
+        const uint32_t hp = grow_px(rows[2u * h], (uint32_t)P.last_sample_col * ipb);
+        hxb[h] = fwd_nc16<TRUNC>(hp, P.coef_ncb); hxr[h] = fwd_nc16<TRUNC>(hp, P.coef_ncr);
+      }
     }
     for (uint32_t g0 = warp * 32u; g0 < gpr; g0 += blockDim.x) {            // warp uniform
       const uint32_t g = g0 + lane, c0 = 4u * g;
@@ -117,15 +150,23 @@ __global__ void __launch_bounds__(128) csic_generic_kernel(const __grid_constant
         uint32_t y[4], cb[4], cr[4];                                         // final channel values (quantised)
         if (!avg) {
           uint32_t p[4], xb[4], xr[4];
+          if (pxb == 3u && c0 + 3u < Wo) {                                   // f == 1, RGB24: twelve consecutive bytes
+            const uint32_t o = rows[0].a0 + c0 * 3u, wi = o >> 2, sh = (o & 3u) * 8u;
+            const uint32_t w0 = __ldg(rows[0].base + wi), w1 = __ldg(rows[0].base + wi + 1u), w2 = __ldg(rows[0].base + wi + 2u);
+            const uint32_t w3 = __ldg(rows[0].base + min(wi + 3u, rows[0].maxw));
+            const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
+            p[0] = v0; p[1] = __funnelshift_r(v0, v1, 24); p[2] = __funnelshift_r(v1, v2, 16); p[3] = v2 >> 8;
+          } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) p[j] = ldg_px(yrow + (size_t)min(c0 + j, Wo - 1u) * pxb, last_word);
+            for (int j = 0; j < 4; ++j) p[j] = grow_px(rows[0], min(c0 + j, Wo - 1u) * pxb);
+          }
           if (held_row) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { xb[j] = hxb; xr[j] = hxr; }
+            for (int j = 0; j < 4; ++j) { xb[j] = hxb[0]; xr[j] = hxr[0]; }
           } else if (!P.case_b) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {                                    // sample where j % hfe == 0, hold in between
-              if (j == 0 || (uint32_t)j % hfe == 0u) { xb[j] = fwd_nc16<TRUNC>(p[j], P.coef_ncb); xr[j] = fwd_nc16<TRUNC>(p[j], P.coef_ncr); }
+              if (j == 0 || ((uint32_t)j & (hfe - 1u)) == 0u) { xb[j] = fwd_nc16<TRUNC>(p[j], P.coef_ncb); xr[j] = fwd_nc16<TRUNC>(p[j], P.coef_ncr); }
               else { xb[j] = xb[j - 1]; xr[j] = xr[j - 1]; }
             }
           } else {
@@ -133,7 +174,8 @@ __global__ void __launch_bounds__(128) csic_generic_kernel(const __grid_constant
             for (int j = 0; j < 4; ++j) {
               int sro, sco;
               chroma_src_case_b(P, (int)ro, (int)min(c0 + j, Wo - 1u), sro, sco);
-              const uint32_t pc = ldg_px(in_row((uint32_t)sro * f) + (size_t)sco * pxb, last_word);
+              const GRow cr_ = grow_at(in_row((uint32_t)sro * f), last_word);
+              const uint32_t pc = grow_px(cr_, (uint32_t)sco * pxb);
               xb[j] = fwd_nc16<TRUNC>(pc, P.coef_ncb); xr[j] = fwd_nc16<TRUNC>(pc, P.coef_ncr);
             }
           }
@@ -144,39 +186,45 @@ __global__ void __launch_bounds__(128) csic_generic_kernel(const __grid_constant
             cr[j] = (~(xr[j] >> 8)) & mcr;
           }
         } else {
-          // AVERAGE extension: mean over the f x f block of the stream entering the spatial stage, round half up; the
-          // quantiser before or after the mean as op[] says
+          // AVERAGE extension: mean over the AF x AF block of the stream entering the spatial stage, round half up;
+          // the quantiser before or after the mean as op[] says
           const uint32_t qy = P.quant_first ? my : 0xFFu, qb = P.quant_first ? mcb : 0xFFu, qr = P.quant_first ? mcr : 0xFFu;
-          const uint32_t half = (f * f) >> 1, sh = 2u * (uint32_t)fsh;
+          constexpr uint32_t half = (uint32_t)(AF * AF) >> 1, sh = AF == 2 ? 2u : (AF == 4 ? 4u : 6u);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint32_t co = min(c0 + j, Wo - 1u);
-            int bro = (int)ro, bco = (int)co;                                // block supplying chroma
-            if (P.case_b) chroma_src_case_b(P, (int)ro, (int)co, bro, bco);
+            const uint32_t co = min(c0 + j, Wo - 1u), col0 = co * NR;
             uint32_t sy = 0, sb = 0, sr = 0;
-            for (uint32_t dr = 0; dr < f; ++dr) {
-              const uint8_t* rp = in_row(ro * f + dr) + (size_t)co * pxb;
-              // chroma-first: an odd full-resolution line replays (line - 1, lastSampleCol); pooling-first: the own
-              // chroma of every pixel of the source block
-              const bool hl = !P.case_b && P.vf == 2 && (dr & 1u);
-              const uint8_t* cp = P.case_b ? in_row((uint32_t)bro * f + dr) + (size_t)bco * pxb
-                                           : (hl ? in_row(ro * f + dr - 1u) + (uint32_t)P.last_sample_col * ipb : rp);
-              uint32_t xb = 0, xr = 0;
-              for (uint32_t dc = 0; dc < f; ++dc) {
-                const uint32_t pv = ldg_px(rp + dc * ipb, last_word);
-                sy += (fwd_y16(pv, P.coef_y) >> 8) & qy;
-                if (P.case_b || (!hl && ((co * f + dc) % (uint32_t)P.hf) == 0u) || (hl && dc == 0u)) {
-                  const uint32_t pc = P.case_b ? ldg_px(cp + dc * ipb, last_word) : (hl ? ldg_px(cp, last_word) : pv);
-                  xb = (~(fwd_nc16<TRUNC>(pc, P.coef_ncb) >> 8)) & qb;
-                  xr = (~(fwd_nc16<TRUNC>(pc, P.coef_ncr) >> 8)) & qr;
-                } else if (!hl && dc == 0u) {
-                  // the block starts inside a hold group (hf > f): its sample point lies left of the block
-                  const uint32_t sc = (co * f) - ((co * f) % (uint32_t)P.hf);
-                  const uint32_t pc = ldg_px(in_row(ro * f + dr) + (size_t)sc * ipb, last_word);
-                  xb = (~(fwd_nc16<TRUNC>(pc, P.coef_ncb) >> 8)) & qb;
-                  xr = (~(fwd_nc16<TRUNC>(pc, P.coef_ncr) >> 8)) & qr;
+            if (!P.case_b) {
+#pragma unroll
+              for (uint32_t dr = 0; dr < NR; ++dr) {
+                const bool hl = vheld && (dr & 1u);       // nothing is sampled on an odd line: it replays the held pair
+                uint32_t xb = hxb[dr >> 1], xr = hxr[dr >> 1];
+                if (!hl && (col0 & hfm) != 0u) {          // the block starts inside a hold group (hf > AF): its sample lies to the left
+                  const uint32_t pc = grow_px(rows[dr], (col0 & ~hfm) * ipb);
+                  xb = fwd_nc16<TRUNC>(pc, P.coef_ncb); xr = fwd_nc16<TRUNC>(pc, P.coef_ncr);
                 }
-                sb += xb & 0xFFu; sr += xr & 0xFFu;
+#pragma unroll
+                for (uint32_t dc = 0; dc < NR; ++dc) {
+                  const uint32_t pv = grow_px(rows[dr], (col0 + dc) * ipb);
+                  sy += (fwd_y16(pv, P.coef_y) >> 8) & qy;
+                  if (!hl && ((col0 + dc) & hfm) == 0u) { xb = fwd_nc16<TRUNC>(pv, P.coef_ncb); xr = fwd_nc16<TRUNC>(pv, P.coef_ncr); }
+                  sb += (~(xb >> 8)) & qb; sr += (~(xr >> 8)) & qr;
+                }
+              }
+            } else {
+              // pooling first: the chroma stage then samples the POOLED stream with the full-size counters, i.e. this
+              // pixel takes the pooled chroma of block (bro, bco) (ImageCompressorTop.scala:52-58)
+              int bro, bco;
+              chroma_src_case_b(P, (int)ro, (int)co, bro, bco);
+#pragma unroll
+              for (uint32_t dr = 0; dr < NR; ++dr) {
+                const GRow cr_ = grow_at(in_row((uint32_t)bro * f + dr), last_word);
+#pragma unroll
+                for (uint32_t dc = 0; dc < NR; ++dc) {
+                  sy += (fwd_y16(grow_px(rows[dr], (col0 + dc) * ipb), P.coef_y) >> 8) & qy;
+                  const uint32_t pc = grow_px(cr_, ((uint32_t)bco * NR + dc) * ipb);
+                  sb += (~(fwd_nc16<TRUNC>(pc, P.coef_ncb) >> 8)) & qb; sr += (~(fwd_nc16<TRUNC>(pc, P.coef_ncr) >> 8)) & qr;
+                }
               }
             }
             y[j] = (sy + half) >> sh; cb[j] = (sb + half) >> sh; cr[j] = (sr + half) >> sh;
@@ -481,11 +529,18 @@ int launch_expand_planar(const KPlan& k, const uint8_t* planar, uint8_t* out, in
 }
 
 namespace {
+template <int FMT, int AF>
+int launch_generic_af(const KPlan& k, unsigned blocks, unsigned threads, cudaStream_t st) {
+  if (k.trunc) csic_generic_kernel<true, FMT, AF><<<blocks, threads, 0, st>>>(k);
+  else csic_generic_kernel<false, FMT, AF><<<blocks, threads, 0, st>>>(k);
+  return (int)cudaGetLastError();
+}
 template <int FMT>
 int launch_generic_fmt(const KPlan& k, unsigned blocks, unsigned threads, cudaStream_t st) {
-  if (k.trunc) csic_generic_kernel<true, FMT><<<blocks, threads, 0, st>>>(k);
-  else csic_generic_kernel<false, FMT><<<blocks, threads, 0, st>>>(k);
-  return (int)cudaGetLastError();
+  if (!(k.average && k.f > 1)) return launch_generic_af<FMT, 0>(k, blocks, threads, st);
+  if (k.f == 2) return launch_generic_af<FMT, 2>(k, blocks, threads, st);
+  if (k.f == 4) return launch_generic_af<FMT, 4>(k, blocks, threads, st);
+  return launch_generic_af<FMT, 8>(k, blocks, threads, st);
 }
 }  // namespace
 
@@ -640,10 +695,18 @@ bool plan_pool_kernel(KPlan& k, int sm_count, size_t max_smem_optin) {
     k.caseb_row_add = (uint32_t)k.last_sample_col / (uint32_t)k.Wo;
     k.caseb_col_bytes = ((uint32_t)k.last_sample_col % (uint32_t)k.Wo) * (uint32_t)k.in_px_bytes * (uint32_t)k.f;
   }
-  if (k.Wo % 16 != 0 || k.in_row_bytes % 16 != 0) return false;
+  // Like the row kernel, the kernel processes Wp = Wo rounded up to 16 output pixels per row: columns >= Wo are read
+  // from / written into the row padding, so both pitches must cover Wp (dense buffers qualify when Wo % 16 == 0;
+  // csic_process_host re-pitches other widths in its staging buffers, csic_process_device_pitched takes them as given).
+  k.Wp = (k.Wo + 15) & ~15;
+  const uint32_t opx_p = k.kformat <= KF_RGB888 ? 3u : (uint32_t)k.slot_bytes;
+  if (k.in_row_bytes % 16 != 0 || (uint64_t)k.in_row_bytes < (uint64_t)k.Wp * (uint32_t)k.f * (uint32_t)k.in_px_bytes) return false;
+  if ((uint64_t)k.out_row_bytes < (uint64_t)k.Wp * opx_p) return false;
   if ((reinterpret_cast<uintptr_t>(k.in) | reinterpret_cast<uintptr_t>(k.out)) & 15u) return false;
   if ((k.in_frame_bytes | k.out_frame_bytes | k.out_row_bytes) & 15u) return false;
-  if (k.slots_per_row != k.Wo) return false;
+  k.ragged = k.Wp != k.Wo;
+  k.in_dense = (uint64_t)k.in_row_bytes == (uint64_t)k.Wp * (uint32_t)k.f * (uint32_t)k.in_px_bytes;    // the f rows of a block row are contiguous
+  k.out_dense = (uint64_t)k.out_row_bytes == (uint64_t)k.Wp * opx_p;                                     // output rows are back to back
   if (k.band_rows <= 0 || k.n_frames == 0) return false;
   // 4x4 / 8x8 pooling keeps more live registers per thread: 6 consumer warps leave room for one more CTA per SM
   // (B200 sweep, profiles/r1/sweep_pool_v8.txt: 8K 4x4 0.97 of the copy peak vs 0.92 with 8 warps)
@@ -654,13 +717,13 @@ bool plan_pool_kernel(KPlan& k, int sm_count, size_t max_smem_optin) {
   const uint32_t opx = staged ? 3u : (uint32_t)k.slot_bytes;
   const uint32_t f = (uint32_t)k.f, ipb = (uint32_t)k.in_px_bytes;
   const uint32_t budget = 24u * 1024u, tile_max = budget + budget / 3;
-  const uint32_t block_row_bytes = (uint32_t)k.Wo * f * f * ipb;          // the f input rows of one output row
+  const uint32_t block_row_bytes = (uint32_t)k.Wp * f * f * ipb;          // the f input rows of one output row
   int nsplit = 0;
   for (int n = (int)((block_row_bytes + tile_max - 1) / tile_max); n <= 256; ++n)
-    if (n >= 1 && k.Wo % (16 * n) == 0) { nsplit = n; break; }
+    if (n >= 1 && k.Wp % (16 * n) == 0) { nsplit = n; break; }
   if (nsplit == 0) return false;
   k.nsplit = nsplit;
-  k.tile_px = k.Wo / nsplit;
+  k.tile_px = k.Wp / nsplit;
   k.tile_in_bytes = (uint32_t)k.tile_px * f * f * ipb;                   // per output-row segment: f row parts
   k.tile_out_bytes = (uint32_t)k.tile_px * opx;
   int rows = 1;
@@ -668,6 +731,7 @@ bool plan_pool_kernel(KPlan& k, int sm_count, size_t max_smem_optin) {
     rows = (int)std::max<uint32_t>(1u, budget / k.tile_in_bytes);
     rows = std::min(rows, (int)(2u * (uint32_t)kPoolMaxRows / f));      // held_addr[] holds rows * f/2 entries
     rows = std::min(rows, k.band_rows);
+    if (!k.out_dense) rows = 1;                                           // a tile's output must be one contiguous range
     auto tiles_for = [&](int r) { return (uint64_t)k.n_frames * (uint64_t)((k.band_rows + r - 1) / r); };
     while (rows > 1 && tiles_for(rows) < (uint64_t)sm_count * 4u) rows = (rows + 1) / 2;
   }

@@ -34,7 +34,8 @@ namespace csic {
 struct PoolMeta {
   uint64_t out_base;
   uint32_t n_granules;
-  uint32_t pad[5];
+  uint32_t col0;                      // first output column of the tile (row segments)
+  uint32_t pad[4];
   uint32_t held_addr[kPoolMaxRows];   // index j * (F/2) + dr/2: shared address of the pixel an odd line replays
 };
 static_assert(sizeof(PoolMeta) == kPoolMetaBytes, "kPoolMetaBytes out of sync");
@@ -47,6 +48,7 @@ struct PoolConst {
   int sy, scb, scr, ly, lb;           // bundle slot shifts
   uint32_t gran_per_row, nthreads, row0_of_thread, rem0_of_thread, drow, drem;
   uint32_t seg_row_bytes;
+  uint32_t Wo, ragged;                // pitched rows wider than the frame: bundle slots of columns >= Wo are the row's zero pad
   bool trunc, vhold;
   bool linear_y;                      // ... same for Y: byte 1 of each dp4a result is accumulated by a second dp4a
   bool linear;                        // no quantiser in front of the pooling: chroma sums in the complement domain
@@ -278,6 +280,11 @@ __device__ __forceinline__ void pool_tile(uint32_t in_s, uint32_t out_s, uint8_t
       uint32_t v[4];
 #pragma unroll
       for (int o = 0; o < 4; ++o) v[o] = ((y[o] >> C.sy) << C.ly) | ((cb[o] >> C.scb) << C.lb) | (cr[o] >> C.scr);
+      if (C.ragged) {
+        const uint32_t co = meta->col0 + rem * 4u;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) v[o] = (co + o < C.Wo) ? v[o] : 0u;
+      }
       if (FMT == KF_SLOT32) __stcs(reinterpret_cast<uint4*>(out_g) + q, make_uint4(v[0], v[1], v[2], v[3]));
       else if (FMT == KF_SLOT16) __stcs(reinterpret_cast<uint2*>(out_g) + q, make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16)));
       else __stcs(reinterpret_cast<uint32_t*>(out_g) + q, v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
@@ -404,11 +411,12 @@ __global__ void __maxnreg__(F == 2 ? 56 : 72) csic_pool_kernel(const __grid_cons
           }
       }
       m->n_granules = nrows * ((uint32_t)P.tile_px >> 2);
+      m->col0 = seg * (uint32_t)P.tile_px;
       m->out_base = reinterpret_cast<uint64_t>(P.out) + (uint64_t)k * P.out_frame_bytes + (uint64_t)ro0 * P.out_row_bytes +
                     (uint64_t)seg * P.tile_out_bytes;
       mbar_expect_tx(bar, nrows * P.tile_in_bytes + n_aux * 32u);
       const uint8_t* src = frame + (uint64_t)(ro0 * F) * P.in_row_bytes + (uint64_t)seg * seg_row_bytes;
-      if (P.nsplit == 1) {                   // whole rows: the F*nrows input rows are one contiguous range
+      if (P.nsplit == 1 && P.in_dense) {     // whole dense rows: the F*nrows input rows are one contiguous range
         tma_load_1d(dst, src, nrows * P.tile_in_bytes, bar, pol);
       } else {
         for (uint32_t r = 0; r < nrows * F; ++r)
@@ -440,6 +448,7 @@ __global__ void __maxnreg__(F == 2 ? 56 : 72) csic_pool_kernel(const __grid_cons
     C.drow = (NC / kSplit) / C.gran_per_row;
     C.drem = (NC / kSplit) % C.gran_per_row;
     C.seg_row_bytes = seg_row_bytes;
+    C.Wo = (uint32_t)P.Wo; C.ragged = (uint32_t)P.ragged;
     C.trunc = P.trunc != 0;
     C.vhold = P.vf == 2;
     C.pool_first = P.case_b != 0;

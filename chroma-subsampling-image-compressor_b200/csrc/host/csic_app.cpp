@@ -45,6 +45,10 @@ int process_image(const std::string& in_path, const std::string& out_path, int a
   if (!err.empty()) { std::fprintf(stderr, "[ERROR] %s\n", err.c_str()); return 2; }
   const int W = img.width, H = img.height;
   const bool spatial = op1 == CSIC_STEP_SPATIAL || op2 == CSIC_STEP_SPATIAL || op3 == CSIC_STEP_SPATIAL;   // :43
+  if (spatial && sf == 0) {   // the reference computes w / spatialFactorToUse first (:44): Scala throws before any `require`
+    std::fprintf(stderr, "java.lang.ArithmeticException: / by zero\n");
+    return 3;
+  }
   const int out_w = spatial ? W / sf : W, out_h = spatial ? H / sf : H;                   // :44-45
   if (spatial && sf > 0 && (W % sf != 0 || H % sf != 0))
     std::printf("[WARN] Image dimensions (%dx%d) are not perfectly divisible by spatialFactor (%d). SpatialDownsampler might truncate.\n", W, H, sf);

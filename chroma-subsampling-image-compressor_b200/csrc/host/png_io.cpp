@@ -44,6 +44,8 @@ std::string read_png(const std::string& path, Image& out) {
     if (pos + 12 + len > d.size()) return "truncated PNG";
     const uint8_t* body = &d[pos + 8];
     if (!std::memcmp(type, "IHDR", 4)) {
+      if (len < 13) return "malformed PNG (IHDR shorter than 13 bytes)";
+      if (be32(body) > 0x7FFFFFFFu || be32(body + 4) > 0x7FFFFFFFu) return "malformed PNG (dimensions out of range)";
       w = (int)be32(body); h = (int)be32(body + 4); depth = body[8]; ctype = body[9]; interlace = body[12];
     } else if (!std::memcmp(type, "PLTE", 4)) {
       plte.assign(body, body + len);
@@ -67,7 +69,14 @@ std::string read_png(const std::string& path, Image& out) {
     default: return "unsupported PNG colour type";
   }
   const size_t stride = (size_t)w * spp;
-  std::vector<uint8_t> raw((stride + 1) * (size_t)h);
+  // a hostile IHDR must end in an error message, not in std::bad_alloc: 2^31 bytes of raw scanlines is the cap
+  if (stride + 1 > ((size_t)1 << 31) / (size_t)h) return "PNG too large (more than 2 GiB of scanlines)";
+  std::vector<uint8_t> raw;
+  try {
+    raw.resize((stride + 1) * (size_t)h);
+  } catch (const std::bad_alloc&) {
+    return "out of memory reading PNG";
+  }
   uLongf rawlen = (uLongf)raw.size();
   if (uncompress(raw.data(), &rawlen, idat.data(), (uLong)idat.size()) != Z_OK || rawlen != raw.size()) return "PNG inflate failed";
   std::vector<uint8_t> img(stride * (size_t)h);

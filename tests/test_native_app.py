@@ -29,6 +29,25 @@ def test_cli_errors_without_gpu(tmp_path):
     r = subprocess.run([APP, "--input", os.path.join(GOLDEN, "in16x16.png"), "--sf", "3", "--outdir", str(tmp_path)],
                        capture_output=True, text=True)
     assert r.returncode == 3 and "requirement failed: Factor must be 1, 2, 4, or 8" in r.stderr
+    # --sf 0: the reference divides by the factor before it constructs anything (ImageCompressorTopApp.scala:44)
+    r = subprocess.run([APP, "--input", os.path.join(GOLDEN, "in16x16.png"), "--sf", "0", "--outdir", str(tmp_path)],
+                       capture_output=True, text=True)
+    assert r.returncode == 3 and "ArithmeticException: / by zero" in r.stderr
+
+
+def test_png_reader_rejects_malformed_headers(tmp_path):
+    """A short IHDR or absurd dimensions end in an error message, not in a crash."""
+    import struct, zlib
+    def chunk(t, body):
+        return struct.pack(">I", len(body)) + t + body + struct.pack(">I", zlib.crc32(t + body))
+    sig = b"\x89PNG\r\n\x1a\n"
+    short = tmp_path / "short.png"
+    short.write_bytes(sig + chunk(b"IHDR", b"\0" * 8) + chunk(b"IEND", b""))
+    huge = tmp_path / "huge.png"
+    huge.write_bytes(sig + chunk(b"IHDR", struct.pack(">IIBBBBB", 0x7FFFFFFF, 0x7FFFFFFF, 8, 2, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(b"\0")) + chunk(b"IEND", b""))
+    for f, text in ((short, "IHDR shorter than 13 bytes"), (huge, "PNG too large")):
+        r = subprocess.run([APP, "--input", str(f), "--outdir", str(tmp_path)], capture_output=True, text=True)
+        assert r.returncode not in (0, -8, -11, -6) and text in (r.stdout + r.stderr), (r.returncode, r.stdout, r.stderr)
 
 
 @pytest.mark.gpu
