@@ -90,6 +90,8 @@ WORKLOADS = {
                 "96x96 x131072, 4:2:0 + f=8, YCC888 (12x12 outputs)"),
     "oddavg": (1366, 768, 512, 2, 0, (8, 8, 8), 2, "CSQ", 0,
                "AVERAGE extension on 1366x768 (Wo = 683: breaks the pooling kernel's 16-byte rules)"),
+    "thumb96rgb": (96, 96, 65536, 2, 0, (6, 5, 5), 1, "CSQ", 1,
+                   "96x96 x65536, 4:2:0, f=1, RGB888 (tiny frames, fused reconstruction)"),
     "cfg5": (7680, 4320, 64, 2, 0, (6, 5, 5), 4, "CSQ", 1,
              "BASELINE configs[4]: 7680x4320 x64 frames, 4:2:0 + f=4 + Q_16BIT + RGB888 reconstruct"),
 }

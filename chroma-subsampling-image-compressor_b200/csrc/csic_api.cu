@@ -31,6 +31,9 @@ int cuda_fail(cudaError_t e, const char* what) {
   } while (0)
 
 constexpr int kPipe = 3;   // chunks in flight in csic_process_host
+// Input bytes per pipelined chunk.  B200 + PCIe 5 x16, 4K batches (profiles/r2/e2e_chunk_sweep.txt): 16 MB 32.6 k MP/s,
+// 32 MB 32.3 k, 64 MB (round 1) 31.9 k, 128 MB 31.3 k -- the pipeline's fill and drain cost one chunk each per call.
+constexpr size_t kDefaultChunkBytes = 16u << 20;
 
 // No C++ exception may cross the C ABI (the caller is a JVM, Python or C): std::thread / std::vector / std::string can
 // throw system_error or bad_alloc inside the host pipeline.
@@ -69,7 +72,7 @@ struct csic_ctx {
   int last_family = 0;
   int64_t launches = 0;
   int opt_family = 0;
-  size_t opt_chunk_bytes = 64u << 20;
+  size_t opt_chunk_bytes = kDefaultChunkBytes;
   int opt_ctas_per_sm = 0;
   int opt_stages = 0;
   uint32_t opt_tile_bytes = 0;
@@ -329,7 +332,7 @@ int csic_set_option(csic_ctx* ctx, int option, int64_t value) {
       return CSIC_OK;
     case CSIC_OPT_HOST_CHUNK_BYTES:
       if (value < 0) return CSIC_EINVAL_ARG;
-      ctx->opt_chunk_bytes = value == 0 ? (64u << 20) : (size_t)value;
+      ctx->opt_chunk_bytes = value == 0 ? kDefaultChunkBytes : (size_t)value;
       return CSIC_OK;
     case CSIC_OPT_GRID_CTAS_PER_SM:
       if (value < 0 || value > 32) return CSIC_EINVAL_ARG;

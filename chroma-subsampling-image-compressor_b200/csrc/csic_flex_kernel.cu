@@ -26,6 +26,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <type_traits>
 
 #include "csic_internal.h"
@@ -41,6 +42,7 @@ constexpr int kFlexMaxThreads = 288;                 // 8 consumer warps + the p
 constexpr uint32_t kFlexTileBytes = 24u * 1024u;     // input bytes of one tile (B200 sweep: profiles/r1/sweep_flex.txt)
 constexpr uint32_t kCtaWideSpan = 2048u;             // row spans at least this long are stored by the whole CTA
 constexpr uint32_t kDescBytes = 80u;
+constexpr uint32_t kDirectRowBytes = 1024u;          // output rows shorter than this that cannot be packed leave from registers
 
 __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) {
   asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
@@ -132,6 +134,38 @@ __device__ __forceinline__ void load_granule_any(uint32_t a, uint32_t pxb, uint3
   }
 }
 
+// A granule's output bytes straight from registers to global memory (rows too narrow for the staged path to pay: there
+// every 150-byte row costs a warp ~120 instructions of span_store set-up, head and tail).  `w` holds the granule's
+// little-endian words, `nbytes` of which exist (the row's last granule may be partial); the widest stores the address
+// allows -- words, half words or bytes.  Rows are contiguous in memory and written by one CTA within microseconds, so
+// L2 merges the partial sectors before they reach HBM.
+template <int NW_>
+__device__ __forceinline__ void direct_store(uint8_t* __restrict__ gp, const uint32_t (&w)[NW_], uint32_t nbytes) {
+  const uint32_t al = (uint32_t)reinterpret_cast<uintptr_t>(gp) & 3u;
+  if (al == 0u) {
+#pragma unroll
+    for (int i = 0; i < NW_; ++i) {
+      if (4u * i + 4u <= nbytes) __stcs(reinterpret_cast<uint32_t*>(gp) + i, w[i]);
+      else {
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (4u * i + b < nbytes) gp[4 * i + b] = (uint8_t)(w[i] >> (8 * b));
+      }
+    }
+  } else if (al == 2u) {
+#pragma unroll
+    for (int i = 0; i < 2 * NW_; ++i) {
+      const uint32_t h = (w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+      if (2u * i + 2u <= nbytes) __stcs(reinterpret_cast<unsigned short*>(gp) + i, (unsigned short)h);
+      else if (2u * i < nbytes) gp[2 * i] = (uint8_t)h;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4 * NW_; ++i)
+      if ((uint32_t)i < nbytes) gp[i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+  }
+}
+
 template <int FMT> struct FlexFmt {
   // staging bytes per granule of four slots
   static constexpr uint32_t kUnit = (FMT == KF_YCC888 || FMT == KF_RGB888) ? 12u : (FMT == KF_SLOT32 ? 16u : (FMT == KF_SLOT16 ? 8u : 4u));
@@ -148,7 +182,8 @@ struct FlexDesc {
   uint32_t obase_lo, obase_hi, st_mul, st_add;   // global address of the first output byte; staging row j sits at
                                            //   out_s + j * st_mul + ((obase_lo + j * st_add) & 12)
   uint32_t mode, sh, magic, n_gran;        // how granules are dealt to threads (flex_consume), log2(warps per row), 2^32 / gpr
-  uint32_t row_out, out_one, ncols, pad;   // output bytes per row, "whole dense rows: one packed span", slots (pad slots incl.)
+  uint32_t row_out, out_one, ncols, direct; // output bytes per row, "whole dense rows: one packed span", slots (pad slots incl.),
+                                           // "narrow rows: granules go straight to global memory" (direct_store)
 };
 static_assert(sizeof(FlexDesc) == kDescBytes, "kDescBytes out of sync");
 
@@ -177,23 +212,24 @@ __device__ __forceinline__ void flex_consume(const KPlan& P, uint8_t* smem, uint
   const uint32_t rs_add = P.in_dense ? 0u : (((uint32_t)P.row_step * P.in_row_bytes) & 15u);
 
   // How the granules of a tile are dealt to the threads (FlexDesc::mode, chosen by the producer):
-  //   0  the rows divide the warps (the plan makes nrows a power of two): NW / nrows warps per row, everything
+  //   0  no more rows than warps: a power-of-two number of warps per row (NW / nrows rounded down), everything
   //      row-dependent set up once per warp -- taken when at least 4/5 of the lanes of a row's warps get a granule
-  //   1  very wide rows: row by row with the whole CTA          2  narrow rows that fill whole warps: row by row per warp
-  //   3  one flat loop over the tile's granules
+  //   1  very wide rows: row by row with the whole CTA          2  more rows than warps: one row per warp and round
+  //   3  one flat loop over the tile's granules (rows that deal unevenly)
   uint32_t s = 0, ph = 0;
   for (uint32_t it = 0; it < n_my; ++it) {
     mbar_wait(full0 + s * 8u, ph);
     const uint32_t da = desc0 + s * kDescBytes;
     const uint4 d0 = lds128(da), d1 = lds128(da + 16u), d2 = lds128(da + 32u), d3 = lds128(da + 48u);
+    const uint4 d4 = lds128(da + 64u);   // row_out, out_one, ncols, direct
     const uint32_t Dk = d0.x, Dro0 = d0.y, Dnrows = d0.z, Dcol0 = d0.w, Dnpx = d1.x, Da0 = d1.y;
+    const bool direct = d4.w != 0u;
     consumer_barrier(NC);          // the previous tile has left the staging area
 
     // ---- compute -------------------------------------------------------------------------------------------
     const uint32_t in_s = sbase + s * in_stage, held_s = held_base + s * (uint32_t)kFlexMaxRows * 4u;
     const uint32_t gpr = d1.z, last_px = d1.w;
     uint8_t* obase = reinterpret_cast<uint8_t*>((uint64_t)d2.x | ((uint64_t)d2.y << 32));
-    const uint4 d4 = lds128(da + 64u);   // row_out, out_one (read before the stage goes back to the producer)
     // staging row j sits at  out_s + j * st_mul + ((oa0 + j * st_add) & 12):  the output row's own offset modulo 16,
     // rounded down to a word
     const uint32_t oa0 = d2.x, st_mul = d2.z, st_add = d2.w;
@@ -309,8 +345,10 @@ __device__ __forceinline__ void flex_consume(const KPlan& P, uint8_t* smem, uint
     auto row_st = [&](uint32_t row) { return out_s + row * st_mul + ((oa0 + row * st_add) & 12u); };
     if (d3.x == 0u) {
       const uint32_t parts = 1u << d3.y, row = (tid >> 5) >> d3.y, part = (tid >> 5) & (parts - 1u);
-      const uint32_t rs = row_in(row), so_row = row_st(row), hv = vhold ? lds32(held_s + row * 4u) : 0u;
-      for (uint32_t g = part * 32u + (tid & 31u); g < gpr; g += parts * 32u) granule(row, g, rs, so_row, hv);
+      if (row < Dnrows) {          // 3, 5, 6 or 7 rows on 8 warps leave the last warps without one
+        const uint32_t rs = row_in(row), so_row = row_st(row), hv = vhold ? lds32(held_s + row * 4u) : 0u;
+        for (uint32_t g = part * 32u + (tid & 31u); g < gpr; g += parts * 32u) granule(row, g, rs, so_row, hv);
+      }
     } else if (d3.x == 1u) {     // very wide rows: row by row, nothing row-dependent inside the loop
       for (uint32_t row = 0; row < Dnrows; ++row) {
         const uint32_t rs = row_in(row), so_row = row_st(row), hv = vhold ? lds32(held_s + row * 4u) : 0u;
@@ -412,49 +450,70 @@ __global__ void __launch_bounds__(kFlexMaxThreads, 4) csic_flex_kernel(const __g
       const uint32_t len_in = (npx - 1u) * pxb + ipb;  // first byte of the first .. last byte of the last sampled pixel
       const uint8_t* frame = P.in + (uint64_t)pk * P.in_frame_bytes;
       const uint8_t* src0 = frame + (uint64_t)(ro0 * (uint32_t)P.row_step) * P.in_row_bytes + (uint64_t)col0 * pxb;
-      // the pixel whose chroma a held row replays (ChromaSubsampler.scala:62-65): loads first, used after the TMA issue
-      uint32_t h0 = 0, h1 = 0, h2 = 0, hvalid = 0;
-      if (vhold && lane < nrows) {
-        const uint32_t ro = ro0 + lane;
-        const uint8_t* hp = nullptr;
-        if (!P.case_b) {
-          if (f == 1 && (ro & 1u)) hp = frame + (uint64_t)(ro - 1u) * P.in_row_bytes + (uint32_t)P.last_sample_col * ipb;
-        } else {
-          const uint32_t line = ro >> (31u - __clz(f));   // ro / f (f is 1, 2, 4 or 8); W == f * Wo: one counter line spans f output rows
-          if (line & 1u) {
-            const uint32_t srow = (line - 1u) * f + P.caseb_row_add;
-            hp = frame + (uint64_t)(srow * (uint32_t)P.row_step) * P.in_row_bytes + P.caseb_col_bytes;
+      // the pixel whose chroma a held row replays (ChromaSubsampler.scala:62-65): loads first, used after the TMA issue.
+      // Lanes take rows lane and lane + 32.  In a tall-image launch (KPlan::tall_ho) the held-line rule looks at the row
+      // index inside the row's own frame.
+      uint32_t hw[kFlexMaxRows / 32];
+#pragma unroll
+      for (uint32_t u = 0; u < (uint32_t)kFlexMaxRows / 32u; ++u) {
+        const uint32_t j = lane + 32u * u;
+        uint32_t h0 = 0, h1 = 0, h2 = 0, hvalid = 0;
+        if (vhold && j < nrows) {
+          const uint32_t ro = ro0 + j;
+          uint32_t rf = ro, fr0 = 0;                 // row inside its frame, first launch row of its frame
+          if (P.tall_ho) { const uint32_t kf = ro / (uint32_t)P.tall_ho; fr0 = kf * (uint32_t)P.tall_ho; rf = ro - fr0; }
+          const uint8_t* hp = nullptr;
+          if (!P.case_b) {
+            if (f == 1 && (rf & 1u)) hp = frame + (uint64_t)(ro - 1u) * P.in_row_bytes + (uint32_t)P.last_sample_col * ipb;
+          } else {
+            const uint32_t line = rf >> (31u - __clz(f));   // rf / f (f is 1, 2, 4 or 8); W == f * Wo: one counter line spans f output rows
+            if (line & 1u) {
+              const uint32_t srow = fr0 + (line - 1u) * f + P.caseb_row_add;
+              hp = frame + (uint64_t)(srow * (uint32_t)P.row_step) * P.in_row_bytes + P.caseb_col_bytes;
+            }
           }
+          if (hp) { h0 = ldg8_now(hp); h1 = ldg8_now(hp + 1); h2 = ldg8_now(hp + 2); hvalid = 0x80000000u; }
         }
-        if (hp) { h0 = ldg8_now(hp); h1 = ldg8_now(hp + 1); h2 = ldg8_now(hp + 2); hvalid = 0x80000000u; }
+        hw[u] = hvalid ? (hvalid | h0 | (h1 << 8) | (h2 << 16)) : 0u;
       }
       if (lane == 0) {
         const uint32_t NWc = NC >> 5, gpr = (ncols + 3u) >> 2, srow = gpr * kUnit, row_out = ncols * kOpx;
         const uint64_t ob = reinterpret_cast<uint64_t>(P.out) + (uint64_t)pk * P.out_frame_bytes + (uint64_t)ro0 * P.out_row_bytes +
                             (uint64_t)col0 * kOpx;
         const uint32_t out_one = (P.out_dense && nsplit == 1u && row_out == srow) ? 1u : 0u;   // whole dense rows: one packed span
-        const uint32_t sh = pow2_divides(nrows, NWc) ? 31u - __clz(NWc) - (31u - __clz(nrows)) : 0u;   // log2(NW / nrows)
-        const uint32_t lsh = sh + 5u, iters = (gpr + (1u << lsh) - 1u) >> lsh;                          // lanes per row = 1 << lsh
-        uint32_t mode;
-        if (pow2_divides(nrows, NWc) && gpr * 5u >= (iters << lsh) * 4u) mode = 0u;
-        else if (gpr >= 4u * NC) mode = 1u;
-        else if ((gpr & 31u) == 0u && (NWc & (NWc - 1u)) == 0u && (nrows & (NWc - 1u)) == 0u) mode = 2u;
-        else mode = 3u;
+        // how the granules are dealt to the consumer threads (flex_consume)
+        const uint32_t parts = nrows <= NWc ? NWc / nrows : 0u;                 // warps per row when the rows fit the warps
+        uint32_t mode = 3u, sh = 0u;
+        if (parts && (parts & (parts - 1u)) == 0u) {
+          sh = 31u - __clz(parts);
+          const uint32_t lsh = sh + 5u, iters = (gpr + (1u << lsh) - 1u) >> lsh;   // lanes per row = 1 << lsh
+          if (gpr * 5u >= (iters << lsh) * 4u) mode = 0u;                       // at least 4/5 of those lanes get a granule
+        }
+        if (mode != 0u) {
+          const uint32_t rounds = (nrows + NWc - 1u) / NWc, li = (gpr + 31u) >> 5;
+          if (gpr >= 4u * NC) mode = 1u;
+          else if (nrows > NWc && nrows * 5u >= rounds * NWc * 4u && gpr * 5u >= li * 32u * 4u) mode = 2u;
+        }
         d->k = pk; d->ro0 = ro0; d->nrows = nrows; d->col0 = col0;
         d->npx = npx; d->a0 = (uint32_t)reinterpret_cast<uintptr_t>(src0) & 15u; d->gpr = gpr; d->last_px = npx - 1u;
         d->obase_lo = (uint32_t)ob; d->obase_hi = (uint32_t)(ob >> 32);
         d->st_mul = out_one ? srow : srow + 16u; d->st_add = out_one ? 0u : P.out_row_bytes;
         d->mode = mode; d->sh = sh; d->magic = gpr > 1u ? 0xFFFFFFFFu / gpr + 1u : 0u;   // q / gpr == umulhi(q, magic) for q < 65536
         d->n_gran = nrows * gpr;
-        d->row_out = row_out; d->out_one = out_one; d->ncols = ncols; d->pad = 0u;
+        d->row_out = row_out; d->out_one = out_one; d->ncols = ncols;
+        d->direct = (!out_one && row_out < kDirectRowBytes && FMT != KF_PLANAR) ? 1u : 0u;
       }
       if (P.in_dense) {            // consecutive rows are contiguous in memory: one span
         if (lane == 0) span_fetch(in_s, src0, (nrows - 1u) * P.in_row_bytes + len_in, bar, pol, lim_lo, lim_hi);
-      } else if (lane < nrows) {   // one lane per row span: 16 short rows do not queue up behind one thread
-        span_fetch(in_s + lane * rs_mul, src0 + (uint64_t)lane * rstep, len_in, bar, pol, lim_lo, lim_hi);
+      } else {                     // one lane per row span: 64 short rows do not queue up behind one thread
+        for (uint32_t j = lane; j < nrows; j += 32u)
+          span_fetch(in_s + j * rs_mul, src0 + (uint64_t)j * rstep, len_in, bar, pol, lim_lo, lim_hi);
       }
-      if (vhold && lane < (uint32_t)kFlexMaxRows)
-        sts32(held_base + (s * (uint32_t)kFlexMaxRows + lane) * 4u, hvalid ? (hvalid | h0 | (h1 << 8) | (h2 << 16)) : 0u);
+      if (vhold) {
+#pragma unroll
+        for (uint32_t u = 0; u < (uint32_t)kFlexMaxRows / 32u; ++u)
+          sts32(held_base + (s * (uint32_t)kFlexMaxRows + lane + 32u * u) * 4u, hw[u]);
+      }
       __syncwarp();
       // releases the descriptor, the held words and the hand-copied edge bytes; the phase completes with the last TMA byte
       if (lane == 0) mbar_arrive(bar);
@@ -509,32 +568,86 @@ bool plan_flex_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
   const uint32_t len_in_max = ((std::min((uint32_t)k.tile_px, Wo) - 1u) * f + 1u) * ipb;
   // consecutive processed rows contiguous in memory?  (dense rows, every stored row is read)
   const bool contiguous = k.nsplit == 1 && k.row_step == 1 && k.in_row_bytes == (uint32_t)k.W * ipb;
+  if (k.block_threads <= 0) k.block_threads = kFlexConsumers;
+  k.block_threads = std::min(k.block_threads, kFlexMaxThreads - 32);
+  const uint32_t stages = (uint32_t)std::min(std::max(force_stages, 2), 8);
+  auto up16 = [](uint32_t v) { return (v + 15u) & ~15u; };
+  auto up128 = [](uint32_t v) { return (v + 127u) & ~127u; };
+
+  // "Tall image": when every launch row is a whole frame row and frames lie back to back with the same row stride
+  // inside and across frames (input AND output), the batch IS one image of n_frames * Ho rows -- a tile may then span
+  // frames, which is what batches of small frames need (a 96x96 frame at f = 8 is twelve 288-byte rows: one tile per
+  // frame left the SMs waiting on 3 KB copies).  Only the held-line rule still looks at the row index inside its frame.
+  const uint64_t stored_rows = (uint64_t)(uint32_t)k.Ho * (uint32_t)k.row_step;   // input rows from one frame's first row to the next frame's
+  static const bool no_tall = std::getenv("CSIC_FLEX_NO_TALL") != nullptr;      // experiment switches (tools/): never change results
+  static const int env_rows = std::getenv("CSIC_FLEX_ROWS") ? std::atoi(std::getenv("CSIC_FLEX_ROWS")) : 0;
+  const bool tall = !no_tall && k.nsplit == 1 && !planar && k.n_frames > 1 && k.row0 == 0 && k.band_rows == k.Ho &&
+                    k.in_frame_bytes == stored_rows * k.in_row_bytes && k.out_frame_bytes == (uint64_t)(uint32_t)k.Ho * k.out_row_bytes &&
+                    (uint64_t)k.n_frames * (uint32_t)k.Ho < (1ull << 30) && (uint64_t)k.n_frames * (uint32_t)k.H < (1ull << 31);
+  const uint32_t frames = tall ? 1u : k.n_frames;
+  const uint32_t band_rows = tall ? k.n_frames * (uint32_t)k.Ho : (uint32_t)k.band_rows;
+
+  // Rows per tile (whole rows only).  What the B200 sweeps after the round-2 restructure show (profiles/r2/sweep_flex*.txt,
+  // flex_rows_*.txt): throughput follows (a) the consumer warps that have work, summed over the resident CTAs -- it
+  // saturates near 20 for the light formats and keeps growing to 32 for the fused RGB reconstruction, which is
+  // issue-bound -- and (b) the granules per tile, over which ~110 warp-instructions of per-tile work and two CTA
+  // barriers are spread; two resident CTAs instead of three or four cost another ~15 %.  The candidate that maximises
+  // that product wins: 1366x768 f = 1 RGB888 -> 4 rows, 1080x1920 -> 7, 1918x1078 -> 4, 3838x2158 f = 2 -> 2.
+  const uint32_t NW = (uint32_t)k.block_threads / 32u, gpr = (std::min((uint32_t)k.tile_px, S) + 3u) / 4u;
+  const uint32_t row_in = up16((contiguous ? std::max(len_in_max, k.in_row_bytes) : len_in_max) + 15u) + 16u;
+  uint32_t row_out = ((uint32_t)k.tile_px / 4u) * unit + 16u;
+  if (planar) row_out += 2u * (uint32_t)k.tile_px;
+  // resident CTAs: shared memory, threads, and the 56 registers per thread __launch_bounds__(288, 4) grants
+  const uint32_t cta_cap = std::min<uint32_t>(std::min<uint32_t>(8u, 2048u / ((uint32_t)k.block_threads + 32u)),
+                                              65536u / (56u * ((uint32_t)k.block_threads + 32u)));
+  auto ctas_for = [&](uint32_t r) {
+    const uint32_t smem = stages * (r * row_in + 32u) + r * row_out + 2048u;
+    return std::min<uint32_t>(cta_cap, 227u * 1024u / (smem + 1024u));
+  };
   int rows = 1;
   if (k.nsplit == 1) {
-    const uint32_t per_row = contiguous ? k.in_row_bytes : len_in_max;
-    rows = (int)std::min<uint32_t>((uint32_t)kFlexMaxRows, std::max<uint32_t>(1u, tile_bytes / std::max(1u, per_row)));
-    rows = std::min(rows, k.band_rows);
-    auto tiles_for = [&](int r) { return (uint64_t)k.n_frames * (uint64_t)((k.band_rows + r - 1) / r); };
-    while (rows > 1 && tiles_for(rows) < (uint64_t)sm_count * 8u) rows = (rows + 1) / 2;
+    const uint32_t rmax = std::min<uint32_t>((uint32_t)kFlexMaxRows, band_rows);
+    auto tiles_for = [&](uint32_t r) { return (uint64_t)frames * (uint64_t)((band_rows + r - 1u) / r); };
+    if (force_tile_bytes) {
+      const uint32_t per_row = contiguous ? k.in_row_bytes : len_in_max;
+      rows = (int)std::min<uint32_t>(rmax, std::max<uint32_t>(1u, tile_bytes / std::max(1u, per_row)));
+    } else {
+      // fraction of a CTA's consumer warps that get granules (flex_consume's modes 0 and 2); rows that deal unevenly
+      // or are narrower than a warp run the flat loop: every thread busy, ~15 % more instructions per granule
+      auto busy_frac = [&](uint32_t r) {
+        const bool lanes_ok = gpr * 5u >= ((gpr + 31u) / 32u) * 32u * 4u;
+        if (r <= NW) {
+          const uint32_t parts = NW / r;
+          const uint32_t lanes = parts * 32u, it = (gpr + lanes - 1u) / lanes;
+          if ((parts & (parts - 1u)) == 0u && gpr * 5u >= it * lanes * 4u) return (double)(r * parts) / NW;
+          return 0.85;
+        }
+        const uint32_t rounds = (r + NW - 1u) / NW;
+        if (lanes_ok && r * 5u >= rounds * NW * 4u) return (double)r / (rounds * NW);
+        return 0.85;
+      };
+      const double busy_cap = k.kformat == KF_RGB888 ? 32.0 : 20.0;
+      double best_score = -1.0;
+      for (uint32_t r = 1; r <= rmax; ++r) {
+        const uint32_t c = ctas_for(r);
+        if (c == 0u) break;
+        if (r > 1u && tiles_for(r) < (uint64_t)sm_count * 8u) break;        // keep every SM supplied with several tiles
+        const double gran = (double)r * gpr;
+        const double score = std::min(busy_cap, c * NW * busy_frac(r)) * gran / (gran + 400.0) * (c >= 3u ? 1.0 : 0.85);
+        if (score >= best_score * 1.0001) { best_score = score; rows = (int)r; }
+      }
+    }
+    if (env_rows > 0) rows = (int)std::min<uint32_t>((uint32_t)env_rows, rmax);
   }
-  // a power of two lets the consumer warps split evenly over the rows -- unless rounding down would cost more than a
-  // quarter of the tile (then the flat granule loop takes it; B200 map: profiles/r1/perf_map.txt)
-  int p2 = rows;
-  while (p2 & (p2 - 1)) p2 &= p2 - 1;
-  if (p2 * 4 >= rows * 3) rows = p2;
   k.tile_rows = rows;
   k.in_dense = (contiguous && rows > 1) ? 1 : 0;
-  k.tiles_per_band = (uint32_t)((k.band_rows + rows - 1) / rows);
-  const uint64_t n_tiles = (uint64_t)k.n_frames * (uint64_t)k.tiles_per_band * (uint64_t)k.nsplit;
+  const uint64_t tiles_per_band = ((uint64_t)band_rows + (uint32_t)rows - 1u) / (uint32_t)rows;
+  const uint64_t n_tiles = (uint64_t)frames * tiles_per_band * (uint64_t)k.nsplit;
   if (n_tiles >= (1ull << 31)) return false;
-  k.n_tiles = (uint32_t)n_tiles;
   const uint32_t dense_out_row = planar ? Wo : S * (unit / 4u);
   k.out_dense = k.out_row_bytes == dense_out_row ? 1 : 0;
 
-  auto up16 = [](uint32_t v) { return (v + 15u) & ~15u; };
-  auto up128 = [](uint32_t v) { return (v + 127u) & ~127u; };
-  k.stage_stride = up16((k.in_dense ? std::max(len_in_max, k.in_row_bytes) : len_in_max) + 15u) + 16u;
-  const uint32_t stages = (uint32_t)std::min(std::max(force_stages, 2), 8);
+  k.stage_stride = row_in;
   const uint32_t in_bytes = stages * ((uint32_t)rows * k.stage_stride + 32u);   // + slack: pixel loads read one word ahead
   uint32_t stage_bytes = (uint32_t)rows * (((uint32_t)k.tile_px / 4u) * unit + 16u) + 16u;   // rows at their own offset mod 16
   if (planar) stage_bytes += 2u * (uint32_t)(rows / std::max(1, k.planar_vs) + 1) * (uint32_t)k.tile_px;
@@ -544,11 +657,21 @@ bool plan_flex_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
   k.bar_off = up128(k.meta_off + stages * (uint32_t)kFlexMaxRows * 4u);     // full[S], empty[S] mbarriers, then S descriptors
   k.smem_bytes = k.bar_off + stages * (16u + kDescBytes);
   if (k.smem_bytes > max_smem_optin) return false;
-  if (k.block_threads <= 0) k.block_threads = kFlexConsumers;
-  k.block_threads = std::min(k.block_threads, kFlexMaxThreads - 32);
+  // nothing can fail from here on: commit the tall-image view of the batch
+  k.tiles_per_band = (uint32_t)tiles_per_band;
+  k.n_tiles = (uint32_t)n_tiles;
+  k.tall_ho = 0;
+  if (tall) {
+    k.tall_ho = k.Ho;
+    k.in_frame_bytes *= k.n_frames; k.out_frame_bytes *= k.n_frames;
+    k.H *= (int32_t)k.n_frames; k.Ho = (int32_t)band_rows; k.band_rows = (int32_t)band_rows;
+    k.n_frames = 1;
+  }
   k.stages = (int32_t)stages;
-  k.ctas_per_sm = (int32_t)std::max<uint32_t>(1u, std::min<uint32_t>(std::min<uint32_t>(8u, 2048u / ((uint32_t)k.block_threads + 32u)),
-                                                                      227u * 1024u / (k.smem_bytes + 1024u)));
+  // the grid is a whole number of RESIDENT CTAs per SM: a CTA that has to wait for a slot would run its share of the
+  // tiles after everybody else (round 1 ignored the register limit here: small tiles launched 5-7 CTAs per SM where 4
+  // fit, and the second wave doubled the run time -- 1080x1920 with 4-row tiles: 0.69 instead of 0.9)
+  k.ctas_per_sm = (int32_t)std::max<uint32_t>(1u, std::min<uint32_t>(cta_cap, 227u * 1024u / (k.smem_bytes + 1024u)));
   return true;
 }
 

@@ -65,6 +65,7 @@ struct KPlan {
   int32_t ctas_per_sm;
   uint32_t stage_stride, out_buf_off, out_buf_stride, meta_off, bar_off, smem_bytes;
   uint32_t qmask;                        // my | mcb<<8 | mcr<<16 (per-channel keep masks)
+  int32_t tall_ho;                       // flex kernel: != 0 -> the batch is addressed as ONE image of n * Ho rows; rows per original frame
 };
 
 // Fills the TMA-row-kernel fields of `k`; returns false when the configuration is not eligible
@@ -97,7 +98,7 @@ constexpr int kMaxTileRows = 64;        // rows per tile of the row kernel (smal
 constexpr uint32_t kTileMetaBytes = 32 + 4 * kMaxTileRows;   // sizeof(TileMeta) in csic_rows_kernel.cu
 constexpr int kPoolMaxRows = 16;        // output rows per tile of the pooling kernel (each carries f input rows)
 constexpr uint32_t kPoolMetaBytes = 32 + 4 * kPoolMaxRows;   // sizeof(PoolMeta) in csic_pool_kernel.cu
-constexpr int kFlexMaxRows = 32;        // rows per tile of the flex kernel: one producer lane per row
+constexpr int kFlexMaxRows = 64;        // rows per tile of the flex kernel: the producer's lanes take two rows each
 
 }  // namespace csic
 

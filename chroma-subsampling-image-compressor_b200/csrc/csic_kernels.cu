@@ -272,79 +272,92 @@ __global__ void __launch_bounds__(128) csic_generic_kernel(const __grid_constant
 
 // Decoder of the PLANAR format for ANY width and any alignment of the planes and of the output: chroma fetched with the
 // reference's replay rule (ChromaSubsampler.scala:52-65) expressed in output coordinates (chroma before spatial, or
-// f == 1).  One CTA per output row; the only division (frame / row split) and everything row-dependent happen once
-// per row.  A thread decodes one granule of four pixels (the row's last granule may be partial):
-//   load   Y bytes of a granule are one word at an arbitrary byte address = two aligned LDG.32 and a funnel shift (the
-//          second word is never fetched beyond the last word that holds a byte of the buffer); chroma samples likewise
-//          (4:4:4) or one / two byte loads (hs = 4 / 2);
-//   store  a warp's 32 granules are 384 consecutive output bytes: they go to the warp's shared-memory slot at the
-//          output's own offset modulo 16 (rounded down to a word) and leave as 16-byte st.global.cs aligned on the
-//          GLOBAL address (span_store: LDS.128 + at most four funnel shifts), head / tail bytes one by one.
-// Before: one thread per pixel, three divisions, three byte loads and three byte stores each -- 0.10 of the copy peak.
-__device__ __forceinline__ uint32_t ldg_word_at(const uint8_t* p, const uint8_t* last_word) {
-  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-  const uint32_t* lo = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-  if (((uint32_t)a & 3u) == 0u) return __ldg(lo);
-  const uint32_t* hi = reinterpret_cast<const uint32_t*>(min(reinterpret_cast<uintptr_t>(lo + 1), reinterpret_cast<uintptr_t>(last_word)));
-  return __funnelshift_r(__ldg(lo), __ldg(hi), ((uint32_t)a & 3u) * 8u);
-}
+// f == 1).  One CTA per output row segment of up to 4096 pixels; the only division (frame / row split) and everything
+// row-dependent happen once per row.
+//   load   a thread takes up to four granules of four pixels and issues ALL their loads first (Y word, Cb and Cr
+//          samples: aligned LDG.32 pairs + funnel shifts on per-row word bases, 32-bit offsets), so a warp keeps ~24
+//          loads in flight instead of 3;
+//   store  the whole segment is staged in shared memory at the output's own offset modulo 16 (rounded down to a
+//          word) and leaves as 16-byte st.global.cs aligned on the GLOBAL address (span_store): one head and one tail
+//          of < 16 bytes per row instead of one per 384 bytes.
+// Round 1: one thread per pixel, three divisions, three byte loads and three byte stores each -- 0.10 of the copy
+// peak; the first round-2 version (one granule per thread and trip, per-warp staging) 0.22.
+constexpr uint32_t kExpandSeg = 4096u;   // pixels per staged segment: 12 KB of shared memory
 
 __global__ void __launch_bounds__(128) csic_expand_planar_any_kernel(const __grid_constant__ KPlan P, const uint8_t* __restrict__ planar,
                                                                      uint8_t* __restrict__ out, int to_rgb) {
-  __shared__ __align__(16) uint8_t stage[4][384 + 32];               // per warp: 32 granules + alignment offset + read-ahead slack
-  const uint32_t Wo = (uint32_t)P.Wo, gpr = (Wo + 3u) >> 2, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  __shared__ __align__(16) uint8_t stage[kExpandSeg * 3u + 48u];      // + alignment offset + read-ahead slack of span_store
+  const uint32_t Wo = (uint32_t)P.Wo, tid = threadIdx.x, NT = blockDim.x;
   const uint32_t n_rows = P.n_frames * (uint32_t)P.Ho;
-  const int last_c = (P.last_sample_col / P.f) / P.planar_hs;       // plane column of a line's last sample point
+  const uint32_t last_c = (uint32_t)((P.last_sample_col / P.f) / P.planar_hs);   // plane column of a line's last sample point
   const uint32_t hs_sh = P.planar_hs == 4 ? 2u : (P.planar_hs == 2 ? 1u : 0u), vs_sh = P.planar_vs == 2 ? 1u : 0u;
+  const uint32_t csel = hs_sh == 0 ? 0x3210u : (hs_sh == 1 ? 0x1100u : 0x0000u);   // sample bytes -> the four pixels of a granule
   const bool vhold = P.vf == 2 && P.f == 1;                         // odd lines replay the line above (f == 1 only)
   // last aligned word that still holds a byte of the planar buffer (loads never go past it)
   const uint8_t* last_word = reinterpret_cast<const uint8_t*>(
       (reinterpret_cast<uintptr_t>(planar) + (uint64_t)P.n_frames * P.out_frame_bytes - 1u) & ~(uintptr_t)3);
-  const uint32_t sbase = smem_u32(stage[warp]);
+  const uint32_t sbase = smem_u32(stage);
   for (uint32_t R = blockIdx.x; R < n_rows; R += gridDim.x) {
     const uint32_t k = R / (uint32_t)P.Ho, ro = R - k * (uint32_t)P.Ho;
     const uint8_t* fr = planar + (uint64_t)k * P.out_frame_bytes;
-    const uint8_t* yrow = fr + (size_t)ro * Wo;
     const bool held = vhold && (ro & 1u);
     const size_t crow = (size_t)((held ? ro - 1u : ro) >> vs_sh) * (size_t)P.planar_cw;
-    const uint8_t* cbp = fr + P.planar_cb_off + crow;
-    const uint8_t* crp = fr + P.planar_cr_off + crow;
+    const GRow yr = grow_at(fr + (size_t)ro * Wo, last_word);
+    const GRow br = grow_at(fr + P.planar_cb_off + crow, last_word), rr = grow_at(fr + P.planar_cr_off + crow, last_word);
     uint8_t* orow = out + (uint64_t)R * Wo * 3u;
     uint32_t hcb = 0, hcr = 0;
-    if (held) { hcb = (uint32_t)__ldg(cbp + last_c) * 0x01010101u; hcr = (uint32_t)__ldg(crp + last_c) * 0x01010101u; }
-    for (uint32_t g0 = warp * 32u; g0 < gpr; g0 += blockDim.x) {    // warp uniform
-      const uint32_t g = g0 + lane;
-      uint8_t* og = orow + (size_t)g0 * 12u;                          // first output byte of this warp's group
+    if (held) { hcb = (grow_px(br, last_c) & 0xFFu) * 0x01010101u; hcr = (grow_px(rr, last_c) & 0xFFu) * 0x01010101u; }
+    for (uint32_t seg0 = 0; seg0 < Wo; seg0 += kExpandSeg) {
+      const uint32_t npx = min(kExpandSeg, Wo - seg0), ngr = (npx + 3u) >> 2;
+      uint8_t* og = orow + (size_t)seg0 * 3u;
       const uint32_t st = sbase + ((uint32_t)reinterpret_cast<uintptr_t>(og) & 12u);
-      if (g < gpr) {
-        const uint32_t yw = ldg_word_at(yrow + 4u * g, last_word);
-        uint32_t cbw, crw;                                            // chroma of the four pixels as bytes
-        if (held) {
-          cbw = hcb; crw = hcr;
-        } else if (hs_sh == 0) {
-          cbw = ldg_word_at(cbp + 4u * g, last_word); crw = ldg_word_at(crp + 4u * g, last_word);
-        } else if (hs_sh == 1) {                                      // two samples, each held for two pixels
-          const uint32_t c1 = min(2u * g + 1u, (uint32_t)P.planar_cw - 1u);
-          const uint32_t b2 = (uint32_t)__ldg(cbp + 2u * g) | ((uint32_t)__ldg(cbp + c1) << 8);
-          const uint32_t r2 = (uint32_t)__ldg(crp + 2u * g) | ((uint32_t)__ldg(crp + c1) << 8);
-          cbw = __byte_perm(b2, 0, 0x1100); crw = __byte_perm(r2, 0, 0x1100);
-        } else {
-          cbw = (uint32_t)__ldg(cbp + g) * 0x01010101u; crw = (uint32_t)__ldg(crp + g) * 0x01010101u;
-        }
-        uint32_t v[4];
+      for (uint32_t g0 = tid; g0 < ngr; g0 += 4u * NT) {
+        // All the loads of up to four granules first, as bare LDGs on clamped indices: no branch and no dependent
+        // instruction between them (a funnel shift right behind its two loads stalls the warp -- the GPU issues in
+        // order -- and the next granule's loads with it: ncu showed 11.7 long-scoreboard stalls per issue that way).
+        uint32_t yl[4], yh[4], bl[4], bh[4], rl[4], rh[4];
+        const uint32_t oc0 = seg0 >> hs_sh;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int y = (int)((yw >> (8 * j)) & 0xFFu), cb = (int)((cbw >> (8 * j)) & 0xFFu), cr = (int)((crw >> (8 * j)) & 0xFFu);
-          v[j] = to_rgb ? inverse_rgb(y, cb, cr) : ((uint32_t)y | ((uint32_t)cb << 8) | ((uint32_t)cr << 16));
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t g = min(g0 + (uint32_t)u * NT, ngr - 1u);
+          const uint32_t wy = (yr.a0 + seg0 + 4u * g) >> 2;
+          yl[u] = __ldg(yr.base + wy); yh[u] = __ldg(yr.base + min(wy + 1u, yr.maxw));
         }
-        uint32_t w0, w1, w2;
-        pack_rgb_granule(v, w0, w1, w2);
-        sts32(st + 12u * lane, w0); sts32(st + 12u * lane + 4u, w1); sts32(st + 12u * lane + 8u, w2);
+        if (!held) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t g = min(g0 + (uint32_t)u * NT, ngr - 1u), cs = oc0 + ((4u * g) >> hs_sh);
+            const uint32_t wb = (br.a0 + cs) >> 2, wr = (rr.a0 + cs) >> 2;
+            bl[u] = __ldg(br.base + wb); bh[u] = __ldg(br.base + min(wb + 1u, br.maxw));
+            rl[u] = __ldg(rr.base + wr); rh[u] = __ldg(rr.base + min(wr + 1u, rr.maxw));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t g = g0 + (uint32_t)u * NT;
+          if (g < ngr) {
+            const uint32_t cs = oc0 + ((4u * g) >> hs_sh);
+            const uint32_t yw = __funnelshift_r(yl[u], yh[u], ((yr.a0 + seg0 + 4u * g) & 3u) * 8u);
+            uint32_t cbw = hcb, crw = hcr;
+            if (!held) {
+              cbw = __byte_perm(__funnelshift_r(bl[u], bh[u], ((br.a0 + cs) & 3u) * 8u), 0, csel);
+              crw = __byte_perm(__funnelshift_r(rl[u], rh[u], ((rr.a0 + cs) & 3u) * 8u), 0, csel);
+            }
+            uint32_t v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int y = (int)((yw >> (8 * j)) & 0xFFu), cb = (int)((cbw >> (8 * j)) & 0xFFu), cr = (int)((crw >> (8 * j)) & 0xFFu);
+              v[j] = to_rgb ? inverse_rgb(y, cb, cr) : ((uint32_t)y | ((uint32_t)cb << 8) | ((uint32_t)cr << 16));
+            }
+            uint32_t w0, w1, w2;
+            pack_rgb_granule(v, w0, w1, w2);
+            sts32(st + 12u * g, w0); sts32(st + 12u * g + 4u, w1); sts32(st + 12u * g + 8u, w2);
+          }
+        }
       }
-      __syncwarp();
-      const uint32_t bytes = min(32u * 12u, Wo * 3u - g0 * 12u);      // the row's last granule may hold fewer than four pixels
-      span_store(og, st, bytes, lane, 32u);
-      __syncwarp();
+      __syncthreads();
+      span_store(og, st, npx * 3u, tid, NT);                           // the row's last granule may hold fewer than four pixels
+      __syncthreads();
     }
   }
 }
@@ -575,8 +588,7 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
   // the row padding, so both pitches must cover Wp (dense buffers qualify when Wo % 16 == 0).
   k.Wp = (k.Wo + 15) & ~15;
   const bool planar = k.kformat == KF_PLANAR;
-  const bool staged0 = k.kformat <= KF_RGB888 || planar;
-  const uint32_t opx0 = planar ? 1u : (staged0 ? 3u : (uint32_t)k.slot_bytes);
+  const uint32_t opx0 = planar ? 1u : (k.kformat <= KF_RGB888 ? 3u : (uint32_t)k.slot_bytes);
   const uint64_t need_in = (uint64_t)k.Wp * (uint32_t)k.f * (uint32_t)k.in_px_bytes, need_out = (uint64_t)k.Wp * opx0;
   if (k.in_row_bytes < need_in || k.out_row_bytes < need_out) return false;
   if ((k.in_row_bytes | k.out_row_bytes) & 15u) return false;    // 16-byte TMA granularity of every row start
@@ -599,8 +611,13 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
   if (!k.case_b) k.hfe = std::max(1, k.hf / k.f);
   else k.hfe = k.hf;
 
-  const bool staged = k.kformat <= KF_RGB888 || planar;
-  const uint32_t opx = planar ? 1u : (staged ? 3u : (uint32_t)k.slot_bytes);
+  // 32-bit bundle slots at f == 1 leave through shared memory + TMA bulk stores like the 3-byte formats: there the
+  // output is larger than the input (4 B per 3 B pixel) and per-warp 512-byte st.global bursts held the kernel at 0.90
+  // of the copy peak (ncu: warps waiting on the store path, DRAM 70 % busy) -- 0.98 staged.  Narrower slots and f >= 2
+  // keep the direct stores (16-bit slots at f == 1: 0.94 direct, 0.83 staged; cfg4: 1.03).  Must match kStaged in
+  // csic_rows_kernel.cu.
+  const bool staged = k.kformat <= KF_RGB888 || planar || (k.f == 1 && k.kformat == KF_SLOT32);
+  const uint32_t opx = planar ? 1u : (k.kformat <= KF_RGB888 ? 3u : (uint32_t)k.slot_bytes);
   // Tile budget: input bytes of one tile.  Staged formats also hold two output buffers per CTA.
   const uint32_t tile_budget = force_tile_bytes ? force_tile_bytes : 24u * 1024u;
   const uint32_t ipb = (uint32_t)k.in_px_bytes;

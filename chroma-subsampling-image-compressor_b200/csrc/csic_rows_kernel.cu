@@ -108,21 +108,23 @@ __device__ __forceinline__ void tile_loop(uint32_t in_s, uint32_t out_s, uint8_t
       // (once per granule on a held row, every HFE-th pixel otherwise), the per-pixel part in emit()
       const uint32_t my8 = C.my << 8, mcb8 = C.mcb << 8, mcr8 = C.mcr << 8;
       const uint32_t a = out_s + q * 12u;
-      auto emit = [&](const InvChroma& t0, const InvChroma& t1, const InvChroma& t2, const InvChroma& t3) {
-        uint32_t w0, w1, w2;
-        inv_granule(dy, my8, t0, t1, t2, t3, w0, w1, w2);
-        sts32(a, w0); sts32(a + 4, w1); sts32(a + 8, w2);
-      };
+      // the chroma terms are chosen inside the branch, the per-pixel part runs once behind it: warps of narrow frames
+      // straddle a held and a sampled row, and would otherwise execute the (long) per-pixel part twice
+      InvChroma t[4];
       if (HELD && haddr != 0) {
         const uint32_t hp = lds8(haddr) | (lds8(haddr + 1) << 8) | (lds8(haddr + 2) << 16);
-        const InvChroma t = inv_chroma_terms(fwd_nc16<TRUNC>(hp, C.coef_ncb), fwd_nc16<TRUNC>(hp, C.coef_ncr), mcb8, mcr8);
-        emit(t, t, t, t);
+        t[0] = inv_chroma_terms(fwd_nc16<TRUNC>(hp, C.coef_ncb), fwd_nc16<TRUNC>(hp, C.coef_ncr), mcb8, mcr8);
+        t[1] = t[0]; t[2] = t[0]; t[3] = t[0];
       } else {
-        InvChroma t[4];
 #pragma unroll
-        for (int j = 0; j < 4; j += HFE) t[j] = inv_chroma_terms(fwd_nc16<TRUNC>(p[j], C.coef_ncb), fwd_nc16<TRUNC>(p[j], C.coef_ncr), mcb8, mcr8);
-        emit(t[0], t[1 - 1 % HFE], t[2 - 2 % HFE], t[3 - 3 % HFE]);
+        for (int j = 0; j < 4; ++j) {
+          if (j % HFE == 0) t[j] = inv_chroma_terms(fwd_nc16<TRUNC>(p[j], C.coef_ncb), fwd_nc16<TRUNC>(p[j], C.coef_ncr), mcb8, mcr8);
+          else t[j] = t[j - 1];
+        }
       }
+      uint32_t w0, w1, w2;
+      inv_granule(dy, my8, t[0], t[1], t[2], t[3], w0, w1, w2);
+      sts32(a, w0); sts32(a + 4, w1); sts32(a + 8, w2);
       continue;
     }
     if (HELD && haddr != 0) {
@@ -196,6 +198,13 @@ __device__ __forceinline__ void tile_loop(uint32_t in_s, uint32_t out_s, uint8_t
         for (int j = 0; j < 4; ++j) v[j] = (co + j < C.Wo) ? v[j] : 0u;
       }
       constexpr uint32_t kG = (FMT == KF_SLOT32) ? 16u : (FMT == KF_SLOT16 ? 8u : 4u);
+      if (F == 1 && FMT == KF_SLOT32) {   // staged like the 3-byte formats: rows back to back in the output buffer, TMA store per tile
+        const uint32_t a = out_s + q * kG;
+        if (FMT == KF_SLOT32) asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+        else if (FMT == KF_SLOT16) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v[0] | (v[1] << 16)), "r"(v[2] | (v[3] << 16)) : "memory");
+        else sts32(a, v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
+        continue;
+      }
       uint8_t* dst = out_g + (C.out_dense ? q * kG : orow * C.out_pitch + orem * kG);
       if (FMT == KF_SLOT32) {
         const uint4 w = make_uint4(v[0], v[1], v[2], v[3]);
@@ -235,7 +244,9 @@ __device__ __forceinline__ void tile_dispatch(bool held, int hfe, uint32_t in_s,
 template <int F, int FMT, bool Q8, bool TRUNC>
 __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(const __grid_constant__ KPlan P) {
   extern __shared__ __align__(128) uint8_t smem[];
-  constexpr bool kStaged = (FMT == KF_YCC888 || FMT == KF_RGB888 || FMT == KF_PLANAR);   // output leaves through smem + TMA store
+  // output leaves through smem + TMA store: the 3-byte formats, PLANAR, and 32-bit bundle slots at F == 1 (plan_rows_kernel)
+  constexpr bool kStaged = (FMT == KF_YCC888 || FMT == KF_RGB888 || FMT == KF_PLANAR) || (F == 1 && FMT == KF_SLOT32);
+  constexpr uint32_t kGranOut = (FMT == KF_PLANAR || FMT == KF_SLOT8) ? 4u : (FMT == KF_SLOT16 ? 8u : (FMT == KF_SLOT32 ? 16u : 12u));
   const uint32_t tid = threadIdx.x;
   const uint32_t NC = blockDim.x - 32u;        // consumer threads; the last warp is the producer
   const uint32_t sbase = smem_u32(smem);
@@ -378,7 +389,7 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(con
     const TileMeta* m = reinterpret_cast<const TileMeta*>(smem + P.meta_off) + s;
     uint8_t* out_g = reinterpret_cast<uint8_t*>(m->out_base);
     const uint32_t ngr = m->n_granules & 0x00FFFFFFu, nrc = m->n_granules >> 24;
-    const uint32_t out_bytes = ngr * (FMT == KF_PLANAR ? 4u : 12u);
+    const uint32_t out_bytes = ngr * kGranOut;
     const uint64_t cb_g = m->cb_base, cr_g = m->cr_base;
     if (in4) tile_dispatch<F, FMT, Q8, TRUNC, true>((m->any_held_col0 >> 31) != 0, hfe, in_s, out_s, out_g, m, C);
     else tile_dispatch<F, FMT, Q8, TRUNC, false>((m->any_held_col0 >> 31) != 0, hfe, in_s, out_s, out_g, m, C);

@@ -1,5 +1,8 @@
 """Performance map of the automatic kernel choice (run under gpurun): common and awkward resolutions x factor x
-format, device-resident batches of ~1.5 GB.  Prints kernel family and the fraction of the measured copy peak."""
+format.  Batches are sized by the ALGORITHMIC bytes of a launch (~2 GB, i.e. >= 0.3 ms at the copy peak; input capped at
+24 GB): round 1 sized them by input bytes (1.5 GB), which at f = 8 left 35 us launches whose ramp-up and tail cost 10 %
+(the same kernel measured 0.97 on a 1024-frame 4K batch and 0.84 here).  Prints kernel family and the fraction of the
+measured copy peak."""
 import itertools
 import os
 import sys
@@ -22,9 +25,10 @@ worst = []
 for (W, H), f, (fmt, q), order, pool in itertools.product(sizes, (1, 2, 4, 8), ((0, (8, 8, 8)), (3, (8, 8, 8)), (1, (6, 5, 5))), orders, pools):
     if pool and (f == 1 or W % f or H % f):
         continue
-    frames = max(2, int(1.5e9 // (W * H * 3)))
     p = csic.make_params(W, H, 2, 0, q[0], q[1], q[2], f, tuple(ORD[c] for c in order), pool_mode=pool, out_format=fmt)
     fb = csic.out_shape(p)[3]
+    per_frame = algorithmic_bytes_per_frame(W, H, f, fb, average=bool(pool))
+    frames = max(2, min(int(2.0e9 // per_frame), int(24e9 // (W * H * 3))))
     rgb = torch.empty((frames, H, W, 3), dtype=torch.uint8, device="cuda")
     rgb.random_(0, 256)
     out = torch.empty((frames, fb), dtype=torch.uint8, device="cuda")
