@@ -42,7 +42,8 @@ constexpr int kFlexMaxThreads = 288;                 // 8 consumer warps + the p
 constexpr uint32_t kFlexTileBytes = 24u * 1024u;     // input bytes of one tile (B200 sweep: profiles/r1/sweep_flex.txt)
 constexpr uint32_t kCtaWideSpan = 2048u;             // row spans at least this long are stored by the whole CTA
 constexpr uint32_t kDescBytes = 80u;
-constexpr uint32_t kDirectRowBytes = 1024u;          // output rows shorter than this that cannot be packed leave from registers
+constexpr uint32_t kDirectRowBytes = 257u;           // output rows shorter than this that cannot be packed leave from registers (B200 map:
+                                                     // 75-250-byte rows 1.3x faster direct, 375-1000-byte rows up to 2x faster staged)
 
 __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) {
   asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
@@ -134,38 +135,6 @@ __device__ __forceinline__ void load_granule_any(uint32_t a, uint32_t pxb, uint3
   }
 }
 
-// A granule's output bytes straight from registers to global memory (rows too narrow for the staged path to pay: there
-// every 150-byte row costs a warp ~120 instructions of span_store set-up, head and tail).  `w` holds the granule's
-// little-endian words, `nbytes` of which exist (the row's last granule may be partial); the widest stores the address
-// allows -- words, half words or bytes.  Rows are contiguous in memory and written by one CTA within microseconds, so
-// L2 merges the partial sectors before they reach HBM.
-template <int NW_>
-__device__ __forceinline__ void direct_store(uint8_t* __restrict__ gp, const uint32_t (&w)[NW_], uint32_t nbytes) {
-  const uint32_t al = (uint32_t)reinterpret_cast<uintptr_t>(gp) & 3u;
-  if (al == 0u) {
-#pragma unroll
-    for (int i = 0; i < NW_; ++i) {
-      if (4u * i + 4u <= nbytes) __stcs(reinterpret_cast<uint32_t*>(gp) + i, w[i]);
-      else {
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-          if (4u * i + b < nbytes) gp[4 * i + b] = (uint8_t)(w[i] >> (8 * b));
-      }
-    }
-  } else if (al == 2u) {
-#pragma unroll
-    for (int i = 0; i < 2 * NW_; ++i) {
-      const uint32_t h = (w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
-      if (2u * i + 2u <= nbytes) __stcs(reinterpret_cast<unsigned short*>(gp) + i, (unsigned short)h);
-      else if (2u * i < nbytes) gp[2 * i] = (uint8_t)h;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4 * NW_; ++i)
-      if ((uint32_t)i < nbytes) gp[i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
-  }
-}
-
 template <int FMT> struct FlexFmt {
   // staging bytes per granule of four slots
   static constexpr uint32_t kUnit = (FMT == KF_YCC888 || FMT == KF_RGB888) ? 12u : (FMT == KF_SLOT32 ? 16u : (FMT == KF_SLOT16 ? 8u : 4u));
@@ -190,7 +159,7 @@ static_assert(sizeof(FlexDesc) == kDescBytes, "kDescBytes out of sync");
 }  // namespace
 
 // The consumer warps' loop over this CTA's tiles.
-template <int FMT, bool TRUNC, uint32_t HFE, uint32_t PXB>
+template <int FMT, bool TRUNC, uint32_t HFE, uint32_t PXB, bool DIRECT>
 __device__ __forceinline__ void flex_consume(const KPlan& P, uint8_t* smem, uint32_t n_my) {
   constexpr uint32_t kUnit = FlexFmt<FMT>::kUnit, kOpx = kUnit / 4u;
   const uint32_t tid = threadIdx.x, NC = blockDim.x - 32u, NW = NC >> 5;
@@ -223,7 +192,7 @@ __device__ __forceinline__ void flex_consume(const KPlan& P, uint8_t* smem, uint
     const uint4 d0 = lds128(da), d1 = lds128(da + 16u), d2 = lds128(da + 32u), d3 = lds128(da + 48u);
     const uint4 d4 = lds128(da + 64u);   // row_out, out_one, ncols, direct
     const uint32_t Dk = d0.x, Dro0 = d0.y, Dnrows = d0.z, Dcol0 = d0.w, Dnpx = d1.x, Da0 = d1.y;
-    const bool direct = d4.w != 0u;
+    constexpr bool direct = DIRECT;      // launch-wide (every tile of a launch has the same row geometry when nsplit == 1)
     consumer_barrier(NC);          // the previous tile has left the staging area
 
     // ---- compute -------------------------------------------------------------------------------------------
@@ -255,6 +224,9 @@ __device__ __forceinline__ void flex_consume(const KPlan& P, uint8_t* smem, uint
 #pragma unroll
       for (int j = 0; j < 4; ++j) dy[j] = fwd_y16(p[j], P.coef_y);
       const uint32_t so = so_row + g * kUnit;
+      // direct mode: this granule's first output byte in global memory and how many of its bytes exist in the row
+      uint8_t* gp = obase + (uint64_t)row * P.out_row_bytes + g * kUnit;
+      const uint32_t gbytes = min(kUnit, d4.x - g * kUnit);
       if (FMT == KF_RGB888) {
         // fused reconstruction: the chroma-only part of YCbCr2RGB per chroma SAMPLE (once per granule on a held row,
         // every HFE-th pixel otherwise), the per-pixel part in emit()
@@ -262,7 +234,8 @@ __device__ __forceinline__ void flex_consume(const KPlan& P, uint8_t* smem, uint
         auto emit = [&](const InvChroma& t0, const InvChroma& t1, const InvChroma& t2, const InvChroma& t3) {
           uint32_t w0, w1, w2;
         inv_granule(dy, my8, t0, t1, t2, t3, w0, w1, w2);
-          sts32(so, w0); sts32(so + 4, w1); sts32(so + 8, w2);
+          if (direct) { const uint32_t ww[3] = {w0, w1, w2}; direct_store(gp, ww, gbytes); }
+          else { sts32(so, w0); sts32(so + 4, w1); sts32(so + 8, w2); }
         };
         if (hv) {
           const InvChroma t = inv_chroma_terms(fwd_nc16<TRUNC>(hv & 0x00FFFFFFu, P.coef_ncb), fwd_nc16<TRUNC>(hv & 0x00FFFFFFu, P.coef_ncr), mcb8, mcr8);
@@ -291,13 +264,15 @@ __device__ __forceinline__ void flex_consume(const KPlan& P, uint8_t* smem, uint
       }
       if (FMT == KF_YCC888) {
         // byte 1 of dy is Y, byte 1 of xb/xr is ~Cb/~Cr: gather with PRMT, flip and quantise per word
-        uint32_t t, u;
+        uint32_t t, u, ww[3];
         t = __byte_perm(dy[0], xb[0], 0x0051); u = __byte_perm(xr[0], dy[1], 0x0051);
-        sts32(so, (__byte_perm(t, u, 0x5410) ^ 0x00FFFF00u) & qm0);
+        ww[0] = (__byte_perm(t, u, 0x5410) ^ 0x00FFFF00u) & qm0;
         t = __byte_perm(xb[1], xr[1], 0x0051); u = __byte_perm(dy[2], xb[2], 0x0051);
-        sts32(so + 4, (__byte_perm(t, u, 0x5410) ^ 0xFF00FFFFu) & qm1);
+        ww[1] = (__byte_perm(t, u, 0x5410) ^ 0xFF00FFFFu) & qm1;
         t = __byte_perm(xr[2], dy[3], 0x0051); u = __byte_perm(xb[3], xr[3], 0x0051);
-        sts32(so + 8, (__byte_perm(t, u, 0x5410) ^ 0xFFFF00FFu) & qm2);
+        ww[2] = (__byte_perm(t, u, 0x5410) ^ 0xFFFF00FFu) & qm2;
+        if (direct) direct_store(gp, ww, gbytes);
+        else { sts32(so, ww[0]); sts32(so + 4, ww[1]); sts32(so + 8, ww[2]); }
       } else if (FMT == KF_PLANAR) {
         const uint32_t my4 = my * 0x01010101u;
         sts32(so, __byte_perm(__byte_perm(dy[0], dy[1], 0x0051), __byte_perm(dy[2], dy[3], 0x0051), 0x5410) & my4);
@@ -329,7 +304,11 @@ __device__ __forceinline__ void flex_consume(const KPlan& P, uint8_t* smem, uint
 #pragma unroll
           for (int j = 0; j < 4; ++j) if (c + j > last_px) v[j] = 0u;
         }
-        if (FMT == KF_SLOT32) {
+        if (direct) {
+          if (FMT == KF_SLOT32) direct_store(gp, v, gbytes);
+          else if (FMT == KF_SLOT16) { const uint32_t ww[2] = {v[0] | (v[1] << 16), v[2] | (v[3] << 16)}; direct_store(gp, ww, gbytes); }
+          else { const uint32_t ww[1] = {v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24)}; direct_store(gp, ww, gbytes); }
+        } else if (FMT == KF_SLOT32) {
           if ((so & 15u) == 0) sts128(so, v[0], v[1], v[2], v[3]);
           else if ((so & 7u) == 0) { sts64(so, v[0], v[1]); sts64(so + 8, v[2], v[3]); }
           else { sts32(so, v[0]); sts32(so + 4, v[1]); sts32(so + 8, v[2]); sts32(so + 12, v[3]); }
@@ -369,7 +348,9 @@ __device__ __forceinline__ void flex_consume(const KPlan& P, uint8_t* smem, uint
     if (tid == 0) mbar_arrive(empty0 + s * 8u);
 
     // ---- store ---------------------------------------------------------------------------------------------
-    if (d4.y) {
+    if (direct) {
+      // nothing staged: the granules went out from registers
+    } else if (d4.y) {
       span_store(obase, out_s + (oa0 & 12u), Dnrows * d4.x, tid, NC);
     } else {
       for_each_span(Dnrows, d4.x, NC, [&](uint32_t j, uint32_t t, uint32_t n) {
@@ -501,7 +482,7 @@ __global__ void __launch_bounds__(kFlexMaxThreads, 4) csic_flex_kernel(const __g
         d->mode = mode; d->sh = sh; d->magic = gpr > 1u ? 0xFFFFFFFFu / gpr + 1u : 0u;   // q / gpr == umulhi(q, magic) for q < 65536
         d->n_gran = nrows * gpr;
         d->row_out = row_out; d->out_one = out_one; d->ncols = ncols;
-        d->direct = (!out_one && row_out < kDirectRowBytes && FMT != KF_PLANAR) ? 1u : 0u;
+        d->direct = 0u;   // (the consumers decide launch-wide: see the dispatch at the end of the kernel)
       }
       if (P.in_dense) {            // consecutive rows are contiguous in memory: one span
         if (lane == 0) span_fetch(in_s, src0, (nrows - 1u) * P.in_row_bytes + len_in, bar, pol, lim_lo, lim_hi);
@@ -533,11 +514,20 @@ __global__ void __launch_bounds__(kFlexMaxThreads, 4) csic_flex_kernel(const __g
   // One specialisation per (chroma hold width, pixel stride class), chosen once per CTA: no per-tile dispatch, and a
   // CTA only ever runs one copy of the loop (the nine copies used to thrash the instruction cache: ncu showed
   // `no_instruction` stalls of 1.3 per issue on 1366x768 f = 2).
+  // narrow output rows that cannot be packed into one span leave from registers (direct_store): a separate
+  // specialisation, so that the staged one carries none of its code and registers
+  const uint32_t row_out_full = min((uint32_t)P.tile_px, (uint32_t)P.slots_per_row) * kOpx;
+  const bool out_one_full = P.out_dense && nsplit == 1u && row_out_full == ((min((uint32_t)P.tile_px, (uint32_t)P.slots_per_row) + 3u) >> 2) * kUnit;
+  const bool direct = FMT != KF_PLANAR && nsplit == 1u && !out_one_full && row_out_full < kDirectRowBytes;
   auto run = [&](auto hfe_tag) {
     constexpr uint32_t H = decltype(hfe_tag)::value;
-    if (pxb == 3u) flex_consume<FMT, TRUNC, H, 3u>(P, smem, n_my);          // RGB24, f = 1
-    else if (pxb == 6u) flex_consume<FMT, TRUNC, H, 6u>(P, smem, n_my);     // RGB24, f = 2
-    else flex_consume<FMT, TRUNC, H, 0u>(P, smem, n_my);                    // sampled pixels on a common byte phase
+    if (direct) {
+      if (pxb == 3u) flex_consume<FMT, TRUNC, H, 3u, true>(P, smem, n_my);
+      else if (pxb == 6u) flex_consume<FMT, TRUNC, H, 6u, true>(P, smem, n_my);
+      else flex_consume<FMT, TRUNC, H, 0u, true>(P, smem, n_my);
+    } else if (pxb == 3u) flex_consume<FMT, TRUNC, H, 3u, false>(P, smem, n_my);          // RGB24, f = 1
+    else if (pxb == 6u) flex_consume<FMT, TRUNC, H, 6u, false>(P, smem, n_my);     // RGB24, f = 2
+    else flex_consume<FMT, TRUNC, H, 0u, false>(P, smem, n_my);                    // sampled pixels on a common byte phase
   };
   if (hfe == 1u) run(std::integral_constant<uint32_t, 1u>{});
   else if (hfe == 2u) run(std::integral_constant<uint32_t, 2u>{});

@@ -34,8 +34,10 @@ namespace csic {
 // every parameter set when a test forces it (CSIC_OPT_KERNEL_FAMILY = 1), which makes it the independent second
 // implementation the other kernels are cross-checked against.
 //
-// One CTA per output row (grid-stride); the frame / row split -- the only division outside the case-B source map --
-// happens once per row.  A thread computes one granule of four output slots:
+// One WARP per output row (grid-stride) -- or, when a row has fewer than 32 granules, as many whole rows as fit its
+// 32 lanes (a 96x96 frame pooled 8x8 has three granules per row: one row per CTA left 125 of 128 threads idle, 0.02 of
+// the copy peak).  The frame / row split and, for case B, the split of the row into counter lines are the only
+// divisions and happen once per row.  A thread computes one granule of four output slots:
 //   load    every pixel is three bytes at an arbitrary address = two aligned LDG.32 and a funnel shift through L1 (the
 //           second word never lies beyond the last word that holds a byte of the input); a thread's loads are all
 //           independent, so a warp keeps 8 .. 200 of them in flight;
@@ -43,7 +45,8 @@ namespace csic {
 //           hfe divides 4), held lines replay one pixel per row; case B (ImageCompressorTop.scala:52-58) maps every
 //           element through the full-size counters;
 //   store   a warp's 32 granules are consecutive output bytes: staged in the warp's shared-memory slot at the output's
-//           own offset modulo 16 and written as 16-byte st.global.cs aligned on the GLOBAL address (span_store).
+//           own offset modulo 16 and written as 16-byte st.global.cs aligned on the GLOBAL address (span_store); narrow
+//           rows (several per warp) leave from registers with the widest stores their address allows (direct_store).
 // Round 1's version -- one thread per slot, three divisions, byte loads and byte stores -- ran at 0.13 - 0.30 of the
 // copy peak.
 
@@ -111,7 +114,15 @@ __global__ void __launch_bounds__(128) csic_generic_kernel(const __grid_constant
   const uint32_t sbase = smem_u32(stage[warp]);
   const int fsh = 31 - __clz(P.f);                                          // log2(f)
 
-  for (uint32_t R = blockIdx.x; R < n_rows; R += gridDim.x) {
+  // lanes -> (row of the warp's group, granule): wide rows take the whole warp, narrow ones share it
+  const bool narrow = gpr < 32u;
+  const uint32_t rpw = narrow ? 32u / gpr : 1u;                              // rows per warp and trip
+  const uint32_t sub = narrow ? lane / gpr : 0u, gl = narrow ? lane - sub * gpr : lane;
+  const uint32_t n_groups = (n_rows + rpw - 1u) / rpw, nwarps = blockDim.x >> 5;
+  for (uint32_t grp = blockIdx.x * nwarps + warp; grp < n_groups; grp += gridDim.x * nwarps) {
+    const uint32_t Rw = grp * rpw + sub;
+    const bool row_ok = sub < rpw && Rw < n_rows;                            // lanes beyond the warp's last row idle (they still
+    const uint32_t R = min(Rw, n_rows - 1u);                                 // compute, on a valid row, and store nothing)
     const uint32_t k = R / (uint32_t)P.band_rows, ro = (uint32_t)P.row0 + (R - k * (uint32_t)P.band_rows);
     const uint8_t* frame = P.in + (uint64_t)k * P.in_frame_bytes;
     uint8_t* fout = P.out + (uint64_t)k * P.out_frame_bytes;
@@ -142,8 +153,33 @@ __global__ void __launch_bounds__(128) csic_generic_kernel(const __grid_constant
         hxb[h] = fwd_nc16<TRUNC>(hp, P.coef_ncb); hxr[h] = fwd_nc16<TRUNC>(hp, P.coef_ncr);
       }
     }
-    for (uint32_t g0 = warp * 32u; g0 < gpr; g0 += blockDim.x) {            // warp uniform
-      const uint32_t g = g0 + lane, c0 = 4u * g;
+    // Case B (spatial before chroma, DECIMATE): the chroma stage walks the DECIMATED stream with the full-size counters
+    // (ImageCompressorTop.scala:52-58), so a counter line is W stream elements = W / Wo output rows, and an output row
+    // lies in at most two lines (W >= Wo).  Per row: the column where the second line starts, and for each of the two
+    // lines either its held pair (odd line, vf == 2: element (line-1) * W + lastSampleCol) or the phase of its hold
+    // groups.  Per pixel nothing is divided any more.
+    uint32_t cb_split = 0xFFFFFFFFu, cb_ph[1] = {0u}, cb_hxb[2] = {0u, 0u}, cb_hxr[2] = {0u, 0u};
+    bool cb_held[2] = {false, false};
+    GRow prev_row = rows[0];
+    if (!avg && P.case_b) {
+      const uint32_t m0 = ro * Wo, line0 = m0 / (uint32_t)P.W, col0 = m0 - line0 * (uint32_t)P.W;
+      cb_split = (uint32_t)P.W - col0;                                       // first column of the row that lies in line0 + 1
+#pragma unroll
+      for (int l = 0; l < 2; ++l) {
+        const uint32_t line = line0 + (uint32_t)l;
+        if (l == 0) cb_ph[0] = col0 & hfm;                                   // (column in its line) mod hf of the row's first pixel; 0 for the second line
+        if (P.vf == 2 && (line & 1u) && (l == 0 || cb_split < Wo)) {
+          const uint32_t src = (line - 1u) * (uint32_t)P.W + (uint32_t)P.last_sample_col, sro = src / Wo, sco = src - sro * Wo;
+          const GRow hr = grow_at(in_row(sro * f), last_word);
+          const uint32_t hp = grow_px(hr, sco * pxb);
+          cb_hxb[l] = fwd_nc16<TRUNC>(hp, P.coef_ncb); cb_hxr[l] = fwd_nc16<TRUNC>(hp, P.coef_ncr);
+          cb_held[l] = true;
+        }
+      }
+      if (ro > 0u) prev_row = grow_at(in_row((ro - 1u) * f), last_word);    // a hold group may start at the end of the row above
+    }
+    for (uint32_t g0 = 0; g0 < gpr; g0 += 32u) {                             // warp uniform; one trip when the rows are narrow
+      const uint32_t g = narrow ? gl : g0 + lane, c0 = 4u * g;
       uint8_t* og = orow + (size_t)g0 * kG;                                  // first output byte of this warp's group
       const uint32_t st = sbase + ((uint32_t)reinterpret_cast<uintptr_t>(og) & 12u);
       if (g < gpr) {
@@ -172,11 +208,25 @@ __global__ void __launch_bounds__(128) csic_generic_kernel(const __grid_constant
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              int sro, sco;
-              chroma_src_case_b(P, (int)ro, (int)min(c0 + j, Wo - 1u), sro, sco);
-              const GRow cr_ = grow_at(in_row((uint32_t)sro * f), last_word);
-              const uint32_t pc = grow_px(cr_, (uint32_t)sco * pxb);
-              xb[j] = fwd_nc16<TRUNC>(pc, P.coef_ncb); xr[j] = fwd_nc16<TRUNC>(pc, P.coef_ncr);
+              const uint32_t co = min(c0 + j, Wo - 1u);
+              const bool l = co >= cb_split;                                 // which of the row's two counter lines
+              if (l ? cb_held[1] : cb_held[0]) {
+                xb[j] = l ? cb_hxb[1] : cb_hxb[0]; xr[j] = l ? cb_hxr[1] : cb_hxr[0];
+              } else {
+                // sampled line: the pixel replays the first element of its hold group, (col - col % hf); the group may
+                // begin in the row above (never further back: hf - 1 <= 3 elements; rows narrower than that divide)
+                const uint32_t back = (l ? co - cb_split : co + cb_ph[0]) & hfm;
+                uint32_t pc;
+                if (back == 0u) pc = p[j];
+                else if (back <= co) pc = grow_px(rows[0], (co - back) * pxb);
+                else if (Wo + co >= back) pc = grow_px(prev_row, (Wo + co - back) * pxb);
+                else {
+                  int sro, sco;
+                  chroma_src_case_b(P, (int)ro, (int)co, sro, sco);
+                  pc = grow_px(grow_at(in_row((uint32_t)sro * f), last_word), (uint32_t)sco * pxb);
+                }
+                xb[j] = fwd_nc16<TRUNC>(pc, P.coef_ncb); xr[j] = fwd_nc16<TRUNC>(pc, P.coef_ncr);
+              }
             }
           }
 #pragma unroll
@@ -231,19 +281,20 @@ __global__ void __launch_bounds__(128) csic_generic_kernel(const __grid_constant
             if (!P.quant_first) { y[j] &= my; cb[j] &= mcb; cr[j] &= mcr; }
           }
         }
-        // ---- pack the granule into the warp's staging slot ----
+        // ---- pack the granule: into the warp's staging slot, or (narrow rows) straight to global memory ----
         const uint32_t so = st + kG * lane;
+        uint8_t* gp = orow + (size_t)g * kG;
+        const uint32_t gbytes = min(kG, row_bytes - g * kG);                  // the row's last granule may be partial
+        uint32_t ww[kG / 4u];
         if (FMT == KF_YCC888 || FMT == KF_RGB888) {
           uint32_t v[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             v[j] = FMT == KF_RGB888 ? inverse_rgb((int)y[j], (int)cb[j], (int)cr[j]) : (y[j] | (cb[j] << 8) | (cr[j] << 16));
-          uint32_t w0, w1, w2;
-          pack_rgb_granule(v, w0, w1, w2);
-          sts32(so, w0); sts32(so + 4u, w1); sts32(so + 8u, w2);
+          pack_rgb_granule(v, ww[0], ww[1], ww[2]);
         } else if (FMT == KF_PLANAR) {
-          sts32(so, y[0] | (y[1] << 8) | (y[2] << 16) | (y[3] << 24));
-          if (ro % (uint32_t)P.planar_vs == 0u) {                            // surviving chroma sample points of this row
+          ww[0] = y[0] | (y[1] << 8) | (y[2] << 16) | (y[3] << 24);
+          if (row_ok && ro % (uint32_t)P.planar_vs == 0u) {                  // surviving chroma sample points of this row
             const size_t crow = (size_t)(ro / (uint32_t)P.planar_vs) * (size_t)P.planar_cw;
 #pragma unroll
             for (uint32_t j = 0; j < 4u; ++j)
@@ -258,11 +309,18 @@ __global__ void __launch_bounds__(128) csic_generic_kernel(const __grid_constant
           for (int j = 0; j < 4; ++j)
             v[j] = (c0 + j < Wo) ? ((y[j] >> P.sy) << (P.cb_bits + P.cr_bits)) | ((cb[j] >> P.scb) << P.cr_bits) | (cr[j] >> P.scr)
                                  : 0u;                                        // BUNDLE row padding: zero slots
-          if (FMT == KF_SLOT32) { sts32(so, v[0]); sts32(so + 4u, v[1]); sts32(so + 8u, v[2]); sts32(so + 12u, v[3]); }
-          else if (FMT == KF_SLOT16) { sts32(so, v[0] | (v[1] << 16)); sts32(so + 4u, v[2] | (v[3] << 16)); }
-          else sts32(so, v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
+          if (FMT == KF_SLOT32) { ww[0] = v[0]; ww[kG / 4u > 1u ? 1 : 0] = v[1]; ww[kG / 4u > 2u ? 2 : 0] = v[2]; ww[kG / 4u > 3u ? 3 : 0] = v[3]; }
+          else if (FMT == KF_SLOT16) { ww[0] = v[0] | (v[1] << 16); ww[kG / 4u > 1u ? 1 : 0] = v[2] | (v[3] << 16); }
+          else ww[0] = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+        }
+        if (narrow) {
+          if (row_ok) direct_store(gp, ww, gbytes);
+        } else {
+#pragma unroll
+          for (uint32_t i = 0; i < kG / 4u; ++i) sts32(so + 4u * i, ww[i]);
         }
       }
+      if (narrow) break;                                                     // the rows of this trip are done
       __syncwarp();
       span_store(og, st, min(32u * kG, row_bytes - g0 * kG), lane, 32u);   // the row's last granule may be partial
       __syncwarp();
@@ -561,9 +619,11 @@ int launch_generic(const KPlan& k, int sm_count, void* stream) {
   const uint64_t n_rows = (uint64_t)k.n_frames * (uint64_t)k.band_rows;
   if (n_rows == 0 || k.slots_per_row == 0) return (int)cudaSuccess;
   if (n_rows >= (1ull << 32)) return (int)cudaErrorInvalidValue;
+  // one warp per row, or per 32 / gpr rows when a row has fewer than 32 granules; four warps per CTA
   const uint32_t gpr = ((uint32_t)k.slots_per_row + 3u) >> 2;
-  const unsigned threads = (unsigned)std::min<uint32_t>(128u, (gpr + 31u) & ~31u);
-  const unsigned blocks = (unsigned)std::min<uint64_t>(n_rows, (uint64_t)sm_count * (2048u / threads));
+  const uint64_t groups = gpr < 32u ? (n_rows + 32u / gpr - 1u) / (32u / gpr) : n_rows;
+  const unsigned threads = 128u;
+  const unsigned blocks = (unsigned)std::min<uint64_t>((groups + 3u) / 4u, (uint64_t)sm_count * 16u);
   cudaStream_t st = (cudaStream_t)stream;
   switch (k.kformat) {
     case KF_YCC888: return launch_generic_fmt<KF_YCC888>(k, blocks, threads, st);
@@ -644,6 +704,11 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
     rows = std::min(rows, k.band_rows);
     auto tiles_for = [&](int r) { return (uint64_t)k.n_frames * (uint64_t)((k.band_rows + r - 1) / r); };
     while (rows > 1 && tiles_for(rows) < (uint64_t)sm_count * 4u) rows = (rows + 1) / 2;
+    // staged 32-bit slots: a tile's two output buffers are larger than its input stages; keep two CTAs resident
+    // (4096-pixel rows: two rows per tile left room for one CTA only -- 0.81 of the copy peak instead of 0.98)
+    if (staged && !planar && k.kformat > KF_RGB888)
+      while (rows > 1 && 2u * ((uint32_t)rows * (k.tile_in_bytes + 32u)) + 2u * ((uint32_t)rows * k.tile_out_bytes) + 2048u > 227u * 1024u / 2u - 1024u)
+        --rows;
     if (planar && rows > 1) rows &= ~(k.planar_vs - 1);          // tiles start on a chroma row
     if (rows < 1) rows = 1;
   }

@@ -133,5 +133,37 @@ __device__ __forceinline__ void span_store(uint8_t* __restrict__ g, uint32_t ssr
 }
 
 
+// A granule's output bytes straight from registers to global memory (rows too narrow for the staged path to pay: there
+// every 150-byte row costs a warp ~120 instructions of span_store set-up, head and tail).  `w` holds the granule's
+// little-endian words, `nbytes` of which exist (the row's last granule may be partial); the widest stores the address
+// allows -- words, half words or bytes.  Rows are contiguous in memory and written by one CTA within microseconds, so
+// L2 merges the partial sectors before they reach HBM.
+template <int NW_>
+__device__ __forceinline__ void direct_store(uint8_t* __restrict__ gp, const uint32_t (&w)[NW_], uint32_t nbytes) {
+  const uint32_t al = (uint32_t)reinterpret_cast<uintptr_t>(gp) & 3u;
+  if (al == 0u) {
+#pragma unroll
+    for (int i = 0; i < NW_; ++i) {
+      if (4u * i + 4u <= nbytes) __stcs(reinterpret_cast<uint32_t*>(gp) + i, w[i]);
+      else {
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (4u * i + b < nbytes) gp[4 * i + b] = (uint8_t)(w[i] >> (8 * b));
+      }
+    }
+  } else if (al == 2u) {
+#pragma unroll
+    for (int i = 0; i < 2 * NW_; ++i) {
+      const uint32_t h = (w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+      if (2u * i + 2u <= nbytes) __stcs(reinterpret_cast<unsigned short*>(gp) + i, (unsigned short)h);
+      else if (2u * i < nbytes) gp[2 * i] = (uint8_t)h;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4 * NW_; ++i)
+      if ((uint32_t)i < nbytes) gp[i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+  }
+}
+
 }  // namespace csic
 #endif  // CSIC_TMA_CUH_
