@@ -579,7 +579,6 @@ def main():
     ap.add_argument("--stages", type=int, default=0)
     ap.add_argument("--tile-bytes", type=int, default=0)
     ap.add_argument("--block-threads", type=int, default=0)
-    ap.add_argument("--store-policy", type=int, default=0, choices=[0, 1, 2])
     ap.add_argument("--chunk-mb", type=int, default=0, help="csic_process_host chunk size (CSIC_OPT_HOST_CHUNK_BYTES)")
     ap.add_argument("--shard", default="frames", choices=["frames", "bands"],
                     help="frames: every rank owns its own batch (weak scaling).  bands: every rank owns one aligned "
@@ -610,8 +609,6 @@ def main():
         ctx.set_option(4, args.tile_bytes)
     if args.block_threads:
         ctx.set_option(5, args.block_threads)
-    if args.store_policy:
-        ctx.set_option(8, args.store_policy)
     if args.chunk_mb:
         ctx.set_option(1, args.chunk_mb << 20)
     default_run = args.workload == "cfg4" and args.shard == "frames" and not args.family

@@ -78,7 +78,6 @@ struct csic_ctx {
   uint32_t opt_tile_bytes = 0;
   int opt_block_threads = 0;
   int opt_no_compact = 0;
-  int opt_store_policy = 0;
   uint64_t h2d_bytes = 0;    // bytes csic_process_host has shipped host -> device so far
 };
 
@@ -201,7 +200,6 @@ int run(csic_ctx* ctx, const csic_params* p, const void* d_rgb, size_t n_frames,
   DeviceGuard guard(ctx->device);
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
   k.block_threads = ctx->opt_block_threads;
-  k.store_policy = ctx->opt_store_policy;
   int err;
   if (ctx->opt_family == 0 && csic::plan_rows_kernel(k, ctx->sm_count, ctx->max_smem_optin, ctx->opt_stages, ctx->opt_tile_bytes)) {
     err = csic::launch_rows(k, ctx->sm_count, ctx->opt_ctas_per_sm, st);
@@ -351,10 +349,6 @@ int csic_set_option(csic_ctx* ctx, int option, int64_t value) {
       return CSIC_OK;
     case CSIC_OPT_HOST_NO_BOUNCE:
       ctx->opt_no_bounce = value != 0;
-      return CSIC_OK;
-    case CSIC_OPT_STORE_POLICY:
-      if (value < 0 || value > 2) return CSIC_EINVAL_ARG;
-      ctx->opt_store_policy = (int)value;
       return CSIC_OK;
     case CSIC_OPT_TILE_BYTES:
       if (value < 0 || value > (200 << 10)) return CSIC_EINVAL_ARG;

@@ -52,7 +52,6 @@ struct KPlan {
   int32_t compact;                       // input holds only the rows a DECIMATE pipeline reads (every f-th), densely
   int32_t row_step;                      // input rows between consecutive output rows: f, or 1 when compact
   uint32_t n_frames;
-  int32_t store_policy;                  // CSIC_OPT_STORE_POLICY (row kernel): 0 streaming / evict-first stores, 1 default write-back, 2 .cg
   // ---- TMA row kernel only ----
   int32_t hfe;                           // chroma hold width in *output* pixels inside a 4-pixel granule
   int32_t nsplit, tile_px;               // segments per output row, output pixels per row segment

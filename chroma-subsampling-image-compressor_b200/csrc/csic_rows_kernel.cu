@@ -73,7 +73,6 @@ struct LoopConst {
   uint32_t gran_per_row;
   uint32_t out_pitch, out_dense, ragged, Wo;  // pitched / padded output rows (see KPlan)
   uint32_t pl_cb_off, pl_cr_off, pl_crow_bytes, pl_vs_shift;   // PLANAR staging: region offsets, bytes per chroma row
-  uint32_t st_mode;                          // bundle stores: 0 st.global.cs (streaming), 1 default write-back, 2 st.global.cg
   uint32_t nthreads;                         // consumer threads per CTA
   uint32_t row0_of_thread, rem0_of_thread;   // threadIdx.x / gran_per_row, threadIdx.x % gran_per_row
   uint32_t drow, drem;                       // blockDim.x / gran_per_row, blockDim.x % gran_per_row
@@ -206,22 +205,9 @@ __device__ __forceinline__ void tile_loop(uint32_t in_s, uint32_t out_s, uint8_t
         continue;
       }
       uint8_t* dst = out_g + (C.out_dense ? q * kG : orow * C.out_pitch + orem * kG);
-      if (FMT == KF_SLOT32) {
-        const uint4 w = make_uint4(v[0], v[1], v[2], v[3]);
-        if (C.st_mode == 0u) __stcs(reinterpret_cast<uint4*>(dst), w);
-        else if (C.st_mode == 1u) *reinterpret_cast<uint4*>(dst) = w;
-        else __stcg(reinterpret_cast<uint4*>(dst), w);
-      } else if (FMT == KF_SLOT16) {
-        const uint2 w = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
-        if (C.st_mode == 0u) __stcs(reinterpret_cast<uint2*>(dst), w);
-        else if (C.st_mode == 1u) *reinterpret_cast<uint2*>(dst) = w;
-        else __stcg(reinterpret_cast<uint2*>(dst), w);
-      } else {
-        const uint32_t w = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
-        if (C.st_mode == 0u) __stcs(reinterpret_cast<uint32_t*>(dst), w);
-        else if (C.st_mode == 1u) *reinterpret_cast<uint32_t*>(dst) = w;
-        else __stcg(reinterpret_cast<uint32_t*>(dst), w);
-      }
+      if (FMT == KF_SLOT32) __stcs(reinterpret_cast<uint4*>(dst), make_uint4(v[0], v[1], v[2], v[3]));
+      else if (FMT == KF_SLOT16) __stcs(reinterpret_cast<uint2*>(dst), make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16)));
+      else __stcs(reinterpret_cast<uint32_t*>(dst), v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
     }
   }
 }
@@ -253,7 +239,6 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(con
   const uint32_t S = (uint32_t)P.stages;
   const uint32_t n_my = (P.n_tiles > blockIdx.x) ? (P.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const uint64_t pol = policy_evict_first();   // every byte is touched exactly once: do not keep it in L2
-  const uint64_t pol_st = P.store_policy == 1 ? policy_evict_normal() : pol;   // experiment knob (CSIC_OPT_STORE_POLICY)
   const uint32_t full_bar = sbase + P.bar_off, empty_bar = full_bar + S * 8u;
 
   if (tid == 0) {
@@ -370,7 +355,6 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(con
     C.pl_crow_bytes = (uint32_t)P.tile_px / (uint32_t)max(1, P.planar_hs);
     C.pl_cr_off = C.pl_cb_off + (uint32_t)((P.tile_rows + P.planar_vs - 1) / max(1, P.planar_vs)) * C.pl_crow_bytes;
     C.pl_vs_shift = P.planar_vs == 2 ? 1u : 0u;
-    C.st_mode = (uint32_t)P.store_policy;
     C.nthreads = NC;
     C.row0_of_thread = tid / C.gran_per_row;
     C.rem0_of_thread = tid % C.gran_per_row;
@@ -404,17 +388,17 @@ __global__ void __launch_bounds__(kMaxConsumerThreads + 32) csic_rows_kernel(con
       consumer_barrier(NC);
       if (tid == 0) {
         if (FMT == KF_PLANAR) {
-          tma_store_1d(out_g, out_s, out_bytes, pol_st);
+          tma_store_1d(out_g, out_s, out_bytes, pol);
           if (nrc) {
-            tma_store_1d(reinterpret_cast<void*>(cb_g), out_s + C.pl_cb_off, nrc * C.pl_crow_bytes, pol_st);
-            tma_store_1d(reinterpret_cast<void*>(cr_g), out_s + C.pl_cr_off, nrc * C.pl_crow_bytes, pol_st);
+            tma_store_1d(reinterpret_cast<void*>(cb_g), out_s + C.pl_cb_off, nrc * C.pl_crow_bytes, pol);
+            tma_store_1d(reinterpret_cast<void*>(cr_g), out_s + C.pl_cr_off, nrc * C.pl_crow_bytes, pol);
           }
         } else if (P.out_dense) {
-          tma_store_1d(out_g, out_s, out_bytes, pol_st);
+          tma_store_1d(out_g, out_s, out_bytes, pol);
         } else {                       // pitched output rows: one bulk store per row of the tile
           const uint32_t nrows = out_bytes / P.tile_out_bytes;
           for (uint32_t j = 0; j < nrows; ++j)
-            tma_store_1d(out_g + (uint64_t)j * P.out_row_bytes, out_s + j * P.tile_out_bytes, P.tile_out_bytes, pol_st);
+            tma_store_1d(out_g + (uint64_t)j * P.out_row_bytes, out_s + j * P.tile_out_bytes, P.tile_out_bytes, pol);
         }
         tma_store_commit();
       }

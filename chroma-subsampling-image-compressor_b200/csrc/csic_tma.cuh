@@ -63,12 +63,6 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
   return pol;
 }
 
-__device__ __forceinline__ uint64_t policy_evict_normal() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));

@@ -249,10 +249,9 @@ CSIC_API int csic_synchronize(csic_ctx* ctx);
  * GRID_CTAS_PER_SM / STAGES / TILE_BYTES: overrides for the row kernel's persistent grid, ring depth and
  * input bytes per tile (0 = auto; STAGES / TILE_BYTES / BLOCK_THREADS also steer the flex kernel); HOST_FULL_FRAMES: 1 = csic_process_host copies whole frames even when a
  * DECIMATE pipeline reads only every f-th row (default 0: ship only the rows that are read); HOST_NO_BOUNCE: 1 =
- * do not stage pageable caller buffers through the context's pinned bounce buffers; STORE_POLICY (row kernel): cache policy of
- * the output stores, 0 = streaming / L2 evict-first (default), 1 = write-back / evict-normal, 2 = st.global.cg; BLOCK_THREADS: threads per CTA of the row kernel (multiple of 32, <= 512). */
+ * do not stage pageable caller buffers through the context's pinned bounce buffers; BLOCK_THREADS: threads per CTA of the row kernel (multiple of 32, <= 512). */
 enum csic_option { CSIC_OPT_KERNEL_FAMILY = 0, CSIC_OPT_HOST_CHUNK_BYTES = 1, CSIC_OPT_GRID_CTAS_PER_SM = 2,
-                   CSIC_OPT_STAGES = 3, CSIC_OPT_TILE_BYTES = 4, CSIC_OPT_BLOCK_THREADS = 5, CSIC_OPT_HOST_FULL_FRAMES = 6, CSIC_OPT_HOST_NO_BOUNCE = 7, CSIC_OPT_STORE_POLICY = 8,
+                   CSIC_OPT_STAGES = 3, CSIC_OPT_TILE_BYTES = 4, CSIC_OPT_BLOCK_THREADS = 5, CSIC_OPT_HOST_FULL_FRAMES = 6, CSIC_OPT_HOST_NO_BOUNCE = 7,
                    CSIC_OPT_MULTI_STATIC_SPLIT = 100 /* csic_multi_set_option only */ };
 CSIC_API int csic_set_option(csic_ctx* ctx, int option, int64_t value);
 

@@ -183,3 +183,17 @@ def test_every_bench_workload_is_a_legal_parameter_set():
     W, H, _, a, b, q, f, order, fmt, _ = bench.WORKLOADS["cfg3"]
     fb = csic.out_shape(csic.make_params(W, H, a, b, *q, f, tuple(bench.ORD[c] for c in order), out_format=fmt))[3]
     assert bench.algorithmic_bytes_per_frame(W, H, f, fb) == 12_441_600
+
+
+def test_rtl_crosscheck_harness_plumbing(tmp_path):
+    """tools/rtl_crosscheck/crosscheck.py end to end without a JVM: a stand-in for the reference CLI (answers with the
+    oracle, file named the way the reference's own committed APP_OUTPUT file is) must pass, and a stand-in that flips
+    one byte must be reported -- so on a machine with sbt the only unknown is the RTL itself."""
+    import subprocess, sys
+    tool = os.path.join(ROOT, "tools", "rtl_crosscheck")
+    base = [sys.executable, os.path.join(tool, "crosscheck.py"), "--reference", str(tmp_path), "--cases", "6"]
+    fake = f"{sys.executable} {os.path.join(tool, 'fake_reference.py')}"
+    r = subprocess.run(base + ["--runner", fake], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.count("-> ok") == 6, r.stdout + r.stderr
+    r = subprocess.run(base + ["--runner", fake + " --corrupt"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 1 and "MISMATCH" in r.stdout, r.stdout + r.stderr

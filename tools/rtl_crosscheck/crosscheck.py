@@ -18,6 +18,9 @@ def main():
     ap.add_argument("--cases", type=int, default=20)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--gpu", action="store_true", help="also compare csic_b200 (needs a B200)")
+    ap.add_argument("--runner", default="sbt",
+                    help="program that runs the reference CLI in --reference: called as <runner> '<sbt command line>'.  "
+                         "Default sbt; the self-test passes tools/rtl_crosscheck/fake_reference.py (no JVM needed)")
     args = ap.parse_args()
     from PIL import Image
     import oracle
@@ -35,11 +38,19 @@ def main():
             Image.fromarray(rgb, "RGB").save(inp)
             cli = (f"Test / runMain jpeg.ImageCompressionApp --input {inp} --a {a} --b {b} --yq {q[0]} --cbq {q[1]} "
                    f"--crq {q[2]} --sf {f} --op1 {STEP[ops[0]]} --op2 {STEP[ops[1]]} --op3 {STEP[ops[2]]}")
-            subprocess.run(["sbt", cli], cwd=args.reference, check=True, capture_output=True)
-            out = os.path.join(args.reference, "APP_OUTPUT",
-                               f"case{case}_processed_chroma4-{a}-{b}_Y{q[0]}Cb{q[1]}Cr{q[2]}_sf{f}_order-"
-                               f"{TAG[ops[0]]}-{TAG[ops[1]]}-{TAG[ops[2]]}.png")
-            rtl = np.asarray(Image.open(out).convert("RGB"))
+            subprocess.run(args.runner.split() + [cli], cwd=args.reference, check=True, capture_output=True)
+            # the order tag is `opN.toString.split('.').last.take(2)` (ImageCompressorTopApp.scala:188): "Sp-Co-Ch" as
+            # intended, but "Pr-Pr-Pr" with Chisel versions whose ChiselEnum prints "ProcessingStep(1=SpatialSampling)"
+            # (the reference's own committed APP_OUTPUT file is named that way) -- accept either
+            import glob
+            pat = os.path.join(args.reference, "APP_OUTPUT",
+                               f"case{case}_processed_chroma4-{a}-{b}_Y{q[0]}Cb{q[1]}Cr{q[2]}_sf{f}_order-*.png")
+            hits = sorted(glob.glob(pat), key=os.path.getmtime)
+            if not hits:
+                sys.exit(f"the reference wrote no {pat}")
+            rtl = np.asarray(Image.open(hits[-1]).convert("RGB"))
+            for h in hits:
+                os.remove(h)
         po = oracle.make_params(W, H, a, b, tuple(q), f, name, out_format=1)
         want = oracle.process(po, rgb).reshape(H // f, W // f, 3)
         ok = np.array_equal(rtl, want)
