@@ -191,3 +191,13 @@ def test_no_device_means_error_not_fallback():
     with pytest.raises(csic.CsicError) as e:
         csic.Context(0)
     assert e.value.status == -10 and "no CPU fallback" in str(e.value)
+
+
+def test_library_exports_only_the_c_abi():
+    """nm -D: every defined dynamic symbol is a csic_* function of include/csic.h (linker version script csrc/csic.map);
+    no C++ template specialisation or libstdc++ weak symbol leaks (VERDICT r1 hygiene)."""
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", csic.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    names = [l.split()[-1] for l in out.splitlines() if l.strip()]
+    assert names and all(n.startswith("csic_") for n in names), [n for n in names if not n.startswith("csic_")]
+    assert set(names) == set(_ffi.PROTOTYPES), set(names) ^ set(_ffi.PROTOTYPES)
