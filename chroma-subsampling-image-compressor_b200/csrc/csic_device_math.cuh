@@ -105,6 +105,41 @@ __device__ __forceinline__ void inv_granule(const uint32_t (&dy)[4], uint32_t my
   w2 = __byte_perm(p4, p5, 0x6420);
 }
 
+// The PLANAR decoder's flavour: four pixels given as packed bytes (yw = Y0..Y3, cbw / crw = the chroma each pixel
+// replays, already expanded by the hold rule) -> the twelve RGB bytes.  share = log2 of how many consecutive pixels share
+// a chroma pair (0, 1 or 2; warp-uniform): the chroma terms are computed once per pair.  Same integers as inverse_rgb.
+__device__ __forceinline__ void decode_rgb_granule(uint32_t yw, uint32_t cbw, uint32_t crw, uint32_t share, uint32_t& w0,
+                                                   uint32_t& w1, uint32_t& w2) {
+  auto terms = [&](uint32_t sel) {          // sel: PRMT selector placing the pixel's byte into byte 1, zeros elsewhere
+    const int cb8 = (int)__byte_perm(cbw, 0, sel), cr8 = (int)__byte_perm(crw, 0, sel);
+    InvChroma t;
+    t.tr = 409 * cr8 - 52224 * 256;
+    t.tg = -208 * cr8 + (-100 * cb8 + 39552 * 256);
+    t.tb = 516 * cb8 - 65920 * 256;
+    return t;
+  };
+  const uint32_t dy[4] = {__byte_perm(yw, 0, 0x4404), __byte_perm(yw, 0, 0x4414), __byte_perm(yw, 0, 0x4424), __byte_perm(yw, 0, 0x4434)};
+  const InvChroma t0 = terms(0x4404);
+  InvChroma t1 = t0, t2, t3;
+  if (share == 0u) t1 = terms(0x4414);
+  if (share <= 1u) t2 = terms(0x4424); else t2 = t0;
+  t3 = t2;
+  if (share == 0u) t3 = terms(0x4434);
+  inv_granule(dy, 0xFF00u, t0, t1, t2, t3, w0, w1, w2);
+}
+
+// One decoded granule: interleaved Y,Cb,Cr bytes (eight PRMTs) or RGB (decode_rgb_granule).
+__device__ __forceinline__ void decode_granule(uint32_t yw, uint32_t cbw, uint32_t crw, uint32_t share, int to_rgb, uint32_t& w0,
+                                               uint32_t& w1, uint32_t& w2) {
+  if (to_rgb) {
+    decode_rgb_granule(yw, cbw, crw, share, w0, w1, w2);
+  } else {        // Y0 Cb0 Cr0 Y1 | Cb1 Cr1 Y2 Cb2 | Cr2 Y3 Cb3 Cr3
+    w0 = __byte_perm(__byte_perm(yw, cbw, 0x1040), crw, 0x3410);
+    w1 = __byte_perm(__byte_perm(cbw, crw, 0x0051), __byte_perm(yw, cbw, 0x0062), 0x5410);
+    w2 = __byte_perm(__byte_perm(crw, yw, 0x0072), __byte_perm(cbw, crw, 0x0073), 0x5410);
+  }
+}
+
 // Four 24-bit pixels (R | G << 8 | B << 16) -> the twelve bytes of a granule, three PRMTs.
 __device__ __forceinline__ void pack_rgb_granule(const uint32_t (&v)[4], uint32_t& w0, uint32_t& w1, uint32_t& w2) {
   w0 = __byte_perm(v[0], v[1], 0x4210);     // R0 G0 B0 R1

@@ -401,14 +401,8 @@ __global__ void __launch_bounds__(128) csic_expand_planar_any_kernel(const __gri
               cbw = __byte_perm(__funnelshift_r(bl[u], bh[u], ((br.a0 + cs) & 3u) * 8u), 0, csel);
               crw = __byte_perm(__funnelshift_r(rl[u], rh[u], ((rr.a0 + cs) & 3u) * 8u), 0, csel);
             }
-            uint32_t v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int y = (int)((yw >> (8 * j)) & 0xFFu), cb = (int)((cbw >> (8 * j)) & 0xFFu), cr = (int)((crw >> (8 * j)) & 0xFFu);
-              v[j] = to_rgb ? inverse_rgb(y, cb, cr) : ((uint32_t)y | ((uint32_t)cb << 8) | ((uint32_t)cr << 16));
-            }
             uint32_t w0, w1, w2;
-            pack_rgb_granule(v, w0, w1, w2);
+            decode_granule(yw, cbw, crw, held ? 2u : hs_sh, to_rgb, w0, w1, w2);
             sts32(st + 12u * g, w0); sts32(st + 12u * g + 4u, w1); sts32(st + 12u * g + 8u, w2);
           }
         }
@@ -473,13 +467,7 @@ __global__ void __launch_bounds__(128) csic_expand_planar_rows_kernel(const __gr
         } else {
           cbw = (uint32_t)__ldg(cbp + g) * 0x01010101u; crw = (uint32_t)__ldg(crp + g) * 0x01010101u;
         }
-        uint32_t v[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int y = (int)((yw >> (8 * j)) & 0xFFu), cb = (int)((cbw >> (8 * j)) & 0xFFu), cr = (int)((crw >> (8 * j)) & 0xFFu);
-          v[j] = to_rgb ? inverse_rgb(y, cb, cr) : ((uint32_t)y | ((uint32_t)cb << 8) | ((uint32_t)cr << 16));
-        }
-        w0 = v[0] | (v[1] << 24); w1 = (v[1] >> 8) | (v[2] << 16); w2 = (v[2] >> 16) | (v[3] << 8);
+        decode_granule(yw, cbw, crw, held ? 2u : hs_sh, to_rgb, w0, w1, w2);
       }
       if (A16) {
         uint32_t* st = stage[warp];
@@ -550,15 +538,9 @@ __global__ void __launch_bounds__(128) csic_expand_planar16_kernel(const __grid_
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          uint32_t v[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int y = (int)((yw[i] >> (8 * j)) & 0xFFu), cb = (int)((cbw[i] >> (8 * j)) & 0xFFu), cr = (int)((crw[i] >> (8 * j)) & 0xFFu);
-            v[j] = to_rgb ? inverse_rgb(y, cb, cr) : ((uint32_t)y | ((uint32_t)cb << 8) | ((uint32_t)cr << 16));
-          }
-          st[12 * lane + 3 * i] = v[0] | (v[1] << 24);
-          st[12 * lane + 3 * i + 1] = (v[1] >> 8) | (v[2] << 16);
-          st[12 * lane + 3 * i + 2] = (v[2] >> 16) | (v[3] << 8);
+          uint32_t w0, w1, w2;
+          decode_granule(yw[i], cbw[i], crw[i], held ? 2u : hs_sh, to_rgb, w0, w1, w2);
+          st[12 * lane + 3 * i] = w0; st[12 * lane + 3 * i + 1] = w1; st[12 * lane + 3 * i + 2] = w2;
         }
       }
       __syncwarp();

@@ -197,3 +197,21 @@ def test_rtl_crosscheck_harness_plumbing(tmp_path):
     assert r.returncode == 0 and r.stdout.count("-> ok") == 6, r.stdout + r.stderr
     r = subprocess.run(base + ["--runner", fake + " --corrupt"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 1 and "MISMATCH" in r.stdout, r.stdout + r.stderr
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the arm the driver runs beside ours): one JSON line with the contract's keys, the CPU
+    restatement on a bounded sample, no GPU involved; ranks other than 0 print nothing."""
+    import json, subprocess, sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--workload", "cfg2"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data",
+              "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "MP/s" and line["value"] > 0 and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and "workload" in line["config"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert r.returncode == 0 and r.stdout.strip() == ""
