@@ -399,7 +399,7 @@ int csic_expand_planar_device(csic_ctx* ctx, const csic_params* p, const void* d
   DeviceGuard guard(ctx->device);
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
   int err = csic::launch_expand_planar(k, static_cast<const uint8_t*>(d_planar), static_cast<uint8_t*>(d_out),
-                                       expand_format == CSIC_OUT_RGB888, ctx->sm_count, st);
+                                       expand_format == CSIC_OUT_RGB888, ctx->sm_count, ctx->max_smem_optin, st);
   ctx->launches += 1;
   if (err != (int)cudaSuccess) return cuda_fail((cudaError_t)err, "expand kernel launch");
   return CSIC_OK;

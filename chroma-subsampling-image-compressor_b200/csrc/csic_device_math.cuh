@@ -140,6 +140,39 @@ __device__ __forceinline__ void decode_granule(uint32_t yw, uint32_t cbw, uint32
   }
 }
 
+// The same with the chroma sample of each pixel named by its byte index (c0..c3) inside cbw / crw, so that a caller whose
+// hold pattern is known at compile time (after unrolling) needs no expanded words: the terms of a repeated index are
+// reused, the YCC interleave is eight PRMTs whatever the pattern.
+__device__ __forceinline__ InvChroma dec_terms(uint32_t cbw, uint32_t crw, uint32_t idx) {
+  const uint32_t sel = 0x4404u | (idx << 4);           // the sample's byte into byte 1, zeros elsewhere
+  const int cb8 = (int)__byte_perm(cbw, 0, sel), cr8 = (int)__byte_perm(crw, 0, sel);
+  InvChroma t;
+  t.tr = 409 * cr8 - 52224 * 256;
+  t.tg = -208 * cr8 + (-100 * cb8 + 39552 * 256);
+  t.tb = 516 * cb8 - 65920 * 256;
+  return t;
+}
+__device__ __forceinline__ void rgb_granule_terms(uint32_t yw, const InvChroma& t0, const InvChroma& t1, const InvChroma& t2,
+                                                  const InvChroma& t3, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
+  const uint32_t dy[4] = {__byte_perm(yw, 0, 0x4404), __byte_perm(yw, 0, 0x4414), __byte_perm(yw, 0, 0x4424), __byte_perm(yw, 0, 0x4434)};
+  inv_granule(dy, 0xFFFFFFFFu, t0, t1, t2, t3, w0, w1, w2);
+}
+template <bool RGB>
+__device__ __forceinline__ void decode_granule_idx(uint32_t yw, uint32_t cbw, uint32_t crw, uint32_t c0, uint32_t c1, uint32_t c2,
+                                                   uint32_t c3, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
+  if (RGB) {
+    const InvChroma t0 = dec_terms(cbw, crw, c0);
+    const InvChroma t1 = c1 == c0 ? t0 : dec_terms(cbw, crw, c1);
+    const InvChroma t2 = c2 == c1 ? t1 : dec_terms(cbw, crw, c2);
+    const InvChroma t3 = c3 == c2 ? t2 : dec_terms(cbw, crw, c3);
+    rgb_granule_terms(yw, t0, t1, t2, t3, w0, w1, w2);
+  } else {        // Y0 Cb0 Cr0 Y1 | Cb1 Cr1 Y2 Cb2 | Cr2 Y3 Cb3 Cr3
+    w0 = __byte_perm(__byte_perm(yw, cbw, 0x1000u | ((4u + c0) << 4)), crw, 0x3010u | ((4u + c0) << 8));
+    w1 = __byte_perm(__byte_perm(cbw, crw, c1 | ((4u + c1) << 4)), __byte_perm(yw, cbw, 0x2u | ((4u + c2) << 4)), 0x5410);
+    w2 = __byte_perm(__byte_perm(crw, yw, c2 | 0x70u), __byte_perm(cbw, crw, c3 | ((4u + c3) << 4)), 0x5410);
+  }
+}
+
 // Four 24-bit pixels (R | G << 8 | B << 16) -> the twelve bytes of a granule, three PRMTs.
 __device__ __forceinline__ void pack_rgb_granule(const uint32_t (&v)[4], uint32_t& w0, uint32_t& w1, uint32_t& w2) {
   w0 = __byte_perm(v[0], v[1], 0x4210);     // R0 G0 B0 R1

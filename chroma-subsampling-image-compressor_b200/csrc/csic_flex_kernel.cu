@@ -45,9 +45,6 @@ constexpr uint32_t kDescBytes = 80u;
 constexpr uint32_t kDirectRowBytes = 257u;           // output rows shorter than this that cannot be packed leave from registers (B200 map:
                                                      // 75-250-byte rows 1.3x faster direct, 375-1000-byte rows up to 2x faster staged)
 
-__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) {
-  asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
 __device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
   asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
 }
@@ -59,29 +56,6 @@ __device__ __forceinline__ uint32_t ldg8_now(const uint8_t* p) {
   uint32_t v;
   asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
-}
-
-// Producer side (one thread per span).  global [g, g+len) -> shared, byte i at  slot + (g & 15) + i  (slot 16-byte aligned):
-// the 16-byte hull of the span goes to the TMA engine; where the hull would leave [lo, hi) -- the byte range this
-// launch may touch -- it is clipped and the < 16 edge bytes are copied by hand (first / last span of a launch only).
-__device__ __forceinline__ void span_fetch(uint32_t slot, const uint8_t* __restrict__ g, uint32_t len, uint32_t bar, uint64_t pol,
-                                           uintptr_t lo, uintptr_t hi) {
-  const uintptr_t A = reinterpret_cast<uintptr_t>(g), B = A + len, base = A & ~(uintptr_t)15;
-  uintptr_t start = base, end = (B + 15) & ~(uintptr_t)15;
-  if (start < lo) start += 16;                   // then start > A: head bytes [A, min(start, B)) by hand
-  if (end > hi) end -= 16;                       // then end < B: tail bytes by hand
-  if (end > start) {
-    const uint32_t n = (uint32_t)(end - start);
-    mbar_expect_tx_only(bar, n);
-    tma_load_1d(slot + (uint32_t)(start - base), reinterpret_cast<const void*>(start), n, bar, pol);
-  }
-  if (start > A || end < B) {
-    const uint8_t* gb = reinterpret_cast<const uint8_t*>(base);
-    const uintptr_t h1 = start > A ? (start < B ? start : B) : A;          // head is [A, h1)
-    const uintptr_t t0 = end < B ? (end > h1 ? end : h1) : B;              // tail is [t0, B)
-    for (uintptr_t x = A; x < h1; ++x) sts8(slot + (uint32_t)(x - base), __ldg(gb + (x - base)));
-    for (uintptr_t x = t0; x < B; ++x) sts8(slot + (uint32_t)(x - base), __ldg(gb + (x - base)));
-  }
 }
 
 // n and m powers of two, n <= m  (no division: this runs once per tile in every thread)
@@ -161,7 +135,7 @@ static_assert(sizeof(FlexDesc) == kDescBytes, "kDescBytes out of sync");
 // The consumer warps' loop over this CTA's tiles.
 template <int FMT, bool TRUNC, uint32_t HFE, uint32_t PXB, bool DIRECT>
 __device__ __forceinline__ void flex_consume(const KPlan& P, uint8_t* smem, uint32_t n_my) {
-  constexpr uint32_t kUnit = FlexFmt<FMT>::kUnit, kOpx = kUnit / 4u;
+  constexpr uint32_t kUnit = FlexFmt<FMT>::kUnit;
   const uint32_t tid = threadIdx.x, NC = blockDim.x - 32u, NW = NC >> 5;
   const uint32_t sbase = smem_u32(smem), out_s = sbase + P.out_buf_off, held_base = sbase + P.meta_off;
   const uint32_t S = (uint32_t)P.stages, full0 = sbase + P.bar_off, empty0 = full0 + 8u * S, desc0 = full0 + 16u * S;

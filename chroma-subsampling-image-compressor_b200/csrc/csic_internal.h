@@ -73,7 +73,10 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
 
 // Both return a cudaError_t as int.
 int launch_generic(const KPlan& k, int sm_count, void* stream);
-int launch_expand_planar(const KPlan& k, const uint8_t* planar, uint8_t* out, int to_rgb, int sm_count, void* stream);
+int launch_expand_planar(const KPlan& k, const uint8_t* planar, uint8_t* out, int to_rgb, int sm_count, size_t max_smem_optin, void* stream);
+// TMA-staged decoder for any width / alignment (csic_decode_kernel.cu); -1 = not eligible, else a cudaError_t
+int launch_decode_tma(const KPlan& k, const uint8_t* planar, uint8_t* out, int to_rgb, int sm_count, size_t max_smem_optin, void* stream);
+int decode_set_attributes(size_t max_smem_optin);
 int launch_rows(const KPlan& k, int sm_count, int force_ctas_per_sm, void* stream);
 constexpr int kDefaultBlockThreads = 256;   // consumer threads; one producer warp is added at launch
 constexpr int kMaxConsumerThreads = 512;

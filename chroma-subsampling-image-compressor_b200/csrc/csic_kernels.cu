@@ -339,7 +339,9 @@ __global__ void __launch_bounds__(128) csic_generic_kernel(const __grid_constant
 //          word) and leaves as 16-byte st.global.cs aligned on the GLOBAL address (span_store): one head and one tail
 //          of < 16 bytes per row instead of one per 384 bytes.
 // Round 1: one thread per pixel, three divisions, three byte loads and three byte stores each -- 0.10 of the copy
-// peak; the first round-2 version (one granule per thread and trip, per-warp staging) 0.22.
+// peak; the first round-2 version (one granule per thread and trip, per-warp staging) 0.22; this one 0.4 - 0.5.  Since
+// the TMA-staged decoder (csic_decode_kernel.cu: 0.6 - 0.95) it only runs what that kernel declines, and under
+// CSIC_DEC_NO_TMA in the tests.
 constexpr uint32_t kExpandSeg = 4096u;   // pixels per staged segment: 12 KB of shared memory
 
 __global__ void __launch_bounds__(128) csic_expand_planar_any_kernel(const __grid_constant__ KPlan P, const uint8_t* __restrict__ planar,
@@ -414,166 +416,14 @@ __global__ void __launch_bounds__(128) csic_expand_planar_any_kernel(const __gri
   }
 }
 
-// Same decoder, one CTA per output row, four pixels per thread (needs Wo % 4 == 0).  Everything row-dependent --
-// frame / row split (the only division), held line, plane row addresses, alignment of the row's loads -- is computed once
-// per row; the Y bytes arrive as one word, the chroma samples of a granule as a word / half word / byte when aligned.
-// A16: output rows are 16-byte aligned (Wo % 16 == 0), so a warp's 32 granules = 384 consecutive bytes leave through
-// a shared-memory slot as coalesced 16-byte stores; otherwise three words per granule.
-template <bool A16>
-__global__ void __launch_bounds__(128) csic_expand_planar_rows_kernel(const __grid_constant__ KPlan P, const uint8_t* __restrict__ planar,
-                                                                      uint8_t* __restrict__ out, int to_rgb) {
-  __shared__ __align__(16) uint32_t stage[4][96];
-  const uint32_t gpr = (uint32_t)P.Wo >> 2, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t n_rows = P.n_frames * (uint32_t)P.Ho;
-  const int last_c = (P.last_sample_col / P.f) / P.planar_hs;       // plane column of a line's last sample point
-  const uint32_t hs_sh = P.planar_hs == 4 ? 2u : (P.planar_hs == 2 ? 1u : 0u), vs_sh = P.planar_vs == 2 ? 1u : 0u;
-  const bool vhold = P.vf == 2 && P.f == 1;                         // odd lines replay the line above (f == 1 only)
-  for (uint32_t R = blockIdx.x; R < n_rows; R += gridDim.x) {
-    const uint32_t k = R / (uint32_t)P.Ho, ro = R - k * (uint32_t)P.Ho;
-    const uint8_t* fr = planar + (uint64_t)k * P.out_frame_bytes;
-    const uint8_t* yrow = fr + (size_t)ro * P.Wo;
-    const bool held = vhold && (ro & 1u);
-    const size_t crow = (size_t)((held ? ro - 1u : ro) >> vs_sh) * (size_t)P.planar_cw;
-    const uint8_t* cbp = fr + P.planar_cb_off + crow;
-    const uint8_t* crp = fr + P.planar_cr_off + crow;
-    uint8_t* orow = out + (uint64_t)R * P.Wo * 3u;
-    const bool y_al = (reinterpret_cast<uintptr_t>(yrow) & 3u) == 0;
-    const uint32_t c_al = (uint32_t)((reinterpret_cast<uintptr_t>(cbp) | reinterpret_cast<uintptr_t>(crp)) & 3u);   // 0: words ok, 2: half words ok
-    uint32_t hcb = 0, hcr = 0;
-    if (held) { hcb = __ldg(cbp + last_c); hcr = __ldg(crp + last_c); }
-    for (uint32_t g0 = warp * 32u; g0 < gpr; g0 += blockDim.x) {    // warp uniform
-      const uint32_t g = g0 + lane;
-      uint32_t w0 = 0, w1 = 0, w2 = 0;
-      if (g < gpr) {
-        const uint8_t* yp = yrow + 4u * g;
-        uint32_t yw;
-        if (y_al) yw = __ldg(reinterpret_cast<const uint32_t*>(yp));
-        else yw = (uint32_t)__ldg(yp) | ((uint32_t)__ldg(yp + 1) << 8) | ((uint32_t)__ldg(yp + 2) << 16) | ((uint32_t)__ldg(yp + 3) << 24);
-        // chroma of the four pixels as bytes of cbw / crw
-        uint32_t cbw, crw;
-        if (held) {
-          cbw = hcb * 0x01010101u; crw = hcr * 0x01010101u;
-        } else if (hs_sh == 0) {
-          if (c_al == 0) { cbw = __ldg(reinterpret_cast<const uint32_t*>(cbp + 4u * g)); crw = __ldg(reinterpret_cast<const uint32_t*>(crp + 4u * g)); }
-          else {
-            cbw = (uint32_t)__ldg(cbp + 4u * g) | ((uint32_t)__ldg(cbp + 4u * g + 1) << 8) | ((uint32_t)__ldg(cbp + 4u * g + 2) << 16) | ((uint32_t)__ldg(cbp + 4u * g + 3) << 24);
-            crw = (uint32_t)__ldg(crp + 4u * g) | ((uint32_t)__ldg(crp + 4u * g + 1) << 8) | ((uint32_t)__ldg(crp + 4u * g + 2) << 16) | ((uint32_t)__ldg(crp + 4u * g + 3) << 24);
-          }
-        } else if (hs_sh == 1) {
-          uint32_t b2, r2;
-          if ((c_al & 1u) == 0) { b2 = __ldg(reinterpret_cast<const uint16_t*>(cbp + 2u * g)); r2 = __ldg(reinterpret_cast<const uint16_t*>(crp + 2u * g)); }
-          else { b2 = (uint32_t)__ldg(cbp + 2u * g) | ((uint32_t)__ldg(cbp + 2u * g + 1) << 8); r2 = (uint32_t)__ldg(crp + 2u * g) | ((uint32_t)__ldg(crp + 2u * g + 1) << 8); }
-          cbw = __byte_perm(b2, 0, 0x1100); crw = __byte_perm(r2, 0, 0x1100);      // each sample held for two pixels
-        } else {
-          cbw = (uint32_t)__ldg(cbp + g) * 0x01010101u; crw = (uint32_t)__ldg(crp + g) * 0x01010101u;
-        }
-        decode_granule(yw, cbw, crw, held ? 2u : hs_sh, to_rgb, w0, w1, w2);
-      }
-      if (A16) {
-        uint32_t* st = stage[warp];
-        st[3 * lane] = w0; st[3 * lane + 1] = w1; st[3 * lane + 2] = w2;
-        __syncwarp();
-        const uint32_t valid = min(32u, gpr - g0) * 12u;                 // bytes of this group that exist
-        uint8_t* o = orow + (size_t)g0 * 12u;
-        if (lane < 24u) {
-          if ((lane + 1u) * 16u <= valid) {
-            __stcs(reinterpret_cast<uint4*>(o) + lane, reinterpret_cast<const uint4*>(st)[lane]);
-          } else {
-            for (uint32_t wd = lane * 4u; wd < lane * 4u + 4u; ++wd)
-              if ((wd + 1u) * 4u <= valid) __stcs(reinterpret_cast<uint32_t*>(o) + wd, st[wd]);
-          }
-        }
-        __syncwarp();
-      } else if (g < gpr) {
-        uint32_t* o = reinterpret_cast<uint32_t*>(orow + (size_t)g * 12u);
-        __stcs(o, w0); __stcs(o + 1, w1); __stcs(o + 2, w2);
-      }
-    }
-  }
-}
-
-// Widest variant: sixteen pixels per thread (Wo % 16 == 0, planes and output 16-byte aligned).  What bounds the decoder is
-// bytes in flight -- a thread that waits on one Y word and two chroma half words keeps 16 KB per SM in the air -- so every
-// thread fetches 16 Y bytes and 2 x 4..16 chroma bytes at once (LDG.128 / .64 / .32) and a warp leaves 1536 consecutive
-// output bytes through its shared-memory slot as three rounds of coalesced 16-byte stores.
-__global__ void __launch_bounds__(128) csic_expand_planar16_kernel(const __grid_constant__ KPlan P, const uint8_t* __restrict__ planar,
-                                                                   uint8_t* __restrict__ out, int to_rgb) {
-  __shared__ __align__(16) uint32_t stage[4][12 * 32];
-  const uint32_t gpr = (uint32_t)P.Wo >> 4, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;   // 16-pixel groups per row
-  const uint32_t n_rows = P.n_frames * (uint32_t)P.Ho;
-  const int last_c = (P.last_sample_col / P.f) / P.planar_hs;
-  const uint32_t hs_sh = P.planar_hs == 4 ? 2u : (P.planar_hs == 2 ? 1u : 0u), vs_sh = P.planar_vs == 2 ? 1u : 0u;
-  const bool vhold = P.vf == 2 && P.f == 1;
-  for (uint32_t R = blockIdx.x; R < n_rows; R += gridDim.x) {
-    const uint32_t k = R / (uint32_t)P.Ho, ro = R - k * (uint32_t)P.Ho;
-    const uint8_t* fr = planar + (uint64_t)k * P.out_frame_bytes;
-    const uint8_t* yrow = fr + (size_t)ro * P.Wo;
-    const bool held = vhold && (ro & 1u);
-    const size_t crow = (size_t)((held ? ro - 1u : ro) >> vs_sh) * (size_t)P.planar_cw;
-    const uint8_t* cbp = fr + P.planar_cb_off + crow;
-    const uint8_t* crp = fr + P.planar_cr_off + crow;
-    uint8_t* orow = out + (uint64_t)R * P.Wo * 3u;
-    uint32_t hcb = 0, hcr = 0;
-    if (held) { hcb = (uint32_t)__ldg(cbp + last_c) * 0x01010101u; hcr = (uint32_t)__ldg(crp + last_c) * 0x01010101u; }
-    for (uint32_t g0 = warp * 32u; g0 < gpr; g0 += blockDim.x) {    // warp uniform
-      const uint32_t g = g0 + lane;
-      uint32_t* st = stage[warp];
-      if (g < gpr) {
-        const uint4 yv = __ldg(reinterpret_cast<const uint4*>(yrow) + g);
-        uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w}, cbw[4], crw[4];   // chroma of pixel 4i+j = byte j of cbw[i] / crw[i]
-        if (held) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { cbw[i] = hcb; crw[i] = hcr; }
-        } else if (hs_sh == 0) {
-          const uint4 b = __ldg(reinterpret_cast<const uint4*>(cbp) + g), r = __ldg(reinterpret_cast<const uint4*>(crp) + g);
-          cbw[0] = b.x; cbw[1] = b.y; cbw[2] = b.z; cbw[3] = b.w; crw[0] = r.x; crw[1] = r.y; crw[2] = r.z; crw[3] = r.w;
-        } else if (hs_sh == 1) {       // 8 samples, each held for two pixels
-          const uint2 b = __ldg(reinterpret_cast<const uint2*>(cbp) + g), r = __ldg(reinterpret_cast<const uint2*>(crp) + g);
-          cbw[0] = __byte_perm(b.x, 0, 0x1100); cbw[1] = __byte_perm(b.x, 0, 0x3322); cbw[2] = __byte_perm(b.y, 0, 0x1100); cbw[3] = __byte_perm(b.y, 0, 0x3322);
-          crw[0] = __byte_perm(r.x, 0, 0x1100); crw[1] = __byte_perm(r.x, 0, 0x3322); crw[2] = __byte_perm(r.y, 0, 0x1100); crw[3] = __byte_perm(r.y, 0, 0x3322);
-        } else {                       // 4 samples, each held for four pixels
-          const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(cbp) + g), r = __ldg(reinterpret_cast<const uint32_t*>(crp) + g);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { cbw[i] = __byte_perm(b, 0, 0x1111 * i); crw[i] = __byte_perm(r, 0, 0x1111 * i); }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint32_t w0, w1, w2;
-          decode_granule(yw[i], cbw[i], crw[i], held ? 2u : hs_sh, to_rgb, w0, w1, w2);
-          st[12 * lane + 3 * i] = w0; st[12 * lane + 3 * i + 1] = w1; st[12 * lane + 3 * i + 2] = w2;
-        }
-      }
-      __syncwarp();
-      const uint32_t valid = min(32u, gpr - g0) * 48u;                // bytes of this group that exist (a multiple of 16)
-      uint4* o = reinterpret_cast<uint4*>(orow + (size_t)g0 * 48u);
-#pragma unroll
-      for (uint32_t c = lane; c < 96u; c += 32u)
-        if ((c + 1u) * 16u <= valid) __stcs(o + c, reinterpret_cast<const uint4*>(st)[c]);
-      __syncwarp();
-    }
-  }
-}
-
-int launch_expand_planar(const KPlan& k, const uint8_t* planar, uint8_t* out, int to_rgb, int sm_count, void* stream) {
+int launch_expand_planar(const KPlan& k, const uint8_t* planar, uint8_t* out, int to_rgb, int sm_count, size_t max_smem_optin, void* stream) {
   const uint64_t total = (uint64_t)k.n_frames * (uint64_t)k.Ho * (uint64_t)k.Wo;
   if (total == 0) return (int)cudaSuccess;
+  // the TMA-staged decoder (csic_decode_kernel.cu) takes every realistic shape; what it declines -- rows narrower than a
+  // granule, chroma rows too wide for a stage -- runs on the LDG kernel above
+  const int tma = launch_decode_tma(k, planar, out, to_rgb, sm_count, max_smem_optin, stream);
+  if (tma >= 0) return tma;
   const uint64_t n_rows = (uint64_t)k.n_frames * (uint64_t)k.Ho;
-  if (k.Wo % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0 && n_rows < (1ull << 32)) {
-    const unsigned blocks = (unsigned)std::min<uint64_t>(n_rows, (uint64_t)sm_count * 16);
-    const unsigned threads = (unsigned)std::min<uint32_t>(128u, (((uint32_t)k.Wo >> 2) + 31u) & ~31u);
-    const uint32_t cw_bytes = (uint32_t)k.planar_cw;              // chroma plane rows must keep the vector loads aligned
-    const bool planes16 = (reinterpret_cast<uintptr_t>(planar) & 15u) == 0 && k.out_frame_bytes % 16 == 0 &&
-                          k.planar_cb_off % 16 == 0 && k.planar_cr_off % 16 == 0 &&
-                          cw_bytes % (16u / (uint32_t)k.planar_hs) == 0 && cw_bytes * (uint32_t)k.planar_hs == (uint32_t)k.Wo;
-    if (k.Wo % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0 && planes16) {
-      const unsigned th16 = (unsigned)std::min<uint32_t>(128u, (((uint32_t)k.Wo >> 4) + 31u) & ~31u);
-      csic_expand_planar16_kernel<<<blocks, th16, 0, (cudaStream_t)stream>>>(k, planar, out, to_rgb);
-    } else if (k.Wo % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0)
-      csic_expand_planar_rows_kernel<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(k, planar, out, to_rgb);
-    else
-      csic_expand_planar_rows_kernel<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(k, planar, out, to_rgb);
-    return (int)cudaGetLastError();
-  }
   if (n_rows >= (1ull << 32)) return (int)cudaErrorInvalidValue;
   const unsigned threads = (unsigned)std::min<uint32_t>(128u, ((((uint32_t)k.Wo + 3u) >> 2) + 31u) & ~31u);
   const unsigned blocks = (unsigned)std::min<uint64_t>(n_rows, (uint64_t)sm_count * (2048u / threads));
@@ -739,6 +589,7 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
 int rows_kernel_set_attributes(size_t max_smem_optin) {
   int e;
   if ((e = flex_set_attributes(max_smem_optin)) != 0) return e;
+  if ((e = decode_set_attributes(max_smem_optin)) != 0) return e;
   if ((e = pool_set_attributes_factor<2>(max_smem_optin)) != 0) return e;
   if ((e = pool_set_attributes_factor<4>(max_smem_optin)) != 0) return e;
   if ((e = pool_set_attributes_factor<8>(max_smem_optin)) != 0) return e;

@@ -82,6 +82,33 @@ __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+// Producer side (one thread per span).  global [g, g+len) -> shared, byte i at  slot + (g & 15) + i  (slot 16-byte aligned):
+// the 16-byte hull of the span goes to the TMA engine; where the hull would leave [lo, hi) -- the byte range this
+// launch may touch -- it is clipped and the < 16 edge bytes are copied by hand (first / last span of a launch only).
+__device__ __forceinline__ void span_fetch(uint32_t slot, const uint8_t* __restrict__ g, uint32_t len, uint32_t bar, uint64_t pol,
+                                           uintptr_t lo, uintptr_t hi) {
+  const uintptr_t A = reinterpret_cast<uintptr_t>(g), B = A + len, base = A & ~(uintptr_t)15;
+  uintptr_t start = base, end = (B + 15) & ~(uintptr_t)15;
+  if (start < lo) start += 16;                   // then start > A: head bytes [A, min(start, B)) by hand
+  if (end > hi) end -= 16;                       // then end < B: tail bytes by hand
+  if (end > start) {
+    const uint32_t n = (uint32_t)(end - start);
+    mbar_expect_tx_only(bar, n);
+    tma_load_1d(slot + (uint32_t)(start - base), reinterpret_cast<const void*>(start), n, bar, pol);
+  }
+  if (start > A || end < B) {
+    const uint8_t* gb = reinterpret_cast<const uint8_t*>(base);
+    const uintptr_t h1 = start > A ? (start < B ? start : B) : A;          // head is [A, h1)
+    const uintptr_t t0 = end < B ? (end > h1 ? end : h1) : B;              // tail is [t0, B)
+    for (uintptr_t x = A; x < h1; ++x) sts8(slot + (uint32_t)(x - base), __ldg(gb + (x - base)));
+    for (uintptr_t x = t0; x < B; ++x) sts8(slot + (uint32_t)(x - base), __ldg(gb + (x - base)));
+  }
+}
+
 // The four sampled pixels of a granule, each as a word whose low three bytes are R,G,B.
 // A granule is 4 consecutive output pixels = 4 input pixels at a stride of F pixels (3F bytes);
 // `a` is the shared-memory address of its first byte.

@@ -127,8 +127,8 @@ def test_inverse_exhaustive_ycc_cube(csic, ctx, W, H):
     """YCbCr2RGB.scala:17-26 / RGB2YCbCr.scala:123-132 over ALL 2^24 (Y,Cb,Cr) triples, most of which no RGB input
     reaches through the forward transform (the clamps fire on 42 / 27 / 51 % of the cube for R / G / B): a synthetic
     4:4:4 PLANAR frame whose three planes enumerate the cube is decoded on the GPU by csic_expand_planar_device (the
-    same inverse_rgb the fused kernels use) and compared with the oracle's ycbcr2rgb.  Three widths = the three
-    decoder kernels (16 pixels per thread, 4 per thread, any width)."""
+    same reconstruction arithmetic the fused kernels use) and compared with the oracle's ycbcr2rgb.  Three widths = the
+    three paths of the TMA-staged decoder (16 pixels per thread, 4 per thread with a fixed hold pattern, any width)."""
     import torch
     n = W * H
     assert n >= 1 << 24
@@ -571,6 +571,74 @@ def test_planar_output_and_decoder(csic, ctx):
     assert 2 in fams and fams <= {1, 2, 4}
     cw, chh, ob, orr = csic.planar_shape(both_params(csic, 1920, 1080, 2, 0, (8, 8, 8), 1, "CSQ", 0, 0, 4)[0])
     assert (cw, chh, ob, orr) == (960, 540, 1920 * 1080, 1920 * 1080 + 960 * 540)
+
+
+def _planar_decode_ref(csic, p, planar, to_rgb):
+    """PLANAR -> interleaved stream, restated in numpy: pixel (r, c) shows chroma sample (r // vs, c // hs); the odd
+    lines of a vertically subsampled stream replay the LAST sample of the line above (ChromaSubsampler.scala:52-65)."""
+    w, h, _, fb = csic.out_shape(p)
+    cw, chh, ob, orr = csic.planar_shape(p)
+    f = p.factor
+    hf, vf = 4 // p.chroma_a, (2 if p.chroma_b == 0 else 1)
+    hs, vs = max(1, hf // f), max(1, vf // f)
+    last_c = (((p.width - 1) // hf) * hf // f) // hs
+    n = planar.shape[0]
+    y = planar[:, :w * h].reshape(n, h, w)
+    rows = np.arange(h)
+    held = (rows & 1).astype(bool) if vs == 2 else np.zeros(h, bool)
+    crow = (rows - held) // vs
+    planes = []
+    for off in (ob, orr):
+        c = planar[:, off:off + cw * chh].reshape(n, chh, cw)
+        full = c[:, crow][:, :, np.arange(w) // hs]
+        full[:, held, :] = c[:, crow[held], last_c][:, :, None]
+        planes.append(full)
+    ycc = np.stack([y, planes[0], planes[1]], -1)
+    return oracle.ycbcr2rgb_array(ycc) if to_rgb else ycc
+
+
+@pytest.mark.parametrize("no_tma", [False, True], ids=["tma", "ldg"])
+def test_decoder_any_width_and_alignment(csic, ctx, no_tma, monkeypatch):
+    """csic_expand_planar_device on random planes: widths that are / are not multiples of 4 and 16, frames of one to many
+    tiles (CSIC_DEC_TILE shrinks the tile so that tiles start and end mid-row and on held lines), several frames, every
+    (a, b), f = 1 and 2, planar and output base pointers at every offset modulo 16 with canaries on both sides of the
+    output.  The TMA-staged decoder and the LDG decoders (CSIC_DEC_NO_TMA) must both equal the numpy restatement."""
+    import ctypes
+    import torch
+    from csic_b200 import _ffi
+    from csic_b200.api import check
+    if no_tma:
+        monkeypatch.setenv("CSIC_DEC_NO_TMA", "1")
+    rng = np.random.default_rng(11)
+    shapes = [(333, 50), (1366, 25), (1918, 13), (37, 300), (4, 5), (5, 5), (7, 1), (6000, 3), (1920, 20), (31, 31), (64, 64), (9, 2)]
+    cases = 0
+    for (W, H), ab, f, tile in itertools.product(shapes, ALL_AB, (1, 2), (0, 64, 720)):
+        if W % f or H % f or (tile and W * H // (f * f) > 40000) or (no_tma and tile):
+            continue
+        monkeypatch.setenv("CSIC_DEC_TILE", str(tile)) if tile else monkeypatch.delenv("CSIC_DEC_TILE", raising=False)
+        try:
+            p, _ = both_params(csic, W, H, ab[0], ab[1], (8, 8, 8), f, "CSQ", 0, 0, 4)
+        except csic.IllegalArgumentException:
+            continue
+        w, h, _, fb = csic.out_shape(p)
+        n = 3
+        planar = rng.integers(0, 256, size=(n, fb), dtype=np.uint8)
+        off_in, off_out = (int(rng.integers(0, 16)), int(rng.integers(0, 16))) if cases % 3 else (0, 0)
+        d_in = torch.zeros(n * fb + 64, dtype=torch.uint8, device="cuda")
+        d_in[off_in:off_in + n * fb] = torch.from_numpy(planar.reshape(-1)).cuda()
+        for to_rgb in (False, True):
+            want = _planar_decode_ref(csic, p, planar, to_rgb).reshape(-1)
+            d_out = torch.full((n * w * h * 3 + 128,), 0xA5, dtype=torch.uint8, device="cuda")
+            stream = torch.cuda.current_stream().cuda_stream or 1
+            check(_ffi.lib().csic_expand_planar_device(ctx._h, ctypes.byref(p), d_in.data_ptr() + off_in, n,
+                                                            d_out.data_ptr() + 48 + off_out, 1 if to_rgb else 0, stream))
+            torch.cuda.synchronize()
+            got = d_out.cpu().numpy()
+            body = got[48 + off_out:48 + off_out + want.size]
+            assert np.array_equal(body, want), (W, H, ab, f, tile, to_rgb, off_in, off_out, int(np.flatnonzero(body != want)[0]))
+            assert (got[:48 + off_out] == 0xA5).all() and (got[48 + off_out + want.size:] == 0xA5).all(), (W, H, ab, f, tile)
+        cases += 1
+    assert cases > (60 if no_tma else 200)
 
 
 def test_row_segments_and_ring_depths(csic, ctx):

@@ -13,7 +13,8 @@ from bench import load_peak
 peak, _ = load_peak()
 ctx = csic.Context(0)
 for (W, H, n, a, b, f) in ((1920, 1080, 256, 2, 0, 1), (3840, 2160, 64, 2, 2, 2), (1918, 1078, 256, 2, 0, 1), (1366, 768, 512, 2, 0, 1),
-                           (333, 500, 2048, 2, 2, 1), (1000, 1000, 256, 4, 4, 1), (2732, 1536, 128, 2, 0, 2)):
+                           (333, 500, 2048, 2, 2, 1), (1000, 1000, 256, 4, 4, 1), (2732, 1536, 128, 2, 0, 2), (96, 96, 32768, 2, 0, 1),
+                           (32, 32, 262144, 2, 0, 1), (1001, 999, 256, 2, 0, 1)):
     p = csic.make_params(W, H, a, b, 8, 8, 8, f, out_format=4)
     ow, oh, _, fb = csic.out_shape(p)
     rgb = torch.randint(0, 256, (n, H, W, 3), dtype=torch.uint8, device="cuda")
