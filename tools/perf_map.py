@@ -20,10 +20,13 @@ sizes = [(640, 480), (1280, 720), (1366, 768), (1920, 1080), (2560, 1440), (3840
          (1000, 1000), (500, 333), (333, 500), (1080, 1920), (96, 96), (200, 200)]
 orders = sys.argv[1].split(",") if len(sys.argv) > 1 else ["CSQ"]
 pools = [int(v) for v in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["0"])]
+only_fmts = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else None      # e.g. "1" = RGB888 only
 FAM = {1: "generic", 2: "rows", 3: "pool", 4: "flex"}
 worst = []
 for (W, H), f, (fmt, q), order, pool in itertools.product(sizes, (1, 2, 4, 8), ((0, (8, 8, 8)), (3, (8, 8, 8)), (1, (6, 5, 5))), orders, pools):
     if pool and (f == 1 or W % f or H % f):
+        continue
+    if only_fmts is not None and fmt not in only_fmts:
         continue
     p = csic.make_params(W, H, 2, 0, q[0], q[1], q[2], f, tuple(ORD[c] for c in order), pool_mode=pool, out_format=fmt)
     fb = csic.out_shape(p)[3]
