@@ -42,7 +42,7 @@ namespace {
 
 constexpr int kDecConsumers = 256;        // default consumer threads (+ the producer warp)
 constexpr int kDecMaxConsumers = 512;
-constexpr uint32_t kDecDescBytes = 32u;
+constexpr uint32_t kDecDescBytes = 48u;
 
 struct DecPlan {
   const uint8_t* planar;
@@ -64,6 +64,8 @@ struct DecDesc {
   uint32_t y_s;          // shared address of the tile's first Y byte
   uint32_t cb_s, cr_s;   // shared address of sample (0, 0) of the frame's chroma planes (biased: sample (r, c) is at + r * cw + c)
   uint32_t r0, col0;     // row and column of the tile's first pixel
+  uint32_t nrows;        // rows the tile touches
+  uint32_t pad[3];
 };
 static_assert(sizeof(DecDesc) == kDecDescBytes, "kDecDescBytes out of sync");
 
@@ -75,18 +77,29 @@ __device__ __forceinline__ uint32_t lds_un(uint32_t a) {
 
 // ---- consumer side: one tile ------------------------------------------------------------------------------------
 struct DecTile {
-  uint32_t npx, y_s, cb_s, cr_s, r0, col0, out_s;
+  uint32_t npx, y_s, cb_s, cr_s, r0, col0, nrows, out_s;
 };
+// How a thread walks the rows: (row, col) of its first group of `px` pixels relative to a tile start, and the step to
+// its next group.  Computed once per kernel (four divisions), never per tile.
+struct DecWalk {
+  uint32_t row_t, col_t, drow, dcol;
+};
+__device__ __forceinline__ DecWalk make_walk(uint32_t px, uint32_t tid, uint32_t NC, uint32_t Wo) {
+  DecWalk w;
+  w.row_t = (px * tid) / Wo; w.col_t = px * tid - w.row_t * Wo;
+  w.drow = (px * NC) / Wo;   w.dcol = px * NC - w.drow * Wo;
+  return w;
+}
 
 // Sixteen pixels per thread: rows are a multiple of 16 pixels wide and every plane keeps its 16-byte phase, so a thread's
 // Y bytes are one LDS.128, its chroma samples one LDS.128 / .64 / .32 per plane, and its 48 output bytes three STS.128
 // (lane stride 48 bytes: conflict free).  The hold pattern of every granule is a compile-time constant.
 template <int HS, bool VHOLD, bool RGB>
-__device__ __forceinline__ void tile_wide(const DecTile& T, uint32_t Wo, uint32_t cw, uint32_t last_c, uint32_t tid, uint32_t NC) {
+__device__ __forceinline__ void tile_wide(const DecTile& T, const DecWalk& K, uint32_t Wo, uint32_t cw, uint32_t last_c, uint32_t tid,
+                                          uint32_t NC) {
   const uint32_t n16 = T.npx >> 4;
-  const uint32_t row_t = (16u * tid) / Wo, col_t = 16u * tid - row_t * Wo;
-  const uint32_t drow = (16u * NC) / Wo, dcol = 16u * NC - drow * Wo;
-  uint32_t row = T.r0 + row_t, col = T.col0 + col_t;
+  const uint32_t drow = K.drow, dcol = K.dcol;
+  uint32_t row = T.r0 + K.row_t, col = T.col0 + K.col_t;
   if (col >= Wo) { col -= Wo; ++row; }
   for (uint32_t u = tid; u < n16; u += NC) {
     const uint4 yv = lds128(T.y_s + 16u * u);
@@ -190,11 +203,11 @@ __device__ __forceinline__ void granule_over_row_end(const DecTile& T, uint32_t 
 // afterwards, one thread per row end: one warp pays for the slow lookup instead of every warp that meets a row end
 // (1918-pixel rows: every fourth warp; 333-pixel rows: every third).
 template <int HS, bool VHOLD, bool RGB, bool AL4>
-__device__ __forceinline__ void tile_granules(const DecTile& T, uint32_t Wo, uint32_t cw, uint32_t last_c, uint32_t tid, uint32_t NC) {
+__device__ __forceinline__ void tile_granules(const DecTile& T, const DecWalk& K, uint32_t Wo, uint32_t cw, uint32_t last_c, uint32_t tid,
+                                              uint32_t NC) {
   const uint32_t n_gran = (T.npx + 3u) >> 2;
-  const uint32_t row_t = (4u * tid) / Wo, col_t = 4u * tid - row_t * Wo;
-  const uint32_t drow = (4u * NC) / Wo, dcol = 4u * NC - drow * Wo;
-  uint32_t row = T.r0 + row_t, col = T.col0 + col_t;
+  const uint32_t drow = K.drow, dcol = K.dcol;
+  uint32_t row = T.r0 + K.row_t, col = T.col0 + K.col_t;
   if (col >= Wo) { col -= Wo; ++row; }
   for (uint32_t q = tid; q < n_gran; q += NC) {
     if (AL4 || col + 3u < Wo) granule_in_row<HS, VHOLD, RGB, AL4>(T, q, row, col, cw, last_c);
@@ -203,7 +216,7 @@ __device__ __forceinline__ void tile_granules(const DecTile& T, uint32_t Wo, uin
   }
   if (!AL4) {
     // row end number bi sits at tile pixel e = (bi + 1) * Wo - col0; it cuts a granule unless e is a multiple of 4
-    const uint32_t nb = (T.col0 + T.npx - 1u) / Wo + 1u;         // rows the tile touches
+    const uint32_t nb = T.nrows;                                  // rows the tile touches
     for (uint32_t bi = tid; bi < nb; bi += NC) {
       const uint32_t e = (bi + 1u) * Wo - T.col0;
       if (e <= T.npx && (e & 3u) != 0u) {
@@ -257,6 +270,7 @@ __global__ void __launch_bounds__(kDecMaxConsumers + 32) csic_decode_kernel(cons
           d->y_s = slot + ((uint32_t)reinterpret_cast<uintptr_t>(y) & 15u);
           d->r0 = r0;
           d->col0 = col0;
+          d->nrows = r1 - r0 + 1u;
         } else {
           // first and last sample this tile reads: odd (held) lines read sample last_c of the chroma row they share with
           // the line above, which -- when that line is in the tile too -- is read to its end
@@ -280,21 +294,22 @@ __global__ void __launch_bounds__(kDecMaxConsumers + 32) csic_decode_kernel(cons
   // ============================== consumer warps =============================================
   const uint32_t Wo = P.Wo, cw = P.cw, last_c = P.last_c;
   const bool w16 = (Wo & 15u) == 0u, w4 = (Wo & 3u) == 0u;
+  const DecWalk walk16 = make_walk(16u, tid, NC, Wo), walk4 = make_walk(4u, tid, NC, Wo);
   uint32_t s = 0, par = 0;
   for (uint32_t i = 0; i < n_my; ++i) {
     mbar_wait(full_bar + s * 8u, par);
     const DecDesc* d = reinterpret_cast<const DecDesc*>(smem + P.desc_off) + s;
     DecTile T;
-    T.npx = d->npx; T.y_s = d->y_s; T.cb_s = d->cb_s; T.cr_s = d->cr_s; T.r0 = d->r0; T.col0 = d->col0;
+    T.npx = d->npx; T.y_s = d->y_s; T.cb_s = d->cb_s; T.cr_s = d->cr_s; T.r0 = d->r0; T.col0 = d->col0; T.nrows = d->nrows;
     uint8_t* out_g = reinterpret_cast<uint8_t*>(d->out_g);
     const uint32_t galign = (uint32_t)d->out_g & 15u;
     // staging: byte b of the tile at out_s + b, out_s = buffer + (address of the first output byte mod 16, to the word)
     T.out_s = sbase + P.out_off + (i & 1u) * P.out_stride + (galign & 12u);
     // every plane on its 16-byte phase: the 16-pixel path
     const bool wide = w16 && (galign & 12u) == 0u && (T.y_s & 15u) == 0u && ((T.cb_s | T.cr_s) & ((16u >> HS) - 1u)) == 0u;
-    if (wide) tile_wide<HS, VHOLD, RGB>(T, Wo, cw, last_c, tid, NC);
-    else if (w4) tile_granules<HS, VHOLD, RGB, true>(T, Wo, cw, last_c, tid, NC);
-    else tile_granules<HS, VHOLD, RGB, false>(T, Wo, cw, last_c, tid, NC);
+    if (wide) tile_wide<HS, VHOLD, RGB>(T, walk16, Wo, cw, last_c, tid, NC);
+    else if (w4) tile_granules<HS, VHOLD, RGB, true>(T, walk4, Wo, cw, last_c, tid, NC);
+    else tile_granules<HS, VHOLD, RGB, false>(T, walk4, Wo, cw, last_c, tid, NC);
     // inputs consumed: the stage goes back to the producer
     __syncwarp();
     if ((tid & 31u) == 0) mbar_arrive(empty_bar + s * 8u);

@@ -641,6 +641,37 @@ def test_decoder_any_width_and_alignment(csic, ctx, no_tma, monkeypatch):
     assert cases > (60 if no_tma else 200)
 
 
+@pytest.mark.parametrize("W,H,ab", [(1920, 1080, (2, 0)), (1918, 1078, (2, 0)), (333, 500, (2, 2)), (1001, 999, (1, 0))],
+                         ids=["1080p420", "1918x1078", "333x500", "1001x999"])
+def test_decoder_full_size_batches(csic, ctx, W, H, ab):
+    """The decoder at bench size (every CTA walks many tiles, the stage ring wraps many times, frames start at every
+    alignment): 32 frames of random planes against a torch gather on the device (YCC888, all frames) and the oracle's
+    ycbcr2rgb (RGB888, first and last frame)."""
+    import torch
+    p, _ = both_params(csic, W, H, ab[0], ab[1], (8, 8, 8), 1, "CSQ", 0, 0, 4)
+    w, h, _, fb = csic.out_shape(p)
+    cw, chh, ob, orr = csic.planar_shape(p)
+    hf, vs = 4 // ab[0], (2 if ab[1] == 0 else 1)
+    last_c = ((W - 1) // hf * hf) // hf
+    n = 32
+    g = torch.Generator(device="cuda").manual_seed(W + H)
+    planar = torch.randint(0, 256, (n, fb), dtype=torch.uint8, device="cuda", generator=g)
+    rows = torch.arange(h, device="cuda")
+    held = (rows & 1).bool() if vs == 2 else torch.zeros(h, dtype=torch.bool, device="cuda")
+    crow = (rows - held.long()) // vs
+    ccol = (torch.arange(w, device="cuda") // hf)[None, :].expand(h, w).clone()
+    ccol[held] = last_c
+    idx = (crow[:, None] * cw + ccol).reshape(-1)
+    want = torch.stack([planar[:, :w * h], planar[:, ob:ob + cw * chh][:, idx], planar[:, orr:orr + cw * chh][:, idx]], -1)
+    got = ctx.expand_planar_torch(p, planar, to_rgb=False)
+    ctx.synchronize(); torch.cuda.synchronize()
+    assert torch.equal(got.reshape(n, -1, 3), want)
+    rgb = ctx.expand_planar_torch(p, planar, to_rgb=True)
+    ctx.synchronize(); torch.cuda.synchronize()
+    for k in (0, n - 1):
+        assert np.array_equal(rgb[k].cpu().numpy().reshape(-1, 3), oracle.ycbcr2rgb_array(want[k].cpu().numpy()))
+
+
 def test_row_segments_and_ring_depths(csic, ctx):
     """Force rows to be split into several tiles (CSIC_OPT_TILE_BYTES small -> nsplit > 1: held chroma comes from
     TMA-fetched aux windows, per-segment stores) and vary ring depth / block size / CTAs per SM: results never change."""
