@@ -360,9 +360,9 @@ uint32_t env_u32(const char* name, uint32_t dflt) {
 
 }  // namespace
 
-// Returns a cudaError_t as int, or -1 when the configuration is outside this kernel (the LDG decoders run instead):
-// rows narrower than a granule, more than 2^32 pixels per frame or tiles per launch, or chroma rows so wide that a
-// stage does not fit.
+// Returns a cudaError_t as int, or -1 when the configuration is outside this kernel (the LDG decoder runs instead):
+// rows narrower than a granule, 2^30 or more pixels per frame, 2^32 or more tiles per launch, or chroma rows so wide
+// that a stage does not fit.
 int launch_decode_tma(const KPlan& k, const uint8_t* planar, uint8_t* out, int to_rgb, int sm_count, size_t max_smem_optin, void* stream) {
   if (k.Wo < 4 || k.Ho < 1) return -1;
   const uint64_t A = (uint64_t)k.Wo * (uint64_t)k.Ho;

@@ -597,7 +597,9 @@ bool plan_flex_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
         if (c == 0u) break;
         if (r > 1u && tiles_for(r) < (uint64_t)sm_count * 8u) break;        // keep every SM supplied with several tiles
         const double gran = (double)r * gpr;
-        const double score = std::min(busy_cap, c * NW * busy_frac(r)) * gran / (gran + 400.0) * (c >= 3u ? 1.0 : 0.85);
+        // a short last tile per frame recurs with the frame's period under round-robin tile assignment: weigh by its fill
+        const double fill = (double)band_rows / (double)(((band_rows + r - 1u) / r) * r);
+        const double score = std::min(busy_cap, c * NW * busy_frac(r)) * gran / (gran + 400.0) * (c >= 3u ? 1.0 : 0.85) * fill;
         if (score >= best_score * 1.0001) { best_score = score; rows = (int)r; }
       }
     }

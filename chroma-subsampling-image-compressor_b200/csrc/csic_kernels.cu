@@ -541,6 +541,15 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
     if (staged && !planar && k.kformat > KF_RGB888)
       while (rows > 1 && 2u * ((uint32_t)rows * (k.tile_in_bytes + 32u)) + 2u * ((uint32_t)rows * k.tile_out_bytes) + 2048u > 227u * 1024u / 2u - 1024u)
         --rows;
+    // Equal tiles: CTAs take tiles round robin, so a short last tile per frame recurs with the period of the frame
+    // (96 rows as 64 + 32: every other CTA got the 32-row tiles only and the kernel ran at 0.71 of the copy peak
+    // where 64x64 and 128x128 frames reach 0.98 - 1.01).  Even row counts keep a held line and its sample in one tile.
+    if (rows > 1) {
+      const int t = (k.band_rows + rows - 1) / rows;
+      int bal = (k.band_rows + t - 1) / t;
+      if ((k.vf == 2 || planar) && (bal & 1) && bal < rows) ++bal;
+      rows = std::min(rows, bal);
+    }
     if (planar && rows > 1) rows &= ~(k.planar_vs - 1);          // tiles start on a chroma row
     if (rows < 1) rows = 1;
   }
@@ -649,6 +658,10 @@ bool plan_pool_kernel(KPlan& k, int sm_count, size_t max_smem_optin) {
     if (!k.out_dense) rows = 1;                                           // a tile's output must be one contiguous range
     auto tiles_for = [&](int r) { return (uint64_t)k.n_frames * (uint64_t)((k.band_rows + r - 1) / r); };
     while (rows > 1 && tiles_for(rows) < (uint64_t)sm_count * 4u) rows = (rows + 1) / 2;
+    if (rows > 1) {                                                       // equal tiles (see plan_rows_kernel)
+      const int t = (k.band_rows + rows - 1) / rows;
+      rows = std::min(rows, (k.band_rows + t - 1) / t);
+    }
   }
   k.tile_rows = rows;
   k.tiles_per_band = (uint32_t)((k.band_rows + rows - 1) / rows);
