@@ -96,7 +96,8 @@ int flex_set_attributes(size_t max_smem_optin);
 // Implemented once per spatial factor in csic_rows_kernel.cu (explicit specialisations for F = 1, 2, 4, 8).
 template <int F> int launch_rows_factor(const KPlan& k, unsigned grid, void* stream);
 template <int F> int rows_set_attributes_factor(size_t max_smem_optin);
-constexpr int kMaxTileRows = 64;        // rows per tile of the row kernel (small frames: 64 rows x 384 B still make a 24 KB tile)
+constexpr int kMaxTileRows = 64;        // rows per tile of the row kernel (small frames: 64 rows x 384 B still make a 24 KB tile; 256 rows
+                                        // measured worse on 32x32 and 64x64 frames: the producer's per-row work, profiles/r2/rows_tall.txt)
 constexpr uint32_t kTileMetaBytes = 32 + 4 * kMaxTileRows;   // sizeof(TileMeta) in csic_rows_kernel.cu
 constexpr int kPoolMaxRows = 16;        // output rows per tile of the pooling kernel (each carries f input rows)
 constexpr uint32_t kPoolMetaBytes = 32 + 4 * kPoolMaxRows;   // sizeof(PoolMeta) in csic_pool_kernel.cu

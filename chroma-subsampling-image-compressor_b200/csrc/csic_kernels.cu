@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 
 #include "csic_internal.h"
 #include "csic_device_math.cuh"
@@ -524,6 +525,19 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
   k.tile_px = k.Wp / nsplit;
   k.tile_in_bytes = (uint32_t)k.tile_px * ipb * (uint32_t)k.f;    // one row segment
   k.tile_out_bytes = (uint32_t)k.tile_px * opx;
+  // "Tall image" (as in the flex kernel): when every launch row is a whole frame row and frames lie back to back with the
+  // same row stride inside and across frames, on the input AND the output side, the batch IS one image of n_frames * Ho
+  // rows, and a tile may span frames -- 32x32 frames make 64-row tiles of two frames instead of one 3 KB tile per frame
+  // (0.74 -> 0.95 of the copy peak).  The kernel does not change: the only rule that looks at a row index, "odd lines
+  // replay the line above" (f == 1, 4:2:0 / 4:1:0), reads the same parity when frames have an even number of rows.
+  const uint64_t stored_rows = (uint64_t)(uint32_t)k.Ho * (uint32_t)k.row_step;   // input rows from one frame's first row to the next frame's
+  static const bool no_tall = std::getenv("CSIC_ROWS_NO_TALL") != nullptr;        // experiment switch (tools/): never changes results
+  const bool tall = !no_tall && nsplit == 1 && !planar && !k.case_b && k.n_frames > 1 && k.row0 == 0 && k.band_rows == k.Ho &&
+                    k.in_frame_bytes == stored_rows * k.in_row_bytes && k.out_frame_bytes == (uint64_t)(uint32_t)k.Ho * k.out_row_bytes &&
+                    !(k.vf == 2 && k.f == 1 && (k.Ho & 1)) &&
+                    (uint64_t)k.n_frames * (uint32_t)k.Ho < (1ull << 30) && (uint64_t)k.n_frames * (uint32_t)k.H < (1ull << 31);
+  const uint32_t frames = tall ? 1u : k.n_frames;
+  const int band_rows = tall ? (int)(k.n_frames * (uint32_t)k.Ho) : k.band_rows;
   // Rows per tile: whole rows only (so the tile's output is contiguous), as many as fit the budget,
   // but keep at least ~4 tiles per SM so small batches still spread over the chip.
   int rows = 1;
@@ -533,8 +547,8 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
     if ((uint32_t)rows * k.tile_in_bytes < tile_budget * 7u / 10u && (uint32_t)(rows + 1) * k.tile_in_bytes <= tile_max &&
         rows < kMaxTileRows)
       ++rows;
-    rows = std::min(rows, k.band_rows);
-    auto tiles_for = [&](int r) { return (uint64_t)k.n_frames * (uint64_t)((k.band_rows + r - 1) / r); };
+    rows = std::min(rows, band_rows);
+    auto tiles_for = [&](int r) { return (uint64_t)frames * (uint64_t)((band_rows + r - 1) / r); };
     while (rows > 1 && tiles_for(rows) < (uint64_t)sm_count * 4u) rows = (rows + 1) / 2;
     // staged 32-bit slots: a tile's two output buffers are larger than its input stages; keep two CTAs resident
     // (4096-pixel rows: two rows per tile left room for one CTA only -- 0.81 of the copy peak instead of 0.98)
@@ -545,8 +559,8 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
     // (96 rows as 64 + 32: every other CTA got the 32-row tiles only and the kernel ran at 0.71 of the copy peak
     // where 64x64 and 128x128 frames reach 0.98 - 1.01).  Even row counts keep a held line and its sample in one tile.
     if (rows > 1) {
-      const int t = (k.band_rows + rows - 1) / rows;
-      int bal = (k.band_rows + t - 1) / t;
+      const int t = (band_rows + rows - 1) / rows;
+      int bal = (band_rows + t - 1) / t;
       if ((k.vf == 2 || planar) && (bal & 1) && bal < rows) ++bal;
       rows = std::min(rows, bal);
     }
@@ -554,8 +568,8 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
     if (rows < 1) rows = 1;
   }
   k.tile_rows = rows;
-  k.tiles_per_band = (uint32_t)((k.band_rows + rows - 1) / rows);
-  const uint64_t n_tiles = (uint64_t)k.n_frames * (uint64_t)k.tiles_per_band * (uint64_t)nsplit;
+  k.tiles_per_band = (uint32_t)((band_rows + rows - 1) / rows);
+  const uint64_t n_tiles = (uint64_t)frames * (uint64_t)k.tiles_per_band * (uint64_t)nsplit;
   if (n_tiles >= (1ull << 31)) return false;
   k.n_tiles = (uint32_t)n_tiles;
   // Tiny tiles (whole frames of a few KB: a tile never spans two frames): a granule per thread is all there is, so the
@@ -588,6 +602,11 @@ bool plan_rows_kernel(KPlan& k, int sm_count, size_t max_smem_optin, int force_s
   // (PLANAR 1080p: 0.97 of the copy peak with 3 CTAs vs 0.84 with 2; 16-bit bundles: 0.93 with 4).
   k.ctas_per_sm = (int32_t)std::min<uint32_t>(ctas_for(stages), tiny ? 8u : (k.f == 1 ? 4u : 2u));
   k.stages = stages;
+  if (tall) {                                      // nothing can fail from here on: commit the tall-image view of the batch
+    k.in_frame_bytes *= k.n_frames; k.out_frame_bytes *= k.n_frames;
+    k.H *= (int32_t)k.n_frames; k.Ho = band_rows; k.band_rows = band_rows;
+    k.n_frames = 1;
+  }
   k.out_buf_off = (uint32_t)stages * k.stage_stride;
   k.meta_off = up128(k.out_buf_off + 2u * k.out_buf_stride);
   k.bar_off = up128(k.meta_off + (uint32_t)stages * (uint32_t)kTileMetaBytes);
