@@ -659,7 +659,7 @@ bool plan_pool_kernel(KPlan& k, int sm_count, size_t max_smem_optin) {
   const bool staged = k.kformat <= KF_RGB888;
   const uint32_t opx = staged ? 3u : (uint32_t)k.slot_bytes;
   const uint32_t f = (uint32_t)k.f, ipb = (uint32_t)k.in_px_bytes;
-  const uint32_t budget = 24u * 1024u, tile_max = budget + budget / 3;
+  const uint32_t budget = 24u * 1024u, tile_max = budget + budget / 3;   // (48 KB tiles for 8x8 pooling: 1080p +5 %, 4K / 8K -12 %)
   const uint32_t block_row_bytes = (uint32_t)k.Wp * f * f * ipb;          // the f input rows of one output row
   int nsplit = 0;
   for (int n = (int)((block_row_bytes + tile_max - 1) / tile_max); n <= 256; ++n)
@@ -672,6 +672,9 @@ bool plan_pool_kernel(KPlan& k, int sm_count, size_t max_smem_optin) {
   int rows = 1;
   if (nsplit == 1) {
     rows = (int)std::max<uint32_t>(1u, budget / k.tile_in_bytes);
+    // e.g. 2560x1440 2x2 or 640x480 8x8: an output row carries 15 KB of input -- one row leaves the ring too shallow, two
+    // rows (30 KB) are within the slack (the row kernel's rule)
+    if ((uint32_t)rows * k.tile_in_bytes < budget * 7u / 10u && (uint32_t)(rows + 1) * k.tile_in_bytes <= tile_max) ++rows;
     rows = std::min(rows, (int)(2u * (uint32_t)kPoolMaxRows / f));      // held_addr[] holds rows * f/2 entries
     rows = std::min(rows, k.band_rows);
     if (!k.out_dense) rows = 1;                                           // a tile's output must be one contiguous range
