@@ -1,14 +1,17 @@
-// CUDA kernels of the pixel pipeline, written for sm_100a (B200).
-//
-//   csic_rows_kernel<F, FMT>   the hot path.  Persistent CTAs; packed RGB24 row segments are staged into a
-//                              multi-stage shared-memory ring by the TMA engine (cp.async.bulk + mbarrier
-//                              complete_tx), each thread converts granules of 4 output pixels with dp4a,
-//                              resolves chroma sample-and-hold inside the granule (or from one TMA-fetched
-//                              held pixel per row), quantises, packs, and the tile leaves through a
-//                              double-buffered shared-memory staging area with a TMA bulk store.
-//   csic_generic_kernel        one thread per output slot, closed-form gather; any legal parameter set
-//                              (odd sizes, unaligned pointers, AVERAGE extension).  Not a fallback to the CPU:
-//                              it is the same GPU path for shapes the TMA kernel's alignment rules exclude.
+// Planning and dispatch of the pixel pipeline's kernels, written for sm_100a (B200), and the two kernels that are not
+// TMA-staged.  The staged kernels live in their own files:
+//   csic_rows_kernel.cu    the hot path: packed RGB24 row segments through a shared-memory ring filled by the TMA engine
+//                          (cp.async.bulk + mbarrier complete_tx), dp4a colour matrix, chroma hold inside the granule (or
+//                          from one held pixel per row), quantise, pack, TMA bulk store.  Planned here (plan_rows_kernel).
+//   csic_pool_kernel.cu    the AVERAGE extension, same machinery (plan_pool_kernel).
+//   csic_flex_kernel.cu    DECIMATE for any width / pitch / alignment (hull fetch, staged span stores).
+//   csic_decode_kernel.cu  the PLANAR decoder as flat tiles, any width.
+// In this file:
+//   csic_generic_kernel            a warp per output row, closed-form gather; any legal parameter set (odd sizes,
+//                                  unaligned pointers, AVERAGE on dense odd widths, spatial-before-chroma shapes the
+//                                  staged kernels exclude).  Not a fallback to the CPU: the independent second
+//                                  implementation every other kernel is cross-checked against.
+//   csic_expand_planar_any_kernel  LDG decoder for what csic_decode_kernel declines.
 //
 // Semantics (bit-exact with the reference; citations relative to its root, src/main/scala/jpeg/):
 //   forward   RGB2YCbCr.scala:33-35,50-65,74-76 (FLOOR)   RGB2YCbCr.scala:95-121 (TRUNC)
