@@ -610,7 +610,8 @@ def test_decoder_any_width_and_alignment(csic, ctx, no_tma, monkeypatch):
     if no_tma:
         monkeypatch.setenv("CSIC_DEC_NO_TMA", "1")
     rng = np.random.default_rng(11)
-    shapes = [(333, 50), (1366, 25), (1918, 13), (37, 300), (4, 5), (5, 5), (7, 1), (6000, 3), (1920, 20), (31, 31), (64, 64), (9, 2)]
+    shapes = [(333, 50), (1366, 25), (1918, 13), (37, 300), (4, 5), (5, 5), (7, 1), (6000, 3), (1920, 20), (31, 31), (64, 64), (9, 2),
+              (3, 7), (1, 5), (2, 4)]          # rows narrower than a granule: the TMA-staged kernel declines, the LDG kernel runs
     cases = 0
     for (W, H), ab, f, tile in itertools.product(shapes, ALL_AB, (1, 2), (0, 64, 720)):
         if W % f or H % f or (tile and W * H // (f * f) > 40000) or (no_tma and tile):
