@@ -380,13 +380,16 @@ int launch_decode_tma(const KPlan& k, const uint8_t* planar, uint8_t* out, int t
   P.last_c = (uint32_t)((k.last_sample_col / k.f) / k.planar_hs);
   P.to_rgb = to_rgb ? 1u : 0u;
   const uint32_t vs = (uint32_t)k.planar_vs;
-  // B200 sweep (profiles/r2/decode_sweep.txt): 8192-pixel tiles, two stages; a frame of up to 12288 pixels is one tile
-  // (two CTAs per SM still fit)
+  // B200 sweeps (profiles/r2/decode_sweep.txt): 8192-pixel tiles; a frame of up to 12288 pixels is one tile.  A third
+  // stage pays for the RGB reconstruction and on the 4-pixel paths (1080p 4:2:0 to RGB 0.83 -> 0.90, 333-pixel rows to
+  // YCC 0.86 -> 0.93: the consumers otherwise wait for the next tile's loads) where it still leaves two CTAs per SM
+  // their shared memory; where it does not (full-size chroma planes) two stages of 8192 pixels beat three of 4096, and
+  // the 16-pixel path to YCC888 is fastest with two (0.945 vs 0.92).
   const bool w16 = (k.Wo & 15) == 0;
   uint32_t T = env_u32("CSIC_DEC_TILE", A <= 12288u ? (uint32_t)((A + 15u) & ~(uint64_t)15) : 8192u) & ~15u;
   if (T < 64u) T = 64u;
-  const uint32_t S = std::min(8u, std::max(2u, env_u32("CSIC_DEC_STAGES", 2u)));
-  auto layout = [&](uint32_t t) {
+  const uint32_t S_env = env_u32("CSIC_DEC_STAGES", 0u);
+  auto layout = [&](uint32_t t, uint32_t S) {
     P.tile_px = (uint32_t)std::min<uint64_t>(t, (A + 15u) & ~(uint64_t)15);
     const uint32_t nr = std::min<uint32_t>(P.Ho, (P.tile_px + P.Wo - 2u) / P.Wo + 1u);       // rows a tile can touch
     const uint32_t ncr = vs == 2u ? nr / 2u + 1u : nr;
@@ -400,8 +403,10 @@ int launch_decode_tma(const KPlan& k, const uint8_t* planar, uint8_t* out, int t
     P.bar_off = P.desc_off + S * kDecDescBytes;
     return (size_t)P.bar_off + 2u * S * 8u;
   };
-  size_t smem = layout(T);
-  while (smem > max_smem_optin / 2 && T > 256u) { T = (T / 2u) & ~15u; smem = layout(T); }      // keep two CTAs per SM
+  uint32_t S = S_env ? std::min(8u, std::max(2u, S_env)) : ((to_rgb || !w16) ? 3u : 2u);
+  size_t smem = layout(T, S);
+  if (!S_env && S == 3u && smem > max_smem_optin / 2) { S = 2u; smem = layout(T, S); }
+  while (smem > max_smem_optin / 2 && T > 256u) { T = (T / 2u) & ~15u; smem = layout(T, S); }   // keep two CTAs per SM
   if (smem > max_smem_optin) return -1;
   P.tiles_per_frame = (uint32_t)((A + P.tile_px - 1u) / P.tile_px);
   P.tile_px = (uint32_t)((((A + P.tiles_per_frame - 1u) / P.tiles_per_frame) + 15u) & ~(uint64_t)15);   // equal tiles (never larger than planned)
