@@ -343,7 +343,7 @@ __global__ void __maxnreg__(F == 2 ? 56 : 72) csic_pool_kernel(const __grid_cons
     const uint32_t lane = tid - NC;
     if (lane != 0 && !pool_first) return;        // chroma-first orders: one lane feeds the TMA engine
     const uint32_t ipb = (uint32_t)P.in_px_bytes;
-    uint32_t cached_line = 0xFFFFFFFFu, cached_pair = 0;
+    uint32_t cached_line = 0xFFFFFFFFu, cached_frame = 0xFFFFFFFFu, cached_pair = 0;   // the last block this warp reduced
     for (uint32_t i = 0; i < n_my; ++i) {
       const uint32_t s = i % S;
       if (i >= S) mbar_wait(empty_bar + s * 8u, ((i / S) - 1u) & 1u);
@@ -372,7 +372,7 @@ __global__ void __maxnreg__(F == 2 ? 56 : 72) csic_pool_kernel(const __grid_cons
           const uint32_t line = (ro0 + j) / F;
           uint32_t pair = 0;
           if (P.vf == 2 && (line & 1u)) {
-            if (line != cached_line) {
+            if (line != cached_line || k != cached_frame) {        // (a CTA's consecutive tiles are often the same line of DIFFERENT frames)
               const uint8_t* blk = frame + (uint64_t)(((line - 1u) * F + P.caseb_row_add) * F) * P.in_row_bytes + P.caseb_col_bytes;
               int sb = 0, sr = 0;
               for (uint32_t e = lane; e < F * F; e += 32u) {
@@ -387,6 +387,7 @@ __global__ void __maxnreg__(F == 2 ? 56 : 72) csic_pool_kernel(const __grid_cons
               for (int o = 16; o > 0; o >>= 1) { sb += __shfl_xor_sync(0xFFFFFFFFu, sb, o); sr += __shfl_xor_sync(0xFFFFFFFFu, sr, o); }
               cached_pair = 0x80000000u | ((uint32_t)((sb + (F * F) / 2) >> kShift) << 8) | (uint32_t)((sr + (F * F) / 2) >> kShift);
               cached_line = line;
+              cached_frame = k;
             }
             pair = cached_pair;
           }

@@ -544,6 +544,30 @@ def test_multi_on_two_different_devices(csic):
         assert np.array_equal(every.process_host(p, rgb), want)
 
 
+def test_pooling_first_many_small_frames(csic, ctx):
+    """Regression (found by tools/stress.py): with pooling before the chroma stage, the rows of an odd counter line replay
+    the pooled chroma of one block of the line above, which the pooling kernel's producer warp reduces and caches -- the
+    cache was keyed by the line only, and a CTA's consecutive tiles are often the same line of DIFFERENT frames (static
+    round-robin over a batch of small frames).  More tiles than resident CTAs, every frame different."""
+    import torch
+    for (W, H, f, ab, order, n) in ((640, 8, 2, (1, 0), "QSC", 150), (2176, 240, 8, (1, 0), "SQC", 5), (256, 16, 4, (2, 0), "SCQ", 300),
+                                    (128, 8, 2, (2, 0), "SQC", 1200)):
+        p, po = both_params(csic, W, H, ab[0], ab[1], (4, 4, 4), f, order, 0, 1, 1)
+        rgb = np.random.default_rng(W + n).integers(0, 256, size=(n, H, W, 3), dtype=np.uint8)
+        d = torch.from_numpy(rgb).cuda()
+        ctx.set_option(0, 0)
+        out = ctx.process_torch(p, d)
+        ctx.synchronize()
+        assert ctx.last_kernel()[0] == 3, (W, H, f, ab, order)
+        ctx.set_option(0, 1)
+        ref = ctx.process_torch(p, d)
+        ctx.synchronize()
+        ctx.set_option(0, 0)
+        assert torch.equal(out, ref), (W, H, f, ab, order, n, int((out != ref).flatten().nonzero()[0]))
+        pick = [0, n // 2, n - 1]
+        assert np.array_equal(out[pick].cpu().numpy(), oracle.process(po, rgb[pick])), (W, H, f, ab, order)
+
+
 def test_planar_output_and_decoder(csic, ctx):
     """out_format PLANAR (SURVEY 8(f) N3): Y plane + the chroma samples that survive.  Both kernels equal the oracle;
     csic_expand_planar_device replays the planes into exactly the YCC888 / RGB888 stream of the same parameters."""
