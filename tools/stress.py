@@ -2,6 +2,8 @@
 (1) forward: random geometry / mode / order / factor / format / input format / frame count, the automatic kernel choice
     against the gather kernel (family option 1) on the same device buffers, byte for byte;
 (2) decoder: random planes through csic_expand_planar_device against a torch gather.
+(3) host path: csic_process_host (pageable NumPy buffers, random chunk size -> the 3-stream chunk pipeline, re-pitching of
+    odd widths, every-f-th-row shipping) and csic_process_host_band on a random band, against the device path.
 Prints the kernel families seen and the first mismatch, exits non-zero on one."""
 import os
 import sys
@@ -99,3 +101,44 @@ while time.time() - t0 < secs:
         print("DECODER MISMATCH", dict(W=W, H=H, a=a, b=b, f=f, n=n))
         sys.exit(1)
 print(f"decoder: {n_dec} cases: all equal to the torch gather")
+
+t0 = time.time()
+n_host = 0
+while time.time() - t0 < secs / 2:
+    f = int(rng.choice([1, 2, 2, 4, 8]))
+    W, H = (16 * f * int(rng.integers(1, 60)), f * int(rng.integers(1, 120))) if rng.integers(0, 2) else (int(rng.integers(1, 900)), int(rng.integers(1, 200)))
+    a, b = AB[rng.integers(0, len(AB))]
+    order = ORDERS[rng.integers(0, 6)]
+    fmt = int(rng.choice([0, 1, 2, 3]))
+    q = [(8, 8, 8), (6, 5, 5), (3, 3, 2)][rng.integers(0, 3)]
+    inf = int(rng.choice([0, 0, 2]))
+    pool = int(rng.choice([0, 0, 1]))
+    n = int(rng.choice([1, 3, 17, 64]))
+    if n * W * H > 3e7:
+        n = 2
+    try:
+        p = csic.make_params(W, H, a, b, q[0], q[1], q[2], f, tuple(ORD[c] for c in order), 0, pool, fmt, inf)
+    except csic.IllegalArgumentException:
+        continue
+    ch = 3 if inf == 0 else 4
+    rgb = rng.integers(0, 256, size=(n, H, W, ch), dtype=np.uint8)
+    ctx.set_option(0, 0)
+    ref = ctx.process_torch(p, torch.from_numpy(rgb).cuda()).cpu().numpy()
+    ctx.synchronize()
+    ctx.set_option(1, int(rng.choice([0, 1 << 16, 1 << 20, 3 << 20, 16 << 20])))     # host chunk bytes
+    got = ctx.process_host(p, rgb)
+    ok = np.array_equal(got.reshape(ref.shape), ref)
+    oh = csic.out_shape(p)[1]
+    if ok and oh >= 2:
+        r0 = int(rng.integers(0, oh - 1)); nr = int(rng.integers(1, oh - r0 + 1))
+        band = np.full_like(got, 0xA5)
+        ctx.process_host_band(p, rgb, band, r0, nr)
+        rb = csic.out_shape(p)[2]
+        bv, rv = band.reshape(n, oh, rb), ref.reshape(n, oh, rb)
+        ok = np.array_equal(bv[:, r0:r0 + nr], rv[:, r0:r0 + nr]) and bool((bv[:, :r0] == 0xA5).all()) and bool((bv[:, r0 + nr:] == 0xA5).all())
+    ctx.set_option(1, 0)
+    n_host += 1
+    if not ok:
+        print("HOST PATH MISMATCH", dict(W=W, H=H, a=a, b=b, order=order, fmt=fmt, q=q, inf=inf, pool=pool, n=n, f=f))
+        sys.exit(1)
+print(f"host path: {n_host} cases (chunked pipeline + a random band each): all equal to the device path")
