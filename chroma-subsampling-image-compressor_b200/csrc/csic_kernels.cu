@@ -656,7 +656,8 @@ bool plan_pool_kernel(KPlan& k, int sm_count, size_t max_smem_optin) {
   if (k.band_rows <= 0 || k.n_frames == 0) return false;
   // 4x4 / 8x8 pooling keeps more live registers per thread: 6 consumer warps leave room for one more CTA per SM
   // (B200 sweep, profiles/r1/sweep_pool_v8.txt: 8K 4x4 0.97 of the copy peak vs 0.92 with 8 warps)
-  if (k.block_threads <= 0) k.block_threads = k.f >= 4 ? 192 : kDefaultBlockThreads;
+  const bool auto_threads = k.block_threads <= 0;
+  if (auto_threads) k.block_threads = k.f >= 4 ? 192 : kDefaultBlockThreads;
   if (k.block_threads > kMaxConsumerThreads) return false;
 
   const bool staged = k.kformat <= KF_RGB888;
@@ -693,6 +694,12 @@ bool plan_pool_kernel(KPlan& k, int sm_count, size_t max_smem_optin) {
   const uint64_t n_tiles = (uint64_t)k.n_frames * (uint64_t)k.tiles_per_band * (uint64_t)nsplit;
   if (n_tiles >= (1ull << 31)) return false;
   k.n_tiles = (uint32_t)n_tiles;
+  // 8x8 pooling is bound by the integer pipes, and a granule is 256 input pixels: a 15 KB tile has twenty of them, four
+  // threads each -- 80 busy threads of 192 (1080p: 240 output pixels per row, split three ways).  Size the CTA to the
+  // tile and let more of them be resident instead (1080p 8x8: 0.69-0.81 -> 0.78-0.91 of the copy peak).
+  const uint32_t units = (uint32_t)rows * ((uint32_t)k.tile_px >> 2) * 4u;
+  const bool small_cta = auto_threads && k.f == 8 && 2u * units <= (uint32_t)k.block_threads;   // (tiles that fill 2/3 of the CTA or more: 3-4 % slower this way)
+  if (small_cta) k.block_threads = (int32_t)std::max(64u, (units + 31u) & ~31u);
   auto up128 = [](uint32_t v) { return (v + 127u) & ~127u; };
   k.stage_stride = up128((uint32_t)rows * k.tile_in_bytes + (uint32_t)kPoolMaxRows * 32u);
   k.out_buf_stride = staged ? (uint32_t)(kMaxConsumerThreads / 32) * 384u / 2u : 0u;   // 2 x stride = one 384-byte slot per warp
@@ -701,7 +708,9 @@ bool plan_pool_kernel(KPlan& k, int sm_count, size_t max_smem_optin) {
   if (need > max_smem_optin) return false;
   // pooling converts every input pixel: the kernel is issue-bound, so take all the warps that fit (measured:
   // 4 CTAs 0.79 of the copy peak on the 4K 2x2 case vs 0.73 with 2)
-  k.ctas_per_sm = (int32_t)std::max<uint32_t>(1u, std::min<uint32_t>(4u, 227u * 1024u / (need + 1024u)));
+  const uint32_t threads = (uint32_t)k.block_threads + 32u;
+  const uint32_t by_regs = 65536u / ((k.f == 2 ? 56u : 72u) * threads);     // __maxnreg__ of csic_pool_kernel
+  k.ctas_per_sm = (int32_t)std::max<uint32_t>(1u, std::min<uint32_t>(std::min<uint32_t>(small_cta ? 8u : 4u, by_regs), 227u * 1024u / (need + 1024u)));
   k.out_buf_off = 2u * k.stage_stride;
   k.meta_off = up128(k.out_buf_off + 2u * k.out_buf_stride);
   k.bar_off = up128(k.meta_off + 2u * kPoolMetaBytes);
