@@ -1,6 +1,7 @@
 """One-off randomised stress on the GPU (run under gpurun; not part of the test suite): for ~N seconds each,
-(1) forward: random geometry / mode / order / factor / format / input format / frame count, the automatic kernel choice
-    against the gather kernel (family option 1) on the same device buffers, byte for byte;
+(1) forward: random geometry / mode / order / factor / format / input format / frame count (a third of the cases: a random
+    row band into a canary-filled buffer), the automatic kernel choice against the gather kernel (family option 1) on the
+    same device buffers, byte for byte;
 (2) decoder: random planes through csic_expand_planar_device against a torch gather.
 (3) host path: csic_process_host (pageable NumPy buffers, random chunk size -> the 3-stream chunk pipeline, re-pitching of
     odd widths, every-f-th-row shipping) and csic_process_host_band on a random band, against the device path.
@@ -49,19 +50,24 @@ while time.time() - t0 < secs:
         continue
     ch = 3 if inf == 0 else 4
     rgb = torch.randint(0, 256, (n, H, W, ch), dtype=torch.uint8, device="cuda")
+    oh, fb = csic.out_shape(p)[1], csic.out_shape(p)[3]
+    band = (None, None)
+    if fmt != 4 and oh >= 2 and rng.integers(0, 3) == 0:        # a third of the cases: a random row band into a canary-filled buffer
+        r0 = int(rng.integers(0, oh - 1))
+        band = (r0, int(rng.integers(1, oh - r0 + 1)))
     ctx.set_option(0, 0)
-    out = ctx.process_torch(p, rgb)
+    out = ctx.process_torch(p, rgb, torch.full((n, fb), 0xA5, dtype=torch.uint8, device="cuda"), *band)
     ctx.synchronize()
     fam = ctx.last_kernel()[0]
     seen[fam] = seen.get(fam, 0) + 1
     ctx.set_option(0, 1)
-    ref = ctx.process_torch(p, rgb)
+    ref = ctx.process_torch(p, rgb, torch.full((n, fb), 0xA5, dtype=torch.uint8, device="cuda"), *band)
     ctx.synchronize()
     ctx.set_option(0, 0)
     n_fwd += 1
     if not torch.equal(out, ref):
         bad = int((out != ref).flatten().nonzero()[0])
-        print("FORWARD MISMATCH", dict(W=W, H=H, a=a, b=b, order=order, fmt=fmt, q=q, inf=inf, pool=pool, rm=rm, n=n, f=f, fam=fam, first=bad))
+        print("FORWARD MISMATCH", dict(W=W, H=H, a=a, b=b, order=order, fmt=fmt, q=q, inf=inf, pool=pool, rm=rm, n=n, f=f, fam=fam, band=band, first=bad))
         sys.exit(1)
 print(f"forward: {n_fwd} cases, kernel families {seen}: all equal to the gather kernel", flush=True)
 
